@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- edges aggregated / second of the message-passing aggregation path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2]
+                    [--graph rmat|uniform] [--dtype f32|bf16]
+
+Workload (BASELINE.json north_star "Target"): GCN aggregation forward + backward on a synthetic
+ogbn-products-shaped graph (C3: N=2,449,029 nodes, E=123,718,280 edges incl. self loops, K=100 fp32),
+through the public operator `gspmm(edge_index, weight, x, 'sum')` + autograd backward.  One step = one
+forward SpMM + one backward SpMM (transposed CSR) = 2*E edge aggregations.  The CSR is cached per graph
+(its build time is reported separately as csr_build_ms).  `--workload c2` is BASELINE.json configs[1]
+(N=1M, E=50M, K=128).
+
+N > 1: the graph fits one GPU, so ranks run independent replicas on independent graphs (weak scaling, no
+data-path collective).  Timing: CUDA events, barrier + synchronize on both sides, max
+over ranks.  Inputs (x 0.98 GB, CSR 1.5 GB) are far larger than the 126 MB L2, so no explicit flush.
+
+--impl reference: the reference's own CPU operators (oracle/_ref = /root/reference/gammagl/mpops/torch_ext
+compiled unmodified; else the C oracle port) on a bounded sample of the same workload, host cores only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, E incl. self loops, K, description)
+    'c3': (2449029, 123718280, 100, 'GCN aggregation fwd+bwd, synthetic ogbn-products shape (2.45M nodes / 123.7M edges / feat 100)'),
+    'c2': (1000000, 50000000, 128, 'gspmm fwd+bwd microbench, synthetic 1M nodes / 50M edges / feat 128'),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    ap.add_argument('--graph', default='rmat', choices=['rmat', 'uniform'])
+    ap.add_argument('--dtype', default='f32', choices=['f32', 'bf16'])
+    ap.add_argument('--scale', type=float, default=1.0, help='shrink N and E (debug only; reported in config)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+# synthetic graphs (generated on the device they are used on; seeded)
+# ----------------------------------------------------------------------------------------------------
+def gen_graph(torch, N, E, kind, seed, device):
+    """edge_index[2,E] int64, unsorted: E-N random edges (uniform or RMAT 0.57/0.19/0.19/0.05 with random
+    relabelling) + N self loops (as examples/gcn/gcn_trainer.py:58 appends), then a random edge permutation."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    Er = max(E - N, 0)
+    if kind == 'uniform':
+        src = torch.randint(0, N, (Er,), generator=g, device=device)
+        dst = torch.randint(0, N, (Er,), generator=g, device=device)
+    else:
+        bits = max(1, (N - 1).bit_length())
+        src = torch.zeros(Er, dtype=torch.int64, device=device)
+        dst = torch.zeros(Er, dtype=torch.int64, device=device)
+        a, b, c = 0.57, 0.19, 0.19
+        for _ in range(bits):
+            u = torch.rand(Er, generator=g, device=device)
+            sbit = (u >= a + b).to(torch.int64)                       # quadrants c, d -> source bit 1
+            dbit = (((u >= a) & (u < a + b)) | (u >= a + b + c)).to(torch.int64)   # quadrants b, d -> dest bit 1
+            src = (src << 1) | sbit
+            dst = (dst << 1) | dbit
+            del u, sbit, dbit
+        src %= N
+        dst %= N
+        relabel = torch.randperm(N, generator=g, device=device)
+        src = relabel[src]
+        dst = relabel[dst]
+        del relabel
+    loops = torch.arange(N, device=device)
+    src = torch.cat([src, loops])[:E]
+    dst = torch.cat([dst, loops])[:E]
+    perm = torch.randperm(src.numel(), generator=g, device=device)
+    ei = torch.stack([src[perm], dst[perm]])
+    del src, dst, perm
+    return ei
+
+
+def gcn_norm(torch, ei, N):
+    """calc_gcn_norm (gammagl/utils/norm.py:5-30): w = deg^-1/2[src] * deg^-1/2[dst], deg = in-degree by src."""
+    deg = torch.bincount(ei[0], minlength=N).to(torch.float32)
+    dinv = deg.pow(-0.5)
+    dinv[torch.isinf(dinv)] = 0
+    return (dinv[ei[0]] * dinv[ei[1]]).contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle sampler running during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.idx = str(gpu_index)
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [s.strip() for s in line.split(',')]
+            if len(f) >= 9 and f[0] == self.idx:
+                self.rows.append(f)
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[1])) for r in self.rows if r[1].replace('.', '').isdigit())
+        mx = [int(float(r[2])) for r in self.rows if r[2].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx[0] if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU legs (the only places that execute oracle/)
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_leg(N, E, K, steps, warmup, graph_kind):
+    """Time the reference CPU gspmm forward+backward on a bounded sample of the workload (same average degree,
+    same K): E_cpu edges.  Returns dict(value edges/s, cores, kind, sample, ms_per_step)."""
+    import torch
+    from oracle.build_ref import load_ref
+    E_cpu = int(min(E, 4_000_000))
+    N_cpu = max(2, int(round(N * (E_cpu / E))))
+    ei = gen_graph(torch, N_cpu, E_cpu, 'uniform' if graph_kind == 'uniform' else 'rmat', 1234, 'cpu')
+    w = gcn_norm(torch, ei, N_cpu)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N_cpu, K, generator=g)
+    gout = torch.randn(N_cpu, K, generator=g)
+    ref = None
+    try:
+        ref = load_ref()
+    except Exception:
+        ref = None
+    if ref is not None:
+        kind = 'reference'
+
+        def step():
+            xx = x.clone().requires_grad_(True)
+            ref.c_spmm_sum(ei, w, xx).backward(gout)
+    else:
+        kind = 'port'
+        from oracle import oracle as O
+        ein, wn, xn, gn = ei.numpy(), w.numpy(), x.numpy(), gout.numpy()
+
+        def step():
+            O.spmm_fwd('sum', ein, wn, xn)
+            O.spmm_bwd('sum', ein, wn, gn)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {'value': 2 * E_cpu / dt, 'unit': 'edges/s', 'cores': 1, 'kind': kind, 'ms_per_step': dt * 1e3,
+            'host_threads_available': os.cpu_count(), 'torch_threads': torch.get_num_threads(),
+            'sample': 'c_spmm_sum fwd+bwd on %d nodes / %d edges (same avg degree and K=%d as the workload), '
+                      '%d timed reps; edge loops are single-threaded in the reference build (setup.py:50 never '
+                      'enables OpenMP)' % (N_cpu, E_cpu, K, steps)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    N, E, K, desc = WORKLOADS[args.workload]
+    N, E = int(N * args.scale), int(E * args.scale)
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    r = cpu_reference_leg(N, E, K, steps, warm, args.graph)
+    line = {
+        'impl': 'reference', 'metric': 'edges aggregated/sec (SpMM+scatter fwd+bwd)', 'value': r['value'], 'unit': 'edges/s',
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': desc, 'graph': args.graph, 'N': N, 'E': E, 'K': K, 'note': 'CPU, bounded sample per step'},
+        'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+        'e2e': {'value': r['value'], 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# the B200 arm
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl b200 needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    from gammagl_b200 import _lib, mpops
+    from gammagl_b200.csr import graph_of
+    lib = _lib.load()
+
+    N, E, K, desc = WORKLOADS[args.workload]
+    N, E = int(N * args.scale), int(E * args.scale)
+    dtype = torch.float32 if args.dtype == 'f32' else torch.bfloat16
+    esz = 4 if args.dtype == 'f32' else 2
+
+    ei = gen_graph(torch, N, E, args.graph, 1000 + rank, dev)
+    w = gcn_norm(torch, ei, N)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    x = torch.randn(N, K, generator=g, device=dev).to(dtype).requires_grad_(True)
+    gout = torch.randn(N, K, generator=g, device=dev).to(dtype)
+
+    # CSR ingest (once per graph; reported separately)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    gr = graph_of(ei, N)
+    _ = gr.fwd, gr.bwd
+    torch.cuda.synchronize()
+    csr_ms = (time.perf_counter() - t0) * 1e3
+    max_in = int(gr.fwd.degrees().max())
+    max_out = int(gr.bwd.degrees().max())
+
+    def step():
+        x.grad = None
+        out = mpops.gspmm(ei, w, x, 'sum')
+        out.backward(gout)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.15)
+    mpops.PROFILE = []
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    prof, mpops.PROFILE = mpops.PROFILE, None
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * 2 * E / (ms_max * 1e-3)
+
+    # per-launch duration of the dominant kernel group (forward SpMM and backward SpMM are the same kernel)
+    kern_ms = [a.elapsed_time(b) for (_, a, b) in prof]
+    kavg = sum(kern_ms) / max(1, len(kern_ms))
+    alg_bytes = E * (K * esz + 4 + 4) + N * (K * esz + 4)
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (kavg * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'kernel': 'spmm_rows_kernel<float,4,32,1,false> (+chunks/finalize for rows > 1024 edges)',
+                'algorithmic_bytes_per_launch': alg_bytes, 'avg_launch_ms': kavg, 'launches_timed': len(kern_ms),
+                'peak_source': peak_src,
+                'formula': 'E*(K*s+4+4) + N*(K*s+4) per SpMM pass (SURVEY.md 8d gather model)'}
+
+    # end-to-end through the public operator with HOST buffers (pinned): x and grad_out go up, out and grad_x come back
+    e2e = None
+    if not args.no_e2e:
+        xh = x.detach().cpu().pin_memory()
+        gh = gout.cpu().pin_memory()
+        oh = torch.empty_like(xh).pin_memory()
+        gxh = torch.empty_like(xh).pin_memory()
+        xd = torch.empty_like(x.detach()).requires_grad_(True)
+        gd = torch.empty_like(gout)
+
+        def e2e_step():
+            with torch.no_grad():
+                xd.copy_(xh, non_blocking=True)
+                gd.copy_(gh, non_blocking=True)
+            xd.grad = None
+            out = mpops.gspmm(ei, w, xd, 'sum')
+            out.backward(gd)
+            oh.copy_(out.detach(), non_blocking=True)
+            gxh.copy_(xd.grad, non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            e2e_step()
+        b.record()
+        barrier()
+        ems = a.elapsed_time(b) / args.steps
+        t = torch.tensor([ems], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nb = N * K * esz
+        e2e = {'value': world * 2 * E / (float(t.item()) * 1e-3), 'unit': 'edges/s', 'ms_per_step': float(t.item()),
+               'h2d_bytes_per_step': 2 * nb, 'd2h_bytes_per_step': 2 * nb,
+               'note': 'x and grad_out copied from pinned host memory, out and grad_x copied back, every step; '
+                       'graph (CSR) resident'}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_leg(N, E, K, 2, 1, args.graph)
+        cpu = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+
+    if rank == 0:
+        line = {
+            'metric': 'edges aggregated/sec (SpMM+scatter fwd+bwd)', 'value': value, 'unit': 'edges/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_max, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': desc, 'graph': args.graph, 'N': N, 'E': E, 'K': K, 'scale': args.scale,
+                       'op': "gspmm(edge_index, gcn_norm_weight, x, 'sum') forward + autograd backward (2 SpMM passes/step)",
+                       'l2': 'inputs (x %.2f GB, CSR %.2f GB) exceed the 126 MB L2; no explicit flush' % (N * K * esz / 1e9, E * 12 / 1e9),
+                       'parallelism': 'replicas x%d (independent graphs, no collective)' % world,
+                       'max_in_degree': max_in, 'max_out_degree': max_out, 'csr_build_ms': csr_ms},
+            'roofline': roofline, 'e2e': e2e, 'cpu_baseline': cpu, 'gpu_launches': int(launches), 'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,77 @@
+"""ctypes binding of libgglb200.so (the C ABI declared in include/gglb200.h).
+
+There is no CPU or pure-torch fallback anywhere in this package: if the shared library cannot be
+built/loaded, importing the operators raises.  (The reference swallows extension errors and silently
+falls back to scatter ops, /root/reference/gammagl/mpops/torch.py:83-86 -- deliberately not mirrored.)
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+GGL_SUM, GGL_MEAN, GGL_MAX = 0, 1, 2
+GGL_F32, GGL_BF16, GGL_F16, GGL_F64, GGL_I8, GGL_I16, GGL_I32, GGL_I64, GGL_U8 = range(9)
+LONG_ROW = 1024
+
+_c = ctypes
+_vp, _i64, _i32, _sz, _int = _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_size_t, _c.c_int
+
+# name -> (restype, argtypes); must list every symbol declared in include/gglb200.h
+SIGNATURES = {
+    'gglb200_abi_version': (_int, []),
+    'gglb200_last_error': (_c.c_char_p, []),
+    'gglb200_launch_count': (_i64, []),
+    'gglb200_csr_build_workspace_bytes': (_sz, [_i64, _i64]),
+    'gglb200_csr_plan_ints': (_sz, [_i64]),
+    'gglb200_csr_build': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gglb200_permute_rows': (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    'gglb200_spmm_workspace_bytes': (_sz, [_i64, _i64, _int]),
+    'gglb200_spmm_csr': (_int, [_int, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int,
+                                _vp, _sz, _vp]),
+    'gglb200_segment_gather_bwd': (_int, [_int, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
+    'gglb200_segment_max_bwd': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    'gglb200_scale_rows_by_count': (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    'gglb200_spmm_max_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    'gglb200_bspmm_bwd_w': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
+    'gglb200_edge_softmax_fwd': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
+    'gglb200_edge_softmax_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
+}
+
+_lib = None
+
+
+class GglError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Build (if stale and nvcc is available) and dlopen libgglb200.so.  Raises on any failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    if not os.path.exists(path):
+        raise GglError('libgglb200.so is missing (%s) and could not be built' % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gglb200_abi_version() != 1:
+        raise GglError('libgglb200.so ABI version mismatch')
+    _lib = lib
+    return lib
+
+
+def check(status, what=''):
+    if status != 0:
+        msg = load().gglb200_last_error().decode('utf-8', 'replace')
+        raise GglError('libgglb200 %s failed (status %d): %s' % (what, status, msg))
+
+
+def launch_count():
+    return int(load().gglb200_launch_count())

@@ -1,0 +1,151 @@
+"""CSR structures the kernels consume, built on the GPU from the int64 COO the reference API delivers.
+
+Host-side mirror of the bookkeeping in /root/reference/gammagl/sparse/storage.py:22-297 (row / rowptr /
+col / csr2csc caches), reduced to what the aggregation path needs:
+
+  Csr        rows over `key` (stable by original edge id), `col` gathered from `other`, `perm` = edge ids
+  Graph      the forward CSR (rows = destination i, col = source j) and, lazily, the transposed CSR
+             (rows = source, col = destination) of one edge_index[2,E]
+  caches     an LRU keyed on the *identity of the memory* (storage pointer, offset, shape, strides,
+             tensor._version) that also holds a strong reference to the keyed tensor, so the address
+             cannot be recycled for different contents while the entry lives.
+"""
+import collections
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError('%s must be a torch.Tensor (got %s)' % (name, type(t).__name__))
+    if not t.is_cuda:
+        raise _lib.GglError('%s is on %s: gammagl_b200 is a CUDA-only backend (no CPU fallback)' % (name, t.device))
+
+
+class Csr:
+    """rowptr[N+1] i32, col[E] i32 (or None), perm[E] i32, plan (long-row work list), has_long."""
+    __slots__ = ('rowptr', 'col', 'perm', 'plan', 'n_rows', 'E', 'has_long', 'device', '_ws')
+
+    def workspace(self, K, reduce):
+        """Partials buffer for split rows; empty when the graph has no row longer than LONG_ROW."""
+        if not self.has_long:
+            return None, 0
+        need = _lib.load().gglb200_spmm_workspace_bytes(self.E, K, reduce)
+        ws = self._ws.get('buf')
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws['buf'] = ws
+        return ws, ws.numel()
+
+    def degrees(self):
+        return self.rowptr[1:] - self.rowptr[:-1]
+
+
+def build_csr(key, other, n_rows):
+    """key/other: int64 [E] CUDA tensors (other may be None) -> Csr.  One host sync (long-row count)."""
+    lib = _lib.load()
+    require_cuda(key, 'index')
+    if key.dtype != torch.int64:
+        key = key.to(torch.int64)
+    key = key.contiguous()
+    if other is not None:
+        if other.dtype != torch.int64:
+            other = other.to(torch.int64)
+        other = other.contiguous()
+    E = key.numel()
+    dev = key.device
+    with torch.cuda.device(dev):
+        c = Csr()
+        c.n_rows, c.E, c.device, c._ws = int(n_rows), int(E), dev, {}
+        c.rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+        c.perm = torch.empty(E, dtype=torch.int32, device=dev)
+        c.col = torch.empty(E, dtype=torch.int32, device=dev) if other is not None else None
+        c.plan = torch.empty(lib.gglb200_csr_plan_ints(E), dtype=torch.int32, device=dev)
+        ws_bytes = lib.gglb200_csr_build_workspace_bytes(E, n_rows)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gglb200_csr_build(_ptr(key), _ptr(other), E, n_rows, _ptr(c.rowptr), _ptr(c.col), _ptr(c.perm),
+                                         _ptr(c.plan), _ptr(ws), ws_bytes, _stream(dev)), 'csr_build')
+        c.has_long = bool(int(c.plan[1].item()) > 0) if E > _lib.LONG_ROW else False
+    return c
+
+
+class Graph:
+    """Forward (by destination) and transposed (by source) CSR of one edge_index[2,E]."""
+
+    def __init__(self, edge_index, num_nodes):
+        require_cuda(edge_index, 'edge_index')
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise ValueError('edge_index must have shape [2, E], got %s' % (tuple(edge_index.shape),))
+        self.edge_index = edge_index
+        self.N = int(num_nodes)
+        self.E = int(edge_index.shape[1])
+        self._fwd = None
+        self._bwd = None
+
+    @property
+    def fwd(self):  # rows = dst (edge_index[1]), col = src
+        if self._fwd is None:
+            self._fwd = build_csr(self.edge_index[1], self.edge_index[0], self.N)
+        return self._fwd
+
+    @property
+    def bwd(self):  # rows = src, col = dst
+        if self._bwd is None:
+            self._bwd = build_csr(self.edge_index[0], self.edge_index[1], self.N)
+        return self._bwd
+
+
+class _Lru:
+    def __init__(self, capacity):
+        self.capacity = capacity
+        self.d = collections.OrderedDict()
+
+    @staticmethod
+    def key_of(t, extra):
+        return (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape), tuple(t.stride()), t._version,
+                t.dtype, t.device.index, extra)
+
+    def get(self, t, extra, make):
+        k = self.key_of(t, extra)
+        hit = self.d.get(k)
+        if hit is not None:
+            self.d.move_to_end(k)
+            return hit[1]
+        val = make()
+        self.d[k] = (t, val)  # strong ref to `t` pins its storage => the key cannot alias new contents
+        while len(self.d) > self.capacity:
+            self.d.popitem(last=False)
+        return val
+
+    def clear(self):
+        self.d.clear()
+
+
+_graphs = _Lru(4)
+_segments = _Lru(8)
+
+
+def graph_of(edge_index, num_nodes):
+    """Cached Graph for an edge_index tensor (built on first use; CSR build cost is paid once per graph)."""
+    return _graphs.get(edge_index, int(num_nodes), lambda: Graph(edge_index, num_nodes))
+
+
+def segment_csr_of(segment_ids, num_segments):
+    """Cached CSR over segment ids (col is None: the kernels gather through perm)."""
+    return _segments.get(segment_ids, int(num_segments), lambda: build_csr(segment_ids, None, num_segments))
+
+
+def clear_caches():
+    _graphs.clear()
+    _segments.clear()

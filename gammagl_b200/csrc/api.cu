@@ -1,0 +1,77 @@
+// api.cu -- C ABI entry points of libgglb200.so: argument validation, dtype dispatch, error strings.
+#include "spmm_impl.cuh"
+
+namespace ggl {
+
+std::atomic<int64_t> g_launches{0};
+
+char* error_buffer() {
+  static thread_local char buf[512] = "";
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int64_t plan_max_chunks_host(int64_t E) {
+  int64_t max_long = E / GGLB200_LONG_ROW + 1;
+  return E / GGLB200_LONG_CHUNK + max_long + 1;
+}
+
+}  // namespace ggl
+
+using namespace ggl;
+
+extern "C" int gglb200_abi_version(void) { return GGLB200_ABI_VERSION; }
+extern "C" const char* gglb200_last_error(void) { return error_buffer(); }
+extern "C" int64_t gglb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" size_t gglb200_spmm_workspace_bytes(int64_t E, int64_t K, int reduce) {
+  if (E <= GGLB200_LONG_ROW || K <= 0) return 0;
+  size_t n = (size_t)plan_max_chunks_host(E) * (size_t)K;
+  return n * 8 + (reduce == GGL_MAX ? n * 4 : 0) + 256;
+}
+
+extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
+                                const float* w, const int32_t* wperm, int32_t heads, const void* x, void* out,
+                                int64_t* arg, int64_t arg_empty, int64_t n_rows, int64_t E, int64_t K, int dtype,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  GGL_REQUIRE(reduce == GGL_SUM || reduce == GGL_MEAN || reduce == GGL_MAX, GGL_EINVAL, "spmm: unknown reduce %d", reduce);
+  GGL_REQUIRE(n_rows >= 0 && E >= 0 && K >= 0, GGL_EINVAL, "spmm: negative size");
+  GGL_REQUIRE(n_rows < INT32_MAX && E < INT32_MAX, GGL_ERANGE, "spmm: n_rows/E exceed int32");
+  if (n_rows == 0 || K == 0) return GGL_OK;
+  GGL_REQUIRE(rowptr && out, GGL_EINVAL, "spmm: rowptr/out must not be NULL");
+  GGL_REQUIRE(E == 0 || (col && x), GGL_EINVAL, "spmm: col/x must not be NULL when E > 0");
+  GGL_REQUIRE(heads >= 1, GGL_EINVAL, "spmm: heads must be >= 1");
+  GGL_REQUIRE(heads == 1 || (w != nullptr && K % heads == 0), GGL_EINVAL, "spmm: heads=%d needs w and K %% heads == 0 (K=%lld)", heads, (long long)K);
+  GGL_REQUIRE(arg == nullptr || reduce == GGL_MAX, GGL_EINVAL, "spmm: arg is only produced by GGL_MAX");
+
+  SpmmArgs p;
+  p.reduce = reduce; p.rowptr = rowptr; p.col = col; p.plan = plan; p.w = w; p.wperm = wperm; p.heads = heads;
+  p.x = x; p.out = out; p.arg = arg; p.arg_empty = arg_empty; p.n_rows = n_rows; p.E = E; p.K = K;
+  p.part_val = nullptr; p.part_arg = nullptr; p.stream = (cudaStream_t)stream;
+  if (plan != nullptr && E > GGLB200_LONG_ROW) {
+    size_t need = gglb200_spmm_workspace_bytes(E, K, reduce);
+    GGL_REQUIRE(workspace != nullptr && workspace_bytes >= need, GGL_EWORKSPACE, "spmm: workspace %zu < %zu", workspace_bytes, need);
+    size_t n = (size_t)plan_max_chunks_host(E) * (size_t)K;
+    p.part_val = workspace;
+    p.part_arg = (int32_t*)((char*)workspace + n * 8);
+  }
+  switch (dtype) {
+    case GGL_F32: return launch_spmm<float>(p);
+    case GGL_BF16: return launch_spmm<__nv_bfloat16>(p);
+    case GGL_F16: return launch_spmm<__half>(p);
+    case GGL_F64: return launch_spmm<double>(p);
+    case GGL_I8: return launch_spmm<int8_t>(p);
+    case GGL_U8: return launch_spmm<uint8_t>(p);
+    case GGL_I16: return launch_spmm<int16_t>(p);
+    case GGL_I32: return launch_spmm<int32_t>(p);
+    case GGL_I64: return launch_spmm<int64_t>(p);
+    default: return set_error(GGL_EUNSUPPORTED, "spmm: unknown dtype %d", dtype);
+  }
+}

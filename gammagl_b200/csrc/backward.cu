@@ -1,0 +1,220 @@
+// backward.cu -- backward helpers that are not an SpMM on the transposed CSR.
+//
+//   segment_gather_bwd   SegmentSum::backward  (src/segment_sum.cpp:43-54):  gx[e] = g[ids[e]]
+//                        SegmentMean::backward (src/segment_mean.cpp:44-63): gx[e] = g[ids[e]] / bincount(ids)[ids[e]]
+//   segment_max_bwd      SegmentMax::backward  (src/segment_max.cpp:48-61):  gx[arg[r,k],k] = g[r,k]
+//   scale_rows_by_count  first factor of spmm_mean_cpu_backward (cpu/spmm_mean_cpu.cpp:96-98): g[d,k] / indeg[d]
+//   spmm_max_bwd         spmm_max_cpu_backward (cpu/spmm_max_cpu.cpp:84-96) on the transposed CSR
+// (paths relative to /root/reference/gammagl/mpops/torch_ext)
+#include "common.cuh"
+
+namespace ggl {
+
+static int grid_for(int64_t n, int block = 256) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)kSMs * 32;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// Row gather, dtype-agnostic: rows are moved as W-byte words.  One warp per edge row, lanes over words.
+template <typename W>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const W* __restrict__ g, const int64_t* __restrict__ ids,
+                                                          W* __restrict__ gx, int64_t E, int32_t words) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < E; e += warps) {
+    const int64_t r = __ldg(ids + e);
+    const W* src = g + r * words;
+    W* dst = gx + e * words;
+    for (int32_t k = lane; k < words; k += 32) __stcs(dst + k, __ldg(src + k));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_mean_kernel(const T* __restrict__ g, const int64_t* __restrict__ ids,
+                                                               const int32_t* __restrict__ rowptr, T* __restrict__ gx,
+                                                               int64_t E, int32_t K) {
+  using acc_t = typename Elem<T>::acc_t;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < E; e += warps) {
+    const int64_t r = __ldg(ids + e);
+    const acc_t cnt = (acc_t)(__ldg(rowptr + r + 1) - __ldg(rowptr + r));
+    const T* src = g + r * K;
+    T* dst = gx + e * K;
+    for (int32_t k = lane; k < K; k += 32) dst[k] = Elem<T>::from_acc(Elem<T>::to_acc(__ldg(src + k)) / cnt);
+  }
+}
+template <> __global__ void gather_rows_mean_kernel<__nv_bfloat16>(const __nv_bfloat16* __restrict__ g, const int64_t* __restrict__ ids,
+                                                                   const int32_t* __restrict__ rowptr, __nv_bfloat16* __restrict__ gx,
+                                                                   int64_t E, int32_t K) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < E; e += warps) {
+    const int64_t r = ids[e];
+    const float cnt = (float)(rowptr[r + 1] - rowptr[r]);
+    for (int32_t k = lane; k < K; k += 32) gx[e * K + k] = __float2bfloat16_rn(__bfloat162float(g[r * K + k]) / cnt);
+  }
+}
+template <> __global__ void gather_rows_mean_kernel<__half>(const __half* __restrict__ g, const int64_t* __restrict__ ids,
+                                                            const int32_t* __restrict__ rowptr, __half* __restrict__ gx,
+                                                            int64_t E, int32_t K) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < E; e += warps) {
+    const int64_t r = ids[e];
+    const float cnt = (float)(rowptr[r + 1] - rowptr[r]);
+    for (int32_t k = lane; k < K; k += 32) gx[e * K + k] = __float2half_rn(__half2float(g[r * K + k]) / cnt);
+  }
+}
+
+template <typename W>
+__global__ void __launch_bounds__(256) scatter_arg_kernel(const W* __restrict__ g, const int64_t* __restrict__ arg,
+                                                          const int32_t* __restrict__ rowptr, W* __restrict__ gx,
+                                                          int64_t n_rows, int64_t E, int32_t K) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps) {
+    if (__ldg(rowptr + r + 1) == __ldg(rowptr + r)) continue;  // empty segment: constant output, zero gradient
+    for (int32_t k = lane; k < K; k += 32) {
+      const int64_t e = __ldg(arg + r * K + k);
+      if (e >= 0 && e < E) gx[e * K + k] = __ldg(g + r * K + k);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_rows_kernel(const float* __restrict__ g, const int32_t* __restrict__ rowptr,
+                                                         float* __restrict__ out, int64_t n_rows, int32_t K) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps) {
+    const int32_t cnt = __ldg(rowptr + r + 1) - __ldg(rowptr + r);
+    const float c = (float)cnt;
+    for (int32_t k = lane; k < K; k += 32) {
+      float v = __ldg(g + r * K + k);
+      out[r * K + k] = cnt > 0 ? __fdiv_rn(v, c) : v;
+    }
+  }
+}
+
+// rows = source nodes; sequential over the row's edges (ascending original edge id) like the reference loop
+__global__ void __launch_bounds__(256) spmm_max_bwd_kernel(const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
+                                                           const float* __restrict__ w, const int32_t* __restrict__ wperm,
+                                                           const float* __restrict__ g, const int64_t* __restrict__ argsrc,
+                                                           float* __restrict__ gx, int64_t n_rows, int32_t K) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_rows; s += warps) {
+    const int32_t b = __ldg(rowptr_t + s), e = __ldg(rowptr_t + s + 1);
+    for (int32_t k0 = 0; k0 < K; k0 += 32) {
+      const int32_t k = k0 + lane;
+      float acc = 0.f;
+      for (int32_t i = b; i < e; ++i) {
+        const int64_t d = __ldg(col_t + i);
+        const float wi = w ? __ldg(w + (wperm ? __ldg(wperm + i) : i)) : 1.f;
+        if (k < K && __ldg(argsrc + d * K + k) == s) acc = __fadd_rn(acc, __fmul_rn(wi, __ldg(g + d * K + k)));
+      }
+      if (k < K) gx[s * K + k] = acc;
+    }
+  }
+}
+
+static int elem_bytes(int dtype) {
+  switch (dtype) {
+    case GGL_F32: case GGL_I32: return 4;
+    case GGL_BF16: case GGL_F16: case GGL_I16: return 2;
+    case GGL_F64: case GGL_I64: return 8;
+    case GGL_I8: case GGL_U8: return 1;
+    default: return 0;
+  }
+}
+
+}  // namespace ggl
+
+using namespace ggl;
+
+extern "C" int gglb200_segment_gather_bwd(int reduce, const void* g, const int64_t* ids, const int32_t* rowptr, void* gx,
+                                          int64_t E, int64_t K, int dtype, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(reduce == GGL_SUM || reduce == GGL_MEAN, GGL_EINVAL, "segment_gather_bwd: reduce must be SUM or MEAN");
+  GGL_REQUIRE(E >= 0 && K >= 0, GGL_EINVAL, "segment_gather_bwd: negative size");
+  const int eb = elem_bytes(dtype);
+  GGL_REQUIRE(eb > 0, GGL_EUNSUPPORTED, "segment_gather_bwd: unknown dtype %d", dtype);
+  if (E == 0 || K == 0) return GGL_OK;
+  GGL_REQUIRE(g && ids && gx, GGL_EINVAL, "segment_gather_bwd: NULL pointer");
+  GGL_REQUIRE(K < INT32_MAX / 8, GGL_ERANGE, "segment_gather_bwd: K too large");
+  const int grid = grid_for(E * 32);
+  if (reduce == GGL_SUM) {
+    const int64_t rb = K * eb;
+    const uintptr_t al = (uintptr_t)g | (uintptr_t)gx;
+    if (rb % 16 == 0 && al % 16 == 0)
+      gather_rows_kernel<uint4><<<grid, 256, 0, stream>>>((const uint4*)g, ids, (uint4*)gx, E, (int32_t)(rb / 16));
+    else if (rb % 8 == 0 && al % 8 == 0)
+      gather_rows_kernel<uint2><<<grid, 256, 0, stream>>>((const uint2*)g, ids, (uint2*)gx, E, (int32_t)(rb / 8));
+    else if (rb % 4 == 0 && al % 4 == 0)
+      gather_rows_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t*)g, ids, (uint32_t*)gx, E, (int32_t)(rb / 4));
+    else if (rb % 2 == 0 && al % 2 == 0)
+      gather_rows_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)g, ids, (uint16_t*)gx, E, (int32_t)(rb / 2));
+    else
+      gather_rows_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)g, ids, (uint8_t*)gx, E, (int32_t)rb);
+    GGL_LAUNCHED("gather_rows");
+    return GGL_OK;
+  }
+  GGL_REQUIRE(rowptr, GGL_EINVAL, "segment_gather_bwd: MEAN needs rowptr");
+  switch (dtype) {
+    case GGL_F32: gather_rows_mean_kernel<float><<<grid, 256, 0, stream>>>((const float*)g, ids, rowptr, (float*)gx, E, (int32_t)K); break;
+    case GGL_F64: gather_rows_mean_kernel<double><<<grid, 256, 0, stream>>>((const double*)g, ids, rowptr, (double*)gx, E, (int32_t)K); break;
+    case GGL_BF16: gather_rows_mean_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)g, ids, rowptr, (__nv_bfloat16*)gx, E, (int32_t)K); break;
+    case GGL_F16: gather_rows_mean_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)g, ids, rowptr, (__half*)gx, E, (int32_t)K); break;
+    default: return set_error(GGL_EUNSUPPORTED, "segment_gather_bwd: MEAN backward needs a floating dtype (got %d)", dtype);
+  }
+  GGL_LAUNCHED("gather_rows_mean");
+  return GGL_OK;
+}
+
+extern "C" int gglb200_segment_max_bwd(const void* g, const int64_t* arg, const int32_t* rowptr, void* gx, int64_t E,
+                                       int64_t n_rows, int64_t K, int dtype, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(E >= 0 && K >= 0 && n_rows >= 0, GGL_EINVAL, "segment_max_bwd: negative size");
+  const int eb = elem_bytes(dtype);
+  GGL_REQUIRE(eb > 0, GGL_EUNSUPPORTED, "segment_max_bwd: unknown dtype %d", dtype);
+  if (E == 0 || K == 0) return GGL_OK;
+  GGL_REQUIRE(gx, GGL_EINVAL, "segment_max_bwd: gx is NULL");
+  GGL_CUDA(cudaMemsetAsync(gx, 0, (size_t)E * (size_t)K * eb, stream));
+  if (n_rows == 0) return GGL_OK;
+  GGL_REQUIRE(g && arg && rowptr, GGL_EINVAL, "segment_max_bwd: NULL pointer");
+  const int grid = grid_for(n_rows * 32);
+  switch (eb) {
+    case 1: scatter_arg_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)g, arg, rowptr, (uint8_t*)gx, n_rows, E, (int32_t)K); break;
+    case 2: scatter_arg_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)g, arg, rowptr, (uint16_t*)gx, n_rows, E, (int32_t)K); break;
+    case 4: scatter_arg_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t*)g, arg, rowptr, (uint32_t*)gx, n_rows, E, (int32_t)K); break;
+    default: scatter_arg_kernel<uint64_t><<<grid, 256, 0, stream>>>((const uint64_t*)g, arg, rowptr, (uint64_t*)gx, n_rows, E, (int32_t)K); break;
+  }
+  GGL_LAUNCHED("scatter_arg");
+  return GGL_OK;
+}
+
+extern "C" int gglb200_scale_rows_by_count(const float* g, const int32_t* rowptr, float* out, int64_t n_rows, int64_t K,
+                                           void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(n_rows >= 0 && K >= 0, GGL_EINVAL, "scale_rows: negative size");
+  if (n_rows == 0 || K == 0) return GGL_OK;
+  GGL_REQUIRE(g && rowptr && out, GGL_EINVAL, "scale_rows: NULL pointer");
+  scale_rows_kernel<<<grid_for(n_rows * 32), 256, 0, stream>>>(g, rowptr, out, n_rows, (int32_t)K);
+  GGL_LAUNCHED("scale_rows");
+  return GGL_OK;
+}
+
+extern "C" int gglb200_spmm_max_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* w, const int32_t* wperm,
+                                    const float* g, const int64_t* argsrc, float* gx, int64_t n_rows, int64_t K,
+                                    void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(n_rows >= 0 && K >= 0, GGL_EINVAL, "spmm_max_bwd: negative size");
+  if (n_rows == 0 || K == 0) return GGL_OK;
+  GGL_REQUIRE(rowptr_t && g && argsrc && gx, GGL_EINVAL, "spmm_max_bwd: NULL pointer");
+  spmm_max_bwd_kernel<<<grid_for(n_rows * 32), 256, 0, stream>>>(rowptr_t, col_t, w, wperm, g, argsrc, gx, n_rows, (int32_t)K);
+  GGL_LAUNCHED("spmm_max_bwd");
+  return GGL_OK;
+}

@@ -1,0 +1,367 @@
+"""gammagl_b200.mpops -- host-side mirror of `gammagl.mpops` (PyTorch backend) on the B200 kernels.
+
+Same names, argument meaning and return values as /root/reference/gammagl/mpops/torch.py:
+    unsorted_segment_sum / mean / max     (torch.py:43-202)
+    segment_sum / mean / max              (torch.py:209-299; aliases, sortedness is not exploited there either)
+    gspmm(index, weight, x, reduce)       (torch.py:302-351)
+    bspmm(index, weight, x, reduce)       (torch.py:354-365)
+and the seven extension symbols the reference binds from `_torch_ext` (torch.py:4,
+torch_ext/src/operators.cpp:51-59):
+    c_segment_sum / c_segment_mean / c_segment_max / c_spmm_sum / c_spmm_mean / c_spmm_max / c_bspmm_sum
+
+Differences, all deliberate (DESIGN.md "Boundary"):
+  * CUDA tensors only; any failure raises (the reference catches everything and falls back, torch.py:83-86).
+  * empty segments of *_max hold lowest() like the compiled reference extension
+    (cpu/segment_max_cpu.cpp:40), not 0 like the pure-torch fallback (torch.py:40).
+  * the gradient of an empty max-segment is dropped instead of leaking into edge row N
+    (src/segment_max.cpp:55-59 scatters the sentinel N).
+  * gspmm / bspmm additionally accept bf16 / f16 x (fp32 accumulate); the reference is fp32-only.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .csr import _ptr, _stream, graph_of, require_cuda, segment_csr_of
+
+use_ext = True  # mirrors the module flag of the reference (torch.py:2-7); always the native path here
+PROFILE = None  # bench.py sets this to a list: spmm_csr then appends (n_rows, start_event, end_event) per launch
+
+_DTYPES = {
+    torch.float32: _lib.GGL_F32, torch.bfloat16: _lib.GGL_BF16, torch.float16: _lib.GGL_F16,
+    torch.float64: _lib.GGL_F64, torch.int8: _lib.GGL_I8, torch.int16: _lib.GGL_I16,
+    torch.int32: _lib.GGL_I32, torch.int64: _lib.GGL_I64, torch.uint8: _lib.GGL_U8,
+}
+_REDUCE = {'sum': _lib.GGL_SUM, 'mean': _lib.GGL_MEAN, 'max': _lib.GGL_MAX}
+
+
+def _dtype_code(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise _lib.GglError('unsupported dtype %s' % t.dtype)
+
+
+def spmm_csr(csr, col, x2d, reduce, w=None, wperm=None, heads=1, want_arg=False, arg_empty=0, n_rows=None):
+    """Launch the aggregation kernel family on a Csr.  x2d: [n_src, K] contiguous.  Returns (out, arg)."""
+    lib = _lib.load()
+    n_rows = csr.n_rows if n_rows is None else n_rows
+    K = x2d.shape[1]
+    dev = x2d.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n_rows, K), dtype=x2d.dtype, device=dev)
+        arg = torch.empty((n_rows, K), dtype=torch.int64, device=dev) if want_arg else None
+        ws, ws_bytes = csr.workspace(K, reduce)
+        if PROFILE is not None:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        _lib.check(lib.gglb200_spmm_csr(reduce, _ptr(csr.rowptr), _ptr(col), _ptr(csr.plan) if csr.has_long else None,
+                                        _ptr(w), _ptr(wperm), heads, _ptr(x2d), _ptr(out), _ptr(arg), arg_empty,
+                                        n_rows, csr.E, K, _dtype_code(x2d), _ptr(ws), ws_bytes, _stream(dev)),
+                   'spmm_csr')
+        if PROFILE is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            PROFILE.append((n_rows, ev0, ev1))
+    return out, arg
+
+
+# ------------------------------------------------------------------------------------------------
+# segment ops
+# ------------------------------------------------------------------------------------------------
+def _check_segment_args(x, index, N):
+    require_cuda(x, 'x')
+    require_cuda(index, 'segment_ids')
+    if index.dim() != 1:
+        raise IndexError('index dimension should be 1, but got %d' % index.dim())      # segment_sum_cpu.cpp:15-16
+    if x.shape[0] != index.shape[0]:
+        raise IndexError('fisrt dimension of x and index should be same')              # segment_sum_cpu.cpp:17-19
+    if int(N) < 0:
+        raise ValueError('num_segments must be >= 0')
+
+
+class _SegmentReduce(torch.autograd.Function):
+    """SegmentSum / SegmentMean / SegmentMax (torch_ext/src/segment_{sum,mean,max}.cpp)."""
+
+    @staticmethod
+    def forward(ctx, x, index, N, reduce):
+        _check_segment_args(x, index, N)
+        N = int(N)
+        x = x.contiguous()
+        out_shape = (N,) + tuple(x.shape[1:])
+        ctx.x_shape = tuple(x.shape)
+        ctx.reduce = reduce
+        ctx.N = N
+        if x.numel() == 0 or N == 0:                                                  # segment_sum_cpu.cpp:28-30
+            ctx.empty = True
+            return torch.zeros(out_shape, dtype=x.dtype, device=x.device)
+        ctx.empty = False
+        E = x.shape[0]
+        csr = segment_csr_of(index, N)
+        x2d = x.view(E, -1)
+        out, arg = spmm_csr(csr, csr.perm, x2d, reduce, want_arg=(reduce == _lib.GGL_MAX), arg_empty=N)
+        ctx.csr = csr
+        ctx.index = index if index.dtype == torch.int64 and index.is_contiguous() else index.to(torch.int64).contiguous()
+        ctx.arg = arg
+        return out.view(out_shape)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if ctx.empty:
+            return torch.zeros(ctx.x_shape, dtype=grad_out.dtype, device=grad_out.device), None, None, None
+        lib = _lib.load()
+        g = grad_out.contiguous()
+        E = ctx.x_shape[0]
+        K = g.numel() // max(ctx.N, 1)
+        dev = g.device
+        with torch.cuda.device(dev):
+            gx = torch.empty(ctx.x_shape, dtype=g.dtype, device=dev)
+            if ctx.reduce == _lib.GGL_MAX:
+                _lib.check(lib.gglb200_segment_max_bwd(_ptr(g), _ptr(ctx.arg), _ptr(ctx.csr.rowptr), _ptr(gx), E, ctx.N, K,
+                                                       _dtype_code(g), _stream(dev)), 'segment_max_bwd')
+            else:
+                _lib.check(lib.gglb200_segment_gather_bwd(ctx.reduce, _ptr(g), _ptr(ctx.index), _ptr(ctx.csr.rowptr),
+                                                          _ptr(gx), E, K, _dtype_code(g), _stream(dev)),
+                           'segment_gather_bwd')
+        return gx, None, None, None
+
+
+def c_segment_sum(x, index, N):
+    return _SegmentReduce.apply(x, index, N, _lib.GGL_SUM)
+
+
+def c_segment_mean(x, index, N):
+    return _SegmentReduce.apply(x, index, N, _lib.GGL_MEAN)
+
+
+def c_segment_max(x, index, N):
+    return _SegmentReduce.apply(x, index, N, _lib.GGL_MAX)
+
+
+def _num_segments(segment_ids, num_segments):
+    if num_segments is None:
+        num_segments = int(segment_ids.max().item()) + 1                              # torch.py:74-75 (host sync)
+    return num_segments
+
+
+def unsorted_segment_sum(x, segment_ids, num_segments=None):
+    assert x.shape[0] == segment_ids.shape[0], "the length of segment_ids should be equal to data.shape[0]."
+    return c_segment_sum(x, segment_ids, _num_segments(segment_ids, num_segments))
+
+
+def unsorted_segment_mean(x, segment_ids, num_segments=None):
+    assert x.shape[0] == segment_ids.shape[0], "the length of segment_ids should be equal to data.shape[0]."
+    return c_segment_mean(x, segment_ids, _num_segments(segment_ids, num_segments))
+
+
+def unsorted_segment_max(x, segment_ids, num_segments=None):
+    assert x.shape[0] == segment_ids.shape[0], "the length of segment_ids should be equal to data.shape[0]."
+    return c_segment_max(x, segment_ids, _num_segments(segment_ids, num_segments))
+
+
+segment_sum = unsorted_segment_sum        # torch.py:209-237
+segment_mean = unsorted_segment_mean      # torch.py:240-268
+segment_max = unsorted_segment_max        # torch.py:271-299
+
+
+# ------------------------------------------------------------------------------------------------
+# gspmm / bspmm
+# ------------------------------------------------------------------------------------------------
+def _check_spmm_args(index, weight, x):
+    require_cuda(x, 'x')
+    require_cuda(index, 'index')
+    require_cuda(weight, 'weight')
+    if not (x.device == index.device == weight.device):
+        raise _lib.GglError('Tensor device inconsistent error.')                       # src/gspmm.cpp:46
+    if index.dim() != 2 or index.shape[0] != 2:
+        raise ValueError('index must have shape [2, num_edges]')
+    if weight.dtype != torch.float32:
+        raise _lib.GglError('edge weight must be float32 (got %s)' % weight.dtype)     # spmm_sum_cpu.cpp:21-24
+    if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        raise _lib.GglError('x must be float32 / bfloat16 / float16 (got %s)' % x.dtype)
+
+
+class _SpMM(torch.autograd.Function):
+    """SpMMSum / SpMMMean / SpMMMax (torch_ext/src/gspmm.cpp:26-202).  No gradient for `weight`
+    (mark_non_differentiable, src/gspmm.cpp:30,79)."""
+
+    @staticmethod
+    def forward(ctx, index, weight, x, reduce):
+        _check_spmm_args(index, weight, x)
+        E = index.shape[1]
+        if weight.numel() != E:
+            raise ValueError('weight must have num_edges elements')
+        x = x.contiguous()
+        weight = weight.contiguous().view(-1)
+        N = x.shape[0]
+        g = graph_of(index, N)
+        x2d = x.view(N, -1)
+        out, arg = spmm_csr(g.fwd, g.fwd.col, x2d, reduce, w=weight, wperm=g.fwd.perm,
+                            want_arg=(reduce == _lib.GGL_MAX), arg_empty=0)
+        ctx.graph, ctx.reduce, ctx.x_shape = g, reduce, tuple(x.shape)
+        ctx.save_for_backward(weight)
+        ctx.arg = arg
+        return out.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        (weight,) = ctx.saved_tensors
+        g = ctx.graph
+        grad = grad_out.contiguous().view(g.N, -1)
+        K = grad.shape[1]
+        dev = grad.device
+        with torch.cuda.device(dev):
+            if ctx.reduce == _lib.GGL_MAX:
+                if grad.dtype != torch.float32:
+                    raise _lib.GglError('gspmm(max) backward is float32 only')
+                gx = torch.empty_like(grad)
+                _lib.check(lib.gglb200_spmm_max_bwd(_ptr(g.bwd.rowptr), _ptr(g.bwd.col), _ptr(weight), _ptr(g.bwd.perm),
+                                                    _ptr(grad), _ptr(ctx.arg), _ptr(gx), g.N, K, _stream(dev)),
+                           'spmm_max_bwd')
+            else:
+                if ctx.reduce == _lib.GGL_MEAN:
+                    if grad.dtype != torch.float32:
+                        raise _lib.GglError('gspmm(mean) backward is float32 only')
+                    scaled = torch.empty_like(grad)
+                    _lib.check(lib.gglb200_scale_rows_by_count(_ptr(grad), _ptr(g.fwd.rowptr), _ptr(scaled), g.N, K,
+                                                               _stream(dev)), 'scale_rows_by_count')
+                    grad = scaled
+                gx, _ = spmm_csr(g.bwd, g.bwd.col, grad, _lib.GGL_SUM, w=weight, wperm=g.bwd.perm)
+        return None, None, gx.view(ctx.x_shape), None
+
+
+class _BSpMM(torch.autograd.Function):
+    """BSpMMSum (torch_ext/src/gspmm.cpp:204-260): grad for x AND for the per-head weight."""
+
+    @staticmethod
+    def forward(ctx, index, weight, x):
+        _check_spmm_args(index, weight, x)
+        if x.dim() != 3:
+            raise ValueError('bspmm expects x of shape [N, heads, channels]')
+        E = index.shape[1]
+        N, H, C = x.shape
+        if weight.dim() == 1 and H == 1:
+            weight = weight.view(E, 1)
+        if tuple(weight.shape) != (E, H):
+            raise ValueError('bspmm expects weight of shape [num_edges, heads]')
+        x = x.contiguous()
+        weight = weight.contiguous()
+        g = graph_of(index, N)
+        out, _ = spmm_csr(g.fwd, g.fwd.col, x.view(N, H * C), _lib.GGL_SUM, w=weight, wperm=g.fwd.perm, heads=H)
+        ctx.graph = g
+        ctx.save_for_backward(weight, x)
+        return out.view(N, H, C)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        weight, x = ctx.saved_tensors
+        g = ctx.graph
+        N, H, C = x.shape
+        grad = grad_out.contiguous().view(N, H * C)
+        dev = grad.device
+        gx = gw = None
+        with torch.cuda.device(dev):
+            if ctx.needs_input_grad[2]:
+                gx, _ = spmm_csr(g.bwd, g.bwd.col, grad, _lib.GGL_SUM, w=weight, wperm=g.bwd.perm, heads=H)
+                gx = gx.view(N, H, C)
+            if ctx.needs_input_grad[1]:
+                if x.dtype != torch.float32 or grad.dtype != torch.float32:
+                    raise _lib.GglError('bspmm weight gradient is float32 only')
+                gw = torch.empty((g.E, H), dtype=torch.float32, device=dev)
+                _lib.check(lib.gglb200_bspmm_bwd_w(_ptr(g.fwd.rowptr), _ptr(g.fwd.col), _ptr(g.fwd.perm), _ptr(x), _ptr(grad),
+                                                   _ptr(gw), N, g.E, H, C, _stream(dev)), 'bspmm_bwd_w')
+        return None, gw, gx
+
+
+def c_spmm_sum(index, weight, x):
+    return _SpMM.apply(index, weight, x, _lib.GGL_SUM)
+
+
+def c_spmm_mean(index, weight, x):
+    return _SpMM.apply(index, weight, x, _lib.GGL_MEAN)
+
+
+def c_spmm_max(index, weight, x):
+    return _SpMM.apply(index, weight, x, _lib.GGL_MAX)
+
+
+def c_bspmm_sum(index, weight, x):
+    return _BSpMM.apply(index, weight, x)
+
+
+def gspmm(index, weight=None, x=None, reduce='sum'):
+    """Generalized SpMM: out[dst] (+|mean|max)= weight[e] * x[src]  (torch.py:302-351)."""
+    if weight is None:
+        weight = torch.ones(size=(index.shape[1],), dtype=torch.float32, device=index.device)
+    if reduce == 'sum':
+        return c_spmm_sum(index, weight, x)
+    elif reduce == 'mean':
+        return c_spmm_mean(index, weight, x)
+    elif reduce == 'max':
+        return c_spmm_max(index, weight, x)
+    raise Exception("Unsupported reduce type, please choose from ['sum', 'mean', 'max'].")
+
+
+def bspmm(index, weight=None, x=None, reduce='sum'):
+    """Per-head weighted SpMM used by GAT: out[dst,h,:] += weight[e,h] * x[src,h,:]  (torch.py:354-365)."""
+    if weight is None:
+        weight = torch.ones(size=(index.shape[1], x.shape[1]), dtype=torch.float32, device=index.device)
+    if reduce == 'sum':
+        return c_bspmm_sum(index, weight, x)
+    raise Exception("Unsupported reduce type, please choose from ['sum'].")
+
+
+# ------------------------------------------------------------------------------------------------
+# fused edge softmax (gammagl/utils/softmax.py:10-36)
+# ------------------------------------------------------------------------------------------------
+class _EdgeSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, segment_ids, num_segments):
+        lib = _lib.load()
+        require_cuda(data, 'data')
+        require_cuda(segment_ids, 'segment_ids')
+        if data.dtype != torch.float32:
+            raise _lib.GglError('segment_softmax is float32 only')
+        E = data.shape[0]
+        data = data.contiguous()
+        H = data.numel() // max(E, 1)
+        alpha = torch.empty_like(data)
+        ctx.shape = tuple(data.shape)
+        if E == 0:
+            ctx.csr = None
+            return alpha
+        csr = segment_csr_of(segment_ids, int(num_segments))
+        dev = data.device
+        with torch.cuda.device(dev):
+            _lib.check(lib.gglb200_edge_softmax_fwd(_ptr(csr.rowptr), _ptr(csr.perm), _ptr(data), _ptr(alpha), csr.n_rows, E, H,
+                                                    _stream(dev)), 'edge_softmax_fwd')
+        ctx.csr, ctx.H = csr, H
+        ctx.save_for_backward(alpha)
+        return alpha
+
+    @staticmethod
+    def backward(ctx, galpha):
+        if ctx.csr is None:
+            return torch.zeros(ctx.shape, dtype=galpha.dtype, device=galpha.device), None, None
+        lib = _lib.load()
+        (alpha,) = ctx.saved_tensors
+        galpha = galpha.contiguous()
+        gl = torch.empty_like(alpha)
+        dev = alpha.device
+        csr = ctx.csr
+        with torch.cuda.device(dev):
+            _lib.check(lib.gglb200_edge_softmax_bwd(_ptr(csr.rowptr), _ptr(csr.perm), _ptr(alpha), _ptr(galpha), _ptr(gl),
+                                                    csr.n_rows, csr.E, ctx.H, _stream(dev)), 'edge_softmax_bwd')
+        return gl, None, None
+
+
+def segment_softmax(data, segment_ids, num_segments):
+    """softmax of `data` [E, ...] over the edges that share a segment id (gammagl/utils/softmax.py:10-36)."""
+    return _EdgeSoftmax.apply(data, segment_ids, num_segments)
+
+
+__all__ = ['use_ext', 'unsorted_segment_sum', 'unsorted_segment_mean', 'unsorted_segment_max', 'segment_sum',
+           'segment_mean', 'segment_max', 'gspmm', 'bspmm', 'c_segment_sum', 'c_segment_mean', 'c_segment_max',
+           'c_spmm_sum', 'c_spmm_mean', 'c_spmm_max', 'c_bspmm_sum', 'segment_softmax']

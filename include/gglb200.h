@@ -1,0 +1,187 @@
+/*
+ * gglb200.h -- C ABI of libgglb200.so: the B200 (sm_100a) message-passing aggregation backend that
+ * replaces GammaGL's `gammagl.mpops` torch_ext operators.
+ *
+ * Reference interface replaced (all under /root/reference/gammagl/mpops/torch_ext unless stated):
+ *   c_segment_sum / c_segment_mean / c_segment_max   src/operators.cpp:14-27  (SegmentSum/Mean/Max, src/segment_*.cpp)
+ *   c_spmm_sum / c_spmm_mean / c_spmm_max            src/operators.cpp:29-43  (SpMMSum/Mean/Max,  src/gspmm.cpp:26-202)
+ *   c_bspmm_sum                                      src/operators.cpp:45-49  (BSpMMSum,          src/gspmm.cpp:204-260)
+ *   ind2ptr / ptr2ind (COO <-> CSR)                  gammagl/ops/sparse/cpu/convert.cpp:58-128
+ *   segment_softmax                                  gammagl/utils/softmax.py:29-35
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.  Every data pointer is a DEVICE pointer
+ *     owned by the caller (inputs, outputs and workspace); the library never allocates, never
+ *     synchronises with the host and never reads device data on the host.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All work is enqueued on it.
+ *   - Return value: 0 = GGL_OK, negative = GGL_E* below, positive = a cudaError_t.  A human readable
+ *     message for the last failure on the calling thread is available from gglb200_last_error().
+ *   - Re-entrant from any thread; no global mutable state besides the thread-local error string.
+ *   - Indices inside the library are int32 (CSR) -- E and N must be < 2^31.  The int64 COO form the
+ *     reference API delivers (edge_index[2,E], segment_ids[E]) is consumed by gglb200_csr_build.
+ *   - Edge order: every CSR built here is a STABLE sort of the COO input, so edges inside a row keep
+ *     ascending original edge id.  Kernels reduce a row sequentially in that order, which is the
+ *     order of the reference's serial CPU loops (cpu/spmm_sum_cpu.cpp:27-39) -- fp32 sums are
+ *     therefore bit-identical to the reference CPU operators for rows that are not split (see
+ *     GGLB200_LONG_ROW) and max/arg-max tie-breaks (first edge wins) are identical always.
+ */
+#ifndef GGLB200_H_
+#define GGLB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGLB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GGL_API __attribute__((visibility("default")))
+#else
+#define GGL_API
+#endif
+
+/* status codes (negative); positive values are cudaError_t */
+#define GGL_OK              0
+#define GGL_EINVAL         -1   /* bad argument (null pointer, negative size, unknown enum)            */
+#define GGL_EUNSUPPORTED   -2   /* dtype / reduce / shape combination not implemented                   */
+#define GGL_EWORKSPACE     -3   /* workspace too small                                                  */
+#define GGL_ERANGE         -4   /* E or N does not fit int32                                            */
+
+/* reducers: aggr strings of MessagePassing.aggregate (gammagl/layers/conv/message_passing.py:84-92) */
+#define GGL_SUM   0
+#define GGL_MEAN  1
+#define GGL_MAX   2
+
+/* element types of x / out (AT_DISPATCH_ALL_TYPES_AND2(Half,BFloat16), cpu/segment_sum_cpu.cpp:32-34) */
+#define GGL_F32   0
+#define GGL_BF16  1
+#define GGL_F16   2
+#define GGL_F64   3
+#define GGL_I8    4
+#define GGL_I16   5
+#define GGL_I32   6
+#define GGL_I64   7
+#define GGL_U8    8
+
+/* Rows with more than GGLB200_LONG_ROW edges are reduced in chunks of GGLB200_LONG_CHUNK edges whose
+ * partial results are combined in ascending chunk order by a second kernel (deterministic; fp32 sums
+ * of such rows differ from the serial order by rounding only). */
+#define GGLB200_LONG_ROW    1024
+#define GGLB200_LONG_CHUNK   512
+
+GGL_API int         gglb200_abi_version(void);
+GGL_API const char* gglb200_last_error(void);
+/* number of kernels this library has launched from the calling process (bench.py's gpu_launches) */
+GGL_API int64_t     gglb200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * COO -> CSR ingest.  Replaces SparseStorage's host argsort (gammagl/sparse/storage.py:124-140) and
+ * ind2ptr (gammagl/ops/sparse/cpu/convert.cpp:58-90).
+ *
+ *   key   [E] int64  the index rows are formed over (edge_index[1]=dst for the forward CSR,
+ *                    edge_index[0]=src for the transposed CSR, segment_ids for the segment ops)
+ *   other [E] int64  the index gathered into `col` (src resp. dst); may be NULL when col is NULL
+ *   rowptr[N+1] int32 out     rowptr[r]..rowptr[r+1] = edges of row r
+ *   col   [E] int32 out       other[perm[i]]           (may be NULL)
+ *   perm  [E] int32 out       original edge id of the i-th sorted edge (stable: ascending inside a row)
+ *   plan  [gglb200_csr_plan_ints(E)] int32 out   long-row work list consumed by the reduce kernels
+ *   Keys outside [0,N) are a caller error (the reference leaves them unchecked as well,
+ *   cpu/segment_sum_cpu.cpp:47-56); they are clamped into the sort domain and never dereferenced.
+ * ------------------------------------------------------------------------------------------- */
+GGL_API size_t gglb200_csr_build_workspace_bytes(int64_t E, int64_t N);
+GGL_API size_t gglb200_csr_plan_ints(int64_t E);
+GGL_API int    gglb200_csr_build(const int64_t* key, const int64_t* other, int64_t E, int64_t N,
+                         int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* plan,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[i] = in[perm[i]] for i < n; `width` consecutive elements of `elem_bytes` (4 or 8 ... any
+ * multiple of 4) per index.  Used to bring edge weights into CSR order once per (graph, weight). */
+GGL_API int gglb200_permute_rows(const void* in, const int32_t* perm, void* out, int64_t n, int64_t row_bytes,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The aggregation kernel family (one entry point):
+ *
+ *   out[r, k] = REDUCE_{i in [rowptr[r], rowptr[r+1])}  w(i, k) * x[col[i], k]          r < n_rows
+ *
+ *   reduce   GGL_SUM | GGL_MEAN | GGL_MAX
+ *            MEAN divides the sum by the (unweighted) edge count of the row when count > 1
+ *              (cpu/spmm_mean_cpu.cpp:50-58, cpu/segment_mean_cpu.cpp:67-76);
+ *            MAX starts from lowest() and takes `cur < v` in ascending edge order
+ *              (cpu/spmm_max_cpu.cpp:41-49, cpu/segment_max_cpu.cpp:54-62); empty rows stay lowest().
+ *   w        NULL (unweighted: segment ops, GIN, SAGE-mean), or float32
+ *            [E]    when heads == 1   (gspmm,  cpu/spmm_sum_cpu.cpp:31-38)
+ *            [E,H]  when heads == H   (bspmm,  cpu/bspmm_sum_cpu.cpp:43-55; K = H*C, head of k = k / C)
+ *            indexed by i (already in CSR order) when wperm == NULL, else by wperm[i].
+ *   x        [n_src, K] dtype, row major;  out [n_rows, K] dtype (written fully, no pre-zeroing needed)
+ *   arg      NULL, or int64 [n_rows, K] (MAX only): col[i*] of the winning edge; `arg_empty` for
+ *            rows without edges (segment_max: N, cpu/segment_max_cpu.cpp:27; spmm_max: 0,
+ *            cpu/spmm_max_cpu.cpp:23-24).  For the segment ops col := perm, so this is the edge id.
+ *   plan     the array gglb200_csr_build produced for this rowptr
+ *   workspace gglb200_spmm_workspace_bytes(E_upper, K) bytes (partials of long rows)
+ *   dtype    GGL_F32 / GGL_BF16 / GGL_F16 accumulate in fp32; GGL_F64 in fp64; integer types in int64
+ *            truncated to the type (w must be NULL for non-floating dtypes).
+ * ------------------------------------------------------------------------------------------- */
+GGL_API size_t gglb200_spmm_workspace_bytes(int64_t E, int64_t K, int reduce);
+GGL_API int    gglb200_spmm_csr(int reduce,
+                        const int32_t* rowptr, const int32_t* col, const int32_t* plan,
+                        const float* w, const int32_t* wperm, int32_t heads,
+                        const void* x, void* out, int64_t* arg, int64_t arg_empty,
+                        int64_t n_rows, int64_t E, int64_t K, int dtype,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward helpers of the segment ops (src/segment_sum.cpp:43-54, src/segment_mean.cpp:44-63,
+ * src/segment_max.cpp:48-61).
+ *   gather:  gx[e, k] = g[ids[e], k]            (SUM)
+ *            gx[e, k] = g[ids[e], k] / cnt[ids[e]]   (MEAN; cnt = rowptr differences; float dtypes)
+ *   max:     gx[E,K] zero-filled by the callee, then gx[arg[r,k], k] = g[r,k] for every non-empty row r
+ *            (empty rows carry the sentinel and are skipped -- the reference leaks them into row N).
+ * ------------------------------------------------------------------------------------------- */
+GGL_API int gglb200_segment_gather_bwd(int reduce, const void* g, const int64_t* ids, const int32_t* rowptr,
+                               void* gx, int64_t E, int64_t K, int dtype, void* stream);
+GGL_API int gglb200_segment_max_bwd(const void* g, const int64_t* arg, const int32_t* rowptr,
+                            void* gx, int64_t E, int64_t n_rows, int64_t K, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward of spmm_mean / spmm_max on the TRANSPOSED CSR (rows = source nodes).
+ *   mean:  call gglb200_scale_rows_by_count first (g / indeg, cpu/spmm_mean_cpu.cpp:96-98), then
+ *          gglb200_spmm_csr(SUM) on the transposed CSR.
+ *   max:   gx[s,k] = sum over edges (s -> d) with argsrc[d,k] == s of w * g[d,k]
+ *          (cpu/spmm_max_cpu.cpp:84-96; parallel edges count twice, as there).
+ * ------------------------------------------------------------------------------------------- */
+GGL_API int gglb200_scale_rows_by_count(const float* g, const int32_t* rowptr, float* out, int64_t n_rows,
+                                int64_t K, void* stream);
+GGL_API int gglb200_spmm_max_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* w,
+                         const int32_t* wperm, const float* g, const int64_t* argsrc, float* gx,
+                         int64_t n_rows, int64_t K, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * bspmm backward wrt the per-head edge weight (SDDMM), cpu/bspmm_sum_cpu.cpp:95-107:
+ *   gw[e, h] = sum_c x[src_e, h, c] * g[dst_e, h, c]
+ * evaluated over the forward CSR (rows = dst): g row is loaded once per row, x rows are gathered,
+ * results are written to gw[perm[i], h].
+ * ------------------------------------------------------------------------------------------- */
+GGL_API int gglb200_bspmm_bwd_w(const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                        const float* x, const float* g, float* gw,
+                        int64_t n_rows, int64_t E, int32_t H, int32_t C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused edge softmax over incoming edges (gammagl/utils/softmax.py:29-35):
+ *   m[r,h] = max_i logit[perm[i],h];  p = exp(logit - m);  s = sum p;  alpha = p / (s + 1e-16)
+ * fwd writes alpha[perm[i], h]; bwd: glogit = alpha * (galpha - sum_row(alpha * galpha)) (the analytic
+ * gradient of the composed reference ops, with max treated as a constant shift).
+ * ------------------------------------------------------------------------------------------- */
+GGL_API int gglb200_edge_softmax_fwd(const int32_t* rowptr, const int32_t* perm, const float* logit,
+                             float* alpha, int64_t n_rows, int64_t E, int32_t H, void* stream);
+GGL_API int gglb200_edge_softmax_bwd(const int32_t* rowptr, const int32_t* perm, const float* alpha,
+                             const float* galpha, float* glogit, int64_t n_rows, int64_t E, int32_t H,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGLB200_H_ */
