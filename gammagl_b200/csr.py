@@ -35,13 +35,13 @@ def require_cuda(t, name):
 
 class Csr:
     """rowptr[N+1] i32, col[E] i32 (or None), perm[E] i32, plan (long-row work list), has_long."""
-    __slots__ = ('rowptr', 'col', 'perm', 'plan', 'n_rows', 'E', 'has_long', 'device', '_ws')
+    __slots__ = ('rowptr', 'col', 'perm', 'plan', 'n_rows', 'E', 'has_long', 'n_chunks', 'device', '_ws')
 
     def workspace(self, K, reduce):
         """Partials buffer for split rows; empty when the graph has no row longer than LONG_ROW."""
         if not self.has_long:
             return None, 0
-        need = _lib.load().gglb200_spmm_workspace_bytes(self.E, K, reduce)
+        need = _lib.load().gglb200_spmm_workspace_bytes_for_chunks(self.n_chunks, K, reduce)
         ws = self._ws.get('buf')
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -76,7 +76,8 @@ def build_csr(key, other, n_rows):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(lib.gglb200_csr_build(_ptr(key), _ptr(other), E, n_rows, _ptr(c.rowptr), _ptr(c.col), _ptr(c.perm),
                                          _ptr(c.plan), _ptr(ws), ws_bytes, _stream(dev)), 'csr_build')
-        c.has_long = bool(int(c.plan[1].item()) > 0) if E > _lib.LONG_ROW else False
+        c.n_chunks, n_long = (int(v) for v in c.plan[:2].tolist()) if E > _lib.LONG_ROW else (0, 0)
+        c.has_long = n_long > 0
     return c
 
 

@@ -1,4 +1,6 @@
 // api.cu -- C ABI entry points of libgglb200.so: argument validation, dtype dispatch, error strings.
+#include <cstdlib>
+
 #include "spmm_impl.cuh"
 
 namespace ggl {
@@ -18,9 +20,16 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
-int64_t plan_max_chunks_host(int64_t E) {
-  int64_t max_long = E / GGLB200_LONG_ROW + 1;
-  return E / GGLB200_LONG_CHUNK + max_long + 1;
+int64_t plan_max_chunks_host(int64_t E) { return plan_max_chunks(E); }
+
+int tune_ring() {  // 1 = bulk-copy ring (default), 2 = cp.async (LDGSTS) ring, 0 = register-staged kernels
+  static int v = [] {
+    const char* e = getenv("GGLB200_RING");
+    if (e && e[0] == 'n') return 0;
+    if (e && e[0] == 'l') return 2;
+    return 1;
+  }();
+  return v;
 }
 
 }  // namespace ggl
@@ -31,10 +40,16 @@ extern "C" int gglb200_abi_version(void) { return GGLB200_ABI_VERSION; }
 extern "C" const char* gglb200_last_error(void) { return error_buffer(); }
 extern "C" int64_t gglb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+static size_t bytes_per_chunk(int64_t K, int reduce) { return (size_t)K * (8 + (reduce == GGL_MAX ? 4 : 0)); }
+
+extern "C" size_t gglb200_spmm_workspace_bytes_for_chunks(int64_t n_chunks, int64_t K, int reduce) {
+  if (n_chunks <= 0 || K <= 0) return 0;
+  return (size_t)n_chunks * bytes_per_chunk(K, reduce) + 256;
+}
+
 extern "C" size_t gglb200_spmm_workspace_bytes(int64_t E, int64_t K, int reduce) {
   if (E <= GGLB200_LONG_ROW || K <= 0) return 0;
-  size_t n = (size_t)plan_max_chunks_host(E) * (size_t)K;
-  return n * 8 + (reduce == GGL_MAX ? n * 4 : 0) + 256;
+  return gglb200_spmm_workspace_bytes_for_chunks(plan_max_chunks_host(E), K, reduce);
 }
 
 extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
@@ -45,7 +60,7 @@ extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t
   GGL_REQUIRE(n_rows >= 0 && E >= 0 && K >= 0, GGL_EINVAL, "spmm: negative size");
   GGL_REQUIRE(n_rows < INT32_MAX && E < INT32_MAX, GGL_ERANGE, "spmm: n_rows/E exceed int32");
   if (n_rows == 0 || K == 0) return GGL_OK;
-  GGL_REQUIRE(rowptr && out, GGL_EINVAL, "spmm: rowptr/out must not be NULL");
+  GGL_REQUIRE(rowptr && out && plan, GGL_EINVAL, "spmm: rowptr/out/plan must not be NULL");
   GGL_REQUIRE(E == 0 || (col && x), GGL_EINVAL, "spmm: col/x must not be NULL when E > 0");
   GGL_REQUIRE(heads >= 1, GGL_EINVAL, "spmm: heads must be >= 1");
   GGL_REQUIRE(heads == 1 || (w != nullptr && K % heads == 0), GGL_EINVAL, "spmm: heads=%d needs w and K %% heads == 0 (K=%lld)", heads, (long long)K);
@@ -55,12 +70,18 @@ extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t
   p.reduce = reduce; p.rowptr = rowptr; p.col = col; p.plan = plan; p.w = w; p.wperm = wperm; p.heads = heads;
   p.x = x; p.out = out; p.arg = arg; p.arg_empty = arg_empty; p.n_rows = n_rows; p.E = E; p.K = K;
   p.part_val = nullptr; p.part_arg = nullptr; p.stream = (cudaStream_t)stream;
-  if (plan != nullptr && E > GGLB200_LONG_ROW) {
-    size_t need = gglb200_spmm_workspace_bytes(E, K, reduce);
-    GGL_REQUIRE(workspace != nullptr && workspace_bytes >= need, GGL_EWORKSPACE, "spmm: workspace %zu < %zu", workspace_bytes, need);
-    size_t n = (size_t)plan_max_chunks_host(E) * (size_t)K;
+  p.n_tiles = plan_n_tiles(E);
+  p.tile_row = plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E));
+  p.has_long = workspace != nullptr && E > GGLB200_LONG_ROW;
+  p.ws_chunks = 0;
+  if (p.has_long) {
+    GGL_REQUIRE(workspace_bytes >= gglb200_spmm_workspace_bytes_for_chunks(1, K, reduce), GGL_EWORKSPACE,
+                "spmm: workspace of %zu bytes holds no chunk", workspace_bytes);
+    int64_t fit = (int64_t)((workspace_bytes - 256) / bytes_per_chunk(K, reduce));
+    if (fit > plan_max_chunks(E)) fit = plan_max_chunks(E);
+    p.ws_chunks = (int32_t)fit;
     p.part_val = workspace;
-    p.part_arg = (int32_t*)((char*)workspace + n * 8);
+    p.part_arg = (int32_t*)((char*)workspace + (size_t)fit * (size_t)K * 8);
   }
   switch (dtype) {
     case GGL_F32: return launch_spmm<float>(p);

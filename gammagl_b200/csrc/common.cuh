@@ -42,6 +42,26 @@ extern std::atomic<int64_t> g_launches;
 
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
 
+// ---- plan layout (int32 array produced by gglb200_csr_build, consumed by the reduce kernels) --------
+//   [0] n_chunks  [1] n_long_rows  [2] max_chunks (capacity)  [3] max_long (capacity)
+//   [4] n_tiles   [5] GGLB200_TILE_EDGES  [6..7] reserved
+//   [8 .. 8+2*max_chunks)            chunk table: {row, first_edge}          (rows > GGLB200_LONG_ROW edges)
+//   [.. +3*max_long)                 long-row table: {row, first_chunk, n_chunks}
+//   [.. +n_tiles+1)                  tile table: tile_row[t] = first row whose first edge is >= t*TILE_EDGES
+//                                    (tile_row[n_tiles] = N): tile t owns rows [tile_row[t], tile_row[t+1])
+constexpr int kPlanHeader = 8;
+__host__ __device__ inline int64_t plan_max_long(int64_t E) { return E / GGLB200_LONG_ROW + 1; }
+__host__ __device__ inline int64_t plan_max_chunks(int64_t E) { return E / GGLB200_LONG_CHUNK + plan_max_long(E) + 1; }
+__host__ __device__ inline int64_t plan_n_tiles(int64_t E) {
+  int64_t t = (E + GGLB200_TILE_EDGES - 1) / GGLB200_TILE_EDGES;
+  return t < 1 ? 1 : t;
+}
+__host__ __device__ inline int64_t plan_chunk_off() { return kPlanHeader; }
+__host__ __device__ inline int64_t plan_long_off(int64_t max_chunks) { return kPlanHeader + 2 * max_chunks; }
+__host__ __device__ inline int64_t plan_tile_off(int64_t max_chunks, int64_t max_long) {
+  return kPlanHeader + 2 * max_chunks + 3 * max_long;
+}
+
 // ---- element traits ------------------------------------------------------------------------------
 template <typename T> struct Elem;  // acc_t, to_acc, from_acc, lowest
 template <> struct Elem<float> {

@@ -19,14 +19,7 @@
 
 namespace ggl {
 
-// plan layout (int32):
-//   [0] n_chunks  [1] n_long_rows  [2] max_chunks (capacity)  [3] max_long (capacity)
-//   [4 .. 4+2*max_chunks)            chunk table: {row, first_edge}
-//   [4+2*max_chunks .. +3*max_long)  long-row table: {row, first_chunk, n_chunks}
-__host__ __device__ inline int64_t plan_max_long(int64_t E) { return E / GGLB200_LONG_ROW + 1; }
-__host__ __device__ inline int64_t plan_max_chunks(int64_t E) {
-  return E / GGLB200_LONG_CHUNK + plan_max_long(E) + 1;
-}
+// plan layout: see common.cuh
 
 __global__ void __launch_bounds__(256) narrow_keys_kernel(const int64_t* __restrict__ key, int32_t* __restrict__ key32,
                                                           int32_t* __restrict__ id, int64_t E, int32_t n_minus_1) {
@@ -63,8 +56,8 @@ __global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ r
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int32_t max_chunks = plan[2], max_long = plan[3];
-  int32_t* chunk_tab = plan + 4;
-  int32_t* long_tab = plan + 4 + 2 * (int64_t)max_chunks;
+  int32_t* chunk_tab = plan + plan_chunk_off();
+  int32_t* long_tab = plan + plan_long_off(max_chunks);
   for (; r < N; r += stride) {
     int32_t s = rowptr[r], e = rowptr[r + 1];
     int32_t deg = e - s;
@@ -85,8 +78,27 @@ __global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ r
   }
 }
 
-__global__ void plan_init_kernel(int32_t* plan, int32_t max_chunks, int32_t max_long) {
+__global__ void plan_init_kernel(int32_t* plan, int32_t max_chunks, int32_t max_long, int32_t n_tiles) {
   plan[0] = 0; plan[1] = 0; plan[2] = max_chunks; plan[3] = max_long;
+  plan[4] = n_tiles; plan[5] = GGLB200_TILE_EDGES; plan[6] = 0; plan[7] = 0;
+}
+
+// tile_row[t] = lower_bound(rowptr[0..N], t * TILE_EDGES) clipped to N; tile_row[n_tiles] = N
+__global__ void __launch_bounds__(256) tile_rows_kernel(const int32_t* __restrict__ rowptr, int32_t* __restrict__ tile_row,
+                                                        int64_t N, int64_t n_tiles) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; t <= n_tiles; t += stride) {
+    if (t == n_tiles) { tile_row[t] = (int32_t)N; continue; }
+    if (t == 0) { tile_row[0] = 0; continue; }
+    const int64_t target = t * GGLB200_TILE_EDGES;
+    int64_t lo = 0, hi = N;  // first r in [0,N] with rowptr[r] >= target
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)rowptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    tile_row[t] = (int32_t)lo;
+  }
 }
 
 template <typename T>
@@ -131,7 +143,7 @@ using namespace ggl;
 
 extern "C" size_t gglb200_csr_plan_ints(int64_t E) {
   if (E < 0) E = 0;
-  return (size_t)(4 + 2 * plan_max_chunks(E) + 3 * plan_max_long(E));
+  return (size_t)(kPlanHeader + 2 * plan_max_chunks(E) + 3 * plan_max_long(E) + plan_n_tiles(E) + 1);
 }
 
 extern "C" size_t gglb200_csr_build_workspace_bytes(int64_t E, int64_t N) {
@@ -153,10 +165,14 @@ extern "C" int gglb200_csr_build(const int64_t* key, const int64_t* other, int64
   GGL_REQUIRE(workspace_bytes >= gglb200_csr_build_workspace_bytes(E, N), GGL_EWORKSPACE,
               "csr_build: workspace %zu < %zu", workspace_bytes, gglb200_csr_build_workspace_bytes(E, N));
 
-  plan_init_kernel<<<1, 1, 0, stream>>>(plan, (int32_t)plan_max_chunks(E), (int32_t)plan_max_long(E));
+  const int64_t n_tiles = plan_n_tiles(E);
+  int32_t* tile_row = plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E));
+  plan_init_kernel<<<1, 1, 0, stream>>>(plan, (int32_t)plan_max_chunks(E), (int32_t)plan_max_long(E), (int32_t)n_tiles);
   GGL_LAUNCHED("plan_init");
   if (E == 0) {
     GGL_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * (size_t)(N + 1), stream));
+    tile_rows_kernel<<<1, 256, 0, stream>>>(rowptr, tile_row, N, n_tiles);
+    GGL_LAUNCHED("tile_rows");
     return GGL_OK;
   }
   GGL_REQUIRE(N > 0, GGL_EINVAL, "csr_build: E > 0 but N == 0");
@@ -187,6 +203,8 @@ extern "C" int gglb200_csr_build(const int64_t* key, const int64_t* other, int64
   }
   plan_kernel<<<grid_for(N), 256, 0, stream>>>(rowptr, plan, N);
   GGL_LAUNCHED("plan");
+  tile_rows_kernel<<<grid_for(n_tiles + 1), 256, 0, stream>>>(rowptr, tile_row, N, n_tiles);
+  GGL_LAUNCHED("tile_rows");
   return GGL_OK;
 }
 

@@ -9,18 +9,22 @@
 // and their backward passes wrt x (the same kernel on the transposed CSR).
 //
 // Mapping (HBM-bound gather; no tensor cores -- arithmetic intensity 0.5 flop/B):
-//   * a group of LPR lanes owns one output row; each lane owns VEC consecutive features and moves
-//     them with one 16-byte (or 8/4-byte) ld.global.nc per edge -- a K=100 fp32 row is 25 float4
-//     lanes of one warp, fully coalesced 400 B;
-//   * the group reads its col/weight stream cooperatively (one coalesced load of LPR indices), then
-//     broadcasts index j with a shuffle and issues U=8 independent row gathers before any of them
-//     is consumed (memory-level parallelism: 8 x 400 B in flight per warp, ~32 warps/SM);
+//   * a group of LPR lanes owns one output row at a time; each lane owns VEC consecutive features and moves
+//     them 16 bytes (or 8/4) at a time -- a K=100 fp32 row is 25 float4 lanes of one warp, coalesced 400 B;
+//   * work is cut into EDGE TILES (GGLB200_TILE_EDGES edges; a row belongs to the tile its first edge falls
+//     in), so every lane group streams about the same number of edges whatever the degree distribution;
+//     the group walks its edges as ONE FLAT STREAM and flushes its accumulator at row boundaries;
+//   * the gather is latency-bound, not issue-bound (first profile: ~20 KB in flight per SM, DRAM 35 %): the
+//     16-byte configurations therefore run a per-lane cp.async ring in shared memory -- every lane keeps
+//     STAGES x R of its 16-byte row pieces in flight (~200 KB per SM) without holding registers, and
+//     consumes them in stream order from shared memory (spmm_ring_kernel);
 //   * each lane accumulates sequentially in edge order (stable CSR => ascending original edge id),
 //     multiply and add rounded separately (no FMA contraction) => fp32 sums are bit-identical to the
 //     reference's serial CPU loop; max keeps the first winner (strict <);
-//   * rows longer than GGLB200_LONG_ROW are skipped by the row kernel and reduced by the chunk kernel
-//     (one group per GGLB200_LONG_CHUNK edges -> partials) + finalize kernel (ordered combine), which
-//     bounds the tail on power-law graphs without float atomics.
+//   * rows longer than GGLB200_LONG_ROW are reduced chunk-wise (GGLB200_LONG_CHUNK edges -> partials, in the
+//     same launch for the ring kernel) + a finalize kernel (ordered combine): bounded tail on power-law
+//     graphs, deterministic, no float atomics.  Such a row is always the LAST row of its tile (it outruns
+//     the tile window), so the tile stream simply stops in front of it.
 //   * K wider than LPR*VEC is covered by blockIdx.y column tiles.
 #pragma once
 #include "common.cuh"
@@ -31,7 +35,11 @@ struct SpmmArgs {
   int reduce;               // GGL_SUM / GGL_MEAN / GGL_MAX
   const int32_t* rowptr;
   const int32_t* col;
-  const int32_t* plan;      // NULL => no row splitting
+  const int32_t* plan;      // plan array of gglb200_csr_build (tile table + long-row work list)
+  const int32_t* tile_row;  // plan + tile table offset
+  int64_t n_tiles;
+  bool has_long;            // false => caller asserts no row exceeds GGLB200_LONG_ROW (workspace == NULL)
+  int32_t ws_chunks;        // number of chunk partials the workspace can hold
   const float* w;           // NULL => unweighted
   const int32_t* wperm;     // NULL => w already in CSR order
   int32_t heads;            // 1 => w[E]; H => w[E,H]
@@ -40,8 +48,8 @@ struct SpmmArgs {
   int64_t* arg;             // MAX only, may be NULL
   int64_t arg_empty;
   int64_t n_rows, E, K;
-  void* part_val;           // workspace: [max_chunks, K] acc_t
-  int32_t* part_arg;        // workspace: [max_chunks, K] int32 (MAX)
+  void* part_val;           // workspace: [ws_chunks, K] acc_t
+  int32_t* part_arg;        // workspace: [ws_chunks, K] int32 (MAX)
   cudaStream_t stream;
 };
 
@@ -59,12 +67,34 @@ template <int LPR> __device__ __forceinline__ unsigned group_mask(int lane) {
   else return ((1u << LPR) - 1u) << (lane & ~(LPR - 1));
 }
 
-// Reduce edges [start, start+deg) of one row into the lane's VEC accumulators.
+template <typename T, int VEC, int WMODE, bool ISMAX>
+__device__ __forceinline__ void accumulate(typename Elem<T>::acc_t (&acc)[VEC], int32_t (&argv)[VEC], const Pack<T, VEC>& v,
+                                           float wv, int32_t c) {
+  using acc_t = typename Elem<T>::acc_t;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    acc_t xv = Elem<T>::to_acc(v.v[i]);
+    if constexpr (WMODE != 0 && Elem<T>::is_float) xv = mul_rn((acc_t)wv, xv);
+    if constexpr (ISMAX) {
+      if (acc[i] < xv) { acc[i] = xv; argv[i] = c; }
+    } else {
+      acc[i] = add_rn(acc[i], xv);
+    }
+  }
+}
+
+template <typename T, int VEC, bool ISMAX>
+__device__ __forceinline__ void reset_acc(typename Elem<T>::acc_t (&acc)[VEC], int32_t (&argv)[VEC]) {
+  using acc_t = typename Elem<T>::acc_t;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { acc[i] = ISMAX ? Elem<T>::lowest() : (acc_t)0; argv[i] = -1; }
+}
+
+// Reduce edges [start, start+deg) of one row into the lane's VEC accumulators (register-staged gathers).
 template <typename T, int VEC, int LPR, int WMODE, bool ISMAX>
 __device__ __forceinline__ void reduce_range(typename Elem<T>::acc_t (&acc)[VEC], int32_t (&argv)[VEC],
                                              const SpmmArgs& p, const T* __restrict__ xk /* x + kcol */,
                                              int32_t head, bool col_active, int32_t start, int32_t deg, int lane) {
-  using acc_t = typename Elem<T>::acc_t;
   constexpr int U = (LPR >= 8) ? 8 : (LPR == 1 ? 8 : LPR);
   const int sub = lane & (LPR - 1);
   const int gbase = lane & ~(LPR - 1);
@@ -94,6 +124,7 @@ __device__ __forceinline__ void reduce_range(typename Elem<T>::acc_t (&acc)[VEC]
         const int jj = j + u;
         if constexpr (LPR > 1) {
           c[u] = __shfl_sync(gmask, mycol, gbase + (jj & (LPR - 1)));
+          wv[u] = 1.f;
           if constexpr (WMODE == 1) wv[u] = __shfl_sync(gmask, myw, gbase + (jj & (LPR - 1)));
           if constexpr (WMODE == 2) {
             int32_t eid = __shfl_sync(gmask, myeid, gbase + (jj & (LPR - 1)));
@@ -114,18 +145,7 @@ __device__ __forceinline__ void reduce_range(typename Elem<T>::acc_t (&acc)[VEC]
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (j + u < n && col_active) {
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) {
-            acc_t xv = Elem<T>::to_acc(v[u].v[i]);
-            if constexpr (WMODE != 0 && Elem<T>::is_float) xv = mul_rn((acc_t)wv[u], xv);
-            if constexpr (ISMAX) {
-              if (acc[i] < xv) { acc[i] = xv; argv[i] = c[u]; }
-            } else {
-              acc[i] = add_rn(acc[i], xv);
-            }
-          }
-        }
+        if (j + u < n && col_active) accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v[u], wv[u], c[u]);
       }
     }
   }
@@ -168,36 +188,347 @@ __device__ __forceinline__ void finish_row(typename Elem<T>::acc_t (&acc)[VEC], 
   }
 }
 
-constexpr int kWarpsPerBlock = 8;
-
-// ---- kernel 1: one LPR-lane group per row ----------------------------------------------------------
-template <typename T, int VEC, int LPR, int WMODE, bool ISMAX>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_rows_kernel(const SpmmArgs p) {
-  using acc_t = typename Elem<T>::acc_t;
-  constexpr int RPW = 32 / LPR;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane & (LPR - 1);
-  const int64_t row = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * RPW + lane / LPR;
-  const int32_t kcol = ((int32_t)blockIdx.y * LPR + sub) * VEC;
-  const bool col_active = kcol < p.K;
-  const bool valid = row < p.n_rows;
-  int32_t start = 0, deg = 0;
-  if (valid) {
-    start = __ldg(p.rowptr + row);
-    deg = __ldg(p.rowptr + row + 1) - start;
+// Row cursor of a tile: rows [r, r_end) with a register cache of LPR rowptr entries per group.
+template <int LPR>
+struct RowCursor {
+  int32_t r, r_end, rb, my_end, row_start, cur_end;
+  __device__ __forceinline__ void init(const int32_t* __restrict__ rowptr, int32_t r0, int32_t r1, int32_t e0, int sub, int gbase,
+                                       unsigned gmask) {
+    r = r0; r_end = r1; rb = r0; row_start = e0;
+    my_end = (rb + 1 + sub <= r_end) ? __ldg(rowptr + rb + 1 + sub) : INT32_MAX;
+    const int32_t first_end = __shfl_sync(gmask, my_end, gbase);
+    cur_end = (r < r_end) ? first_end : INT32_MAX;
   }
-  const bool is_long = p.plan != nullptr && deg > GGLB200_LONG_ROW;
-  acc_t acc[VEC];
-  int32_t argv[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) { acc[i] = ISMAX ? Elem<T>::lowest() : (acc_t)0; argv[i] = -1; }
-  const int32_t head = (WMODE == 2 && col_active) ? kcol / (int32_t)(p.K / p.heads) : 0;
-  const T* xk = reinterpret_cast<const T*>(p.x) + kcol;
-  reduce_range<T, VEC, LPR, WMODE, ISMAX>(acc, argv, p, xk, head, col_active, start, is_long ? 0 : deg, lane);
-  if (valid && !is_long && col_active) finish_row<T, VEC, ISMAX>(acc, argv, p, row, kcol, deg);
+  // step to the next row (the caller has flushed row r)
+  __device__ __forceinline__ void advance(const int32_t* __restrict__ rowptr, int sub, int gbase, unsigned gmask) {
+    row_start = cur_end;
+    ++r;
+    if (r < r_end) {
+      if (r - rb == LPR) {
+        rb = r;
+        my_end = (rb + 1 + sub <= r_end) ? __ldg(rowptr + rb + 1 + sub) : INT32_MAX;
+      }
+      cur_end = __shfl_sync(gmask, my_end, gbase + ((r - rb) & (LPR - 1)));
+    } else {
+      cur_end = INT32_MAX;
+    }
+  }
+};
+
+// Tile prologue shared by both tile kernels: rows [r0, r1) and the flat edge range [e0, e1) of tile `tile`.
+// A long row (has_long && deg > LONG_ROW) can only be the last row a tile owns; it is left to the chunk path.
+__device__ __forceinline__ bool tile_ranges(const SpmmArgs& p, int64_t tile, int32_t& r0, int32_t& r1, int32_t& e0, int32_t& e1) {
+  r0 = __ldg(p.tile_row + tile);
+  r1 = __ldg(p.tile_row + tile + 1);
+  if (r0 >= r1) return false;
+  e0 = __ldg(p.rowptr + r0);
+  e1 = __ldg(p.rowptr + r1);
+  if (p.has_long) {
+    const int32_t last = __ldg(p.rowptr + r1 - 1);
+    if (e1 - last > GGLB200_LONG_ROW) { e1 = last; --r1; }
+  }
+  return r0 < r1;
 }
 
-// ---- kernel 2: one group per chunk of a long row -> partials ---------------------------------------
+constexpr int kWarpsPerBlock = 8;
+
+// ---- kernel 1a: register-staged tile kernel (all vector widths; used when a lane moves < 16 bytes) ----
+template <typename T, int VEC, int LPR, int WMODE, bool ISMAX>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) spmm_tiles_kernel(const SpmmArgs p) {
+  using acc_t = typename Elem<T>::acc_t;
+  constexpr int GPW = 32 / LPR;
+  constexpr int U = (LPR >= 8) ? 8 : LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (LPR - 1);
+  const int gbase = lane & ~(LPR - 1);
+  const unsigned gmask = group_mask<LPR>(lane);
+  const int64_t tile = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * GPW + lane / LPR;
+  if (tile >= p.n_tiles) return;  // group-uniform
+  const int32_t kcol = ((int32_t)blockIdx.y * LPR + sub) * VEC;
+  const bool col_active = kcol < p.K;
+  const int32_t head = (WMODE == 2 && col_active) ? kcol / (int32_t)(p.K / p.heads) : 0;
+  const T* xk = reinterpret_cast<const T*>(p.x) + kcol;
+  const int64_t K = p.K;
+
+  int32_t r0, r1, e, e_end;
+  if (!tile_ranges(p, tile, r0, r1, e, e_end)) return;
+  RowCursor<LPR> rc;
+  rc.init(p.rowptr, r0, r1, e, sub, gbase, gmask);
+
+  acc_t acc[VEC];
+  int32_t argv[VEC];
+  reset_acc<T, VEC, ISMAX>(acc, argv);
+  auto next_row = [&]() {
+    if (col_active) finish_row<T, VEC, ISMAX>(acc, argv, p, rc.r, kcol, rc.cur_end - rc.row_start);
+    reset_acc<T, VEC, ISMAX>(acc, argv);
+    rc.advance(p.rowptr, sub, gbase, gmask);
+  };
+  auto load_batch = [&](int32_t at, int32_t& bcol, int32_t& beid, float& bw) {
+    bcol = 0; beid = 0; bw = 1.f;
+    const int32_t idx = at + sub;
+    if (idx < e_end) {
+      bcol = ld_stream_i32(p.col + idx);
+      if constexpr (WMODE != 0) beid = p.wperm ? ld_stream_i32(p.wperm + idx) : idx;
+      if constexpr (WMODE == 1) bw = p.wperm ? __ldg(p.w + beid) : ld_stream_f32(p.w + beid);
+    }
+  };
+
+  int32_t mycol, myeid; float myw;
+  load_batch(e, mycol, myeid, myw);
+  while (e < e_end) {
+    const int nb = min(LPR, e_end - e);
+    int32_t ncol, neid; float nw;
+    load_batch(e + LPR, ncol, neid, nw);  // prefetch (predicated off past the tile end)
+#pragma unroll 1
+    for (int j = 0; j < nb; j += U) {
+      Pack<T, VEC> v[U];
+      int32_t c[U];
+      float wv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int jj = j + u;
+        c[u] = __shfl_sync(gmask, mycol, gbase + (jj & (LPR - 1)));
+        wv[u] = 1.f;
+        if constexpr (WMODE == 1) wv[u] = __shfl_sync(gmask, myw, gbase + (jj & (LPR - 1)));
+        if constexpr (WMODE == 2) {
+          const int32_t eid = __shfl_sync(gmask, myeid, gbase + (jj & (LPR - 1)));
+          wv[u] = (jj < nb) ? __ldg(p.w + (int64_t)eid * p.heads + head) : 0.f;
+        }
+        if (jj < nb && col_active) v[u] = ld_gather<T, VEC>(xk + (int64_t)c[u] * K);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int jj = j + u;
+        if (jj < nb) {
+          while (e + jj == rc.cur_end) next_row();
+          if (col_active) accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v[u], wv[u], c[u]);
+        }
+      }
+    }
+    e += nb;
+    mycol = ncol; myeid = neid; myw = nw;
+  }
+  while (rc.r < rc.r_end) next_row();  // last row of the tile + trailing empty rows
+}
+
+// ---- kernel 1b: shared-memory ring tile kernel (lanes own 16 bytes of a row) --------------------------------
+// Each lane group owns a ring of STAGES slots x R feature rows in shared memory and keeps it LAG = STAGES-1
+// slots ahead of consumption, so up to LAG*R rows per group are in flight without holding registers.
+//   COPY == 1 (default): one lane per row issues a bulk async copy (cp.async.bulk, the TMA-class UBLKCP path:
+//             one instruction moves the whole 16-byte-aligned row; completion is counted in bytes on an
+//             mbarrier per stage);
+//   COPY == 0: every lane copies its own 16 bytes with cp.async (LDGSTS) and waits with wait_group.
+// Consumption is in stream order from shared memory (ld.shared.v4 of the lane's own 16-byte column), with a
+// branch-free fast path for slots that lie inside one row.  Groups [0, ws_chunks) of the launch reduce
+// long-row chunks into partials, the remaining groups are edge tiles.
+constexpr int kRingWarps = 4;
+template <int LPR> struct RingCfg {
+  static constexpr int R = LPR >= 8 ? 8 : LPR;                      // rows per slot
+  static constexpr int STAGES = LPR >= 16 ? 4 : 3;                  // LAG*R <= 2*LPR (index batches A,B,C)
+  static constexpr int LAG = STAGES - 1;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <typename T, int VEC, int LPR, int WMODE, bool ISMAX, int COPY>
+__global__ void __launch_bounds__(kRingWarps * 32) spmm_ring_kernel(const SpmmArgs p, const int32_t pitch /* bytes per row slot */) {
+  static_assert(sizeof(T) * VEC == 16, "ring kernel moves 16 bytes per lane");
+  using acc_t = typename Elem<T>::acc_t;
+  using Cfg = RingCfg<LPR>;
+  constexpr int GPW = 32 / LPR, R = Cfg::R, STAGES = Cfg::STAGES, LAG = Cfg::LAG;
+  extern __shared__ __align__(16) unsigned char ring_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (LPR - 1);
+  const int gbase = lane & ~(LPR - 1);
+  const unsigned gmask = group_mask<LPR>(lane);
+  const int gib = warp * GPW + lane / LPR;  // group index in the block
+  const int64_t g = (int64_t)blockIdx.x * (kRingWarps * GPW) + gib;
+  const int32_t kcol = ((int32_t)blockIdx.y * LPR + sub) * VEC;
+  const bool col_active = kcol < p.K;
+  const int32_t head = (WMODE == 2 && col_active) ? kcol / (int32_t)(p.K / p.heads) : 0;
+  const int64_t K = p.K;
+  const T* xt = reinterpret_cast<const T*>(p.x) + (int64_t)blockIdx.y * LPR * VEC;  // first column of this column tile
+  const T* xk = reinterpret_cast<const T*>(p.x) + kcol;
+  // bytes of one row inside this column tile (multiple of 16)
+  const uint32_t rowb = (uint32_t)min((int64_t)LPR * 16, K * (int64_t)sizeof(T) - (int64_t)blockIdx.y * LPR * 16);
+
+  // shared memory: data rings of all groups, then (COPY==1) STAGES mbarriers per group
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(ring_smem);
+  const uint32_t ring = smem0 + (uint32_t)(gib * (STAGES * R)) * pitch;
+  const uint32_t bars = smem0 + (uint32_t)(kRingWarps * GPW * STAGES * R) * pitch + (uint32_t)gib * STAGES * 8;
+  if constexpr (COPY == 1) {
+    if (sub == 0) {
+#pragma unroll
+      for (int i = 0; i < STAGES; ++i) mbar_init(bars + i * 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp(gmask);
+  }
+
+  // ---- what does this group stream? ----
+  int32_t r0 = 0, r1 = 0, e0, e_end;
+  int64_t chunk = -1;
+  if (g < p.ws_chunks) {  // long-row chunk -> partial
+    if (g >= min(__ldg(p.plan + 0), p.ws_chunks)) return;
+    chunk = g;
+    const int32_t* chunk_tab = p.plan + plan_chunk_off();
+    const int32_t row = __ldg(chunk_tab + 2 * g);
+    e0 = __ldg(chunk_tab + 2 * g + 1);
+    e_end = min(e0 + GGLB200_LONG_CHUNK, __ldg(p.rowptr + row + 1));
+  } else {
+    const int64_t tile = g - p.ws_chunks;
+    if (tile >= p.n_tiles) return;
+    if (!tile_ranges(p, tile, r0, r1, e0, e_end)) return;
+  }
+  RowCursor<LPR> rc;
+  rc.init(p.rowptr, r0, r1, e0, sub, gbase, gmask);  // chunk: r0 == r1 -> cur_end = INT32_MAX (no boundaries)
+
+  acc_t acc[VEC];
+  int32_t argv[VEC];
+  reset_acc<T, VEC, ISMAX>(acc, argv);
+  auto next_row = [&]() {
+    if (col_active) finish_row<T, VEC, ISMAX>(acc, argv, p, rc.r, kcol, rc.cur_end - rc.row_start);
+    reset_acc<T, VEC, ISMAX>(acc, argv);
+    rc.advance(p.rowptr, sub, gbase, gmask);
+  };
+
+  const int32_t n = e_end - e0;                 // edges in the stream
+  const int32_t nslots = (n + R - 1) / R;
+
+  // index batches of LPR stream positions: A = batch bA (being consumed), B = bA+1, C = bA+2
+  struct Batch { int32_t col, eid; float w; };
+  auto load_batch = [&](int32_t b) {
+    Batch t; t.col = 0; t.eid = 0; t.w = 1.f;
+    const int32_t pos = b * LPR + sub;
+    if (pos < n) {
+      const int32_t idx = e0 + pos;
+      t.col = ld_stream_i32(p.col + idx);
+      if constexpr (WMODE != 0) t.eid = p.wperm ? ld_stream_i32(p.wperm + idx) : idx;
+      if constexpr (WMODE == 1) t.w = p.wperm ? __ldg(p.w + t.eid) : ld_stream_f32(p.w + t.eid);
+    }
+    return t;
+  };
+  Batch A = load_batch(0), B = load_batch(1), C = load_batch(2);
+  int32_t bA = 0;
+
+  auto issue = [&](int32_t s) {  // start the copies of slot s
+    if (s < nslots) {  // group-uniform
+      const int32_t pos0 = s * R;
+      const int32_t d = pos0 / LPR - bA;  // 0, 1 or 2
+      const int32_t colsrc = d == 0 ? A.col : (d == 1 ? B.col : C.col);
+      const uint32_t dst = ring + (uint32_t)((s % STAGES) * R) * pitch;
+      if constexpr (COPY == 1) {
+        const uint32_t bar = bars + (uint32_t)(s % STAGES) * 8;
+        const int32_t nv = min(R, n - pos0);
+        const int32_t c = __shfl_sync(gmask, colsrc, gbase + ((pos0 + sub) & (LPR - 1)));  // lane u copies row u
+        __syncwarp(gmask);  // every lane of the group has finished reading this stage (slot s - STAGES)
+        if (sub == 0) mbar_arrive_expect_tx(bar, (uint32_t)nv * rowb);
+        if (sub < nv) bulk_copy_g2s(dst + (uint32_t)sub * pitch, xt + (int64_t)c * K, rowb, bar);
+      } else {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const int32_t c = __shfl_sync(gmask, colsrc, gbase + ((pos0 + u) & (LPR - 1)));
+          if (pos0 + u < n && col_active) cp_async16(dst + u * pitch + sub * 16, xk + (int64_t)c * K);
+        }
+      }
+    }
+    if constexpr (COPY == 0) cp_async_commit();
+  };
+
+#pragma unroll
+  for (int s = 0; s < LAG; ++s) issue(s);
+  for (int32_t s = 0; s < nslots; ++s) {
+    const int32_t pos0 = s * R;
+    if (pos0 / LPR != bA) {  // the consumer enters the next index batch
+      A = B; B = C; ++bA;
+      C = load_batch(bA + 2);
+    }
+    issue(s + LAG);
+    // per-edge scalars of this slot, fetched in convergent code
+    float wv[R];
+    int32_t cc[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      wv[u] = 1.f; cc[u] = 0;
+      if constexpr (ISMAX) cc[u] = __shfl_sync(gmask, A.col, gbase + ((pos0 + u) & (LPR - 1)));
+      if constexpr (WMODE == 1) wv[u] = __shfl_sync(gmask, A.w, gbase + ((pos0 + u) & (LPR - 1)));
+      if constexpr (WMODE == 2) {
+        const int32_t eid = __shfl_sync(gmask, A.eid, gbase + ((pos0 + u) & (LPR - 1)));
+        wv[u] = __ldg(p.w + (int64_t)eid * p.heads + head);
+      }
+    }
+    if constexpr (COPY == 1) mbar_wait(bars + (uint32_t)(s % STAGES) * 8, (uint32_t)(s / STAGES) & 1u);
+    else cp_async_wait<LAG>();  // slot s has landed (only this lane's own copies matter)
+    const uint32_t src = ring + (uint32_t)((s % STAGES) * R) * pitch + (uint32_t)sub * 16;
+    if (pos0 + R <= n && e0 + pos0 + R <= rc.cur_end) {
+      // fast path: the whole slot lies inside the current row
+      if (col_active) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          Pack<T, VEC> v;
+          uint32_t* q = reinterpret_cast<uint32_t*>(&v);
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "r"(src + u * pitch));
+          accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v, wv[u], cc[u]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const int32_t pos = pos0 + u;
+        if (pos < n) {  // group-uniform
+          while (e0 + pos == rc.cur_end) next_row();
+          if (col_active) {
+            Pack<T, VEC> v;
+            uint32_t* q = reinterpret_cast<uint32_t*>(&v);
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "r"(src + u * pitch));
+            accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v, wv[u], cc[u]);
+          }
+        }
+      }
+    }
+  }
+  if constexpr (COPY == 0) cp_async_wait<0>();
+  if (chunk >= 0) {
+    if (col_active) {
+      acc_t* pv = reinterpret_cast<acc_t*>(p.part_val) + chunk * K + kcol;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) pv[i] = acc[i];
+      if constexpr (ISMAX) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) p.part_arg[chunk * K + kcol + i] = argv[i];
+      }
+    }
+  } else {
+    while (rc.r < rc.r_end) next_row();  // last row of the tile + trailing empty rows
+  }
+}
+
+// ---- kernel 2: one group per chunk of a long row -> partials (register-staged configurations) -----------
 template <typename T, int VEC, int LPR, int WMODE, bool ISMAX>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_chunks_kernel(const SpmmArgs p) {
   using acc_t = typename Elem<T>::acc_t;
@@ -206,8 +537,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_chunks_kernel(const 
   const int sub = lane & (LPR - 1);
   const int32_t kcol = ((int32_t)blockIdx.y * LPR + sub) * VEC;
   const bool col_active = kcol < p.K;
-  const int32_t n_chunks = min(__ldg(p.plan + 0), __ldg(p.plan + 2));
-  const int32_t* chunk_tab = p.plan + 4;
+  const int32_t n_chunks = min(__ldg(p.plan + 0), p.ws_chunks);
+  const int32_t* chunk_tab = p.plan + plan_chunk_off();
   const int32_t head = (WMODE == 2 && col_active) ? kcol / (int32_t)(p.K / p.heads) : 0;
   const T* xk = reinterpret_cast<const T*>(p.x) + kcol;
   const int64_t groups = (int64_t)gridDim.x * kWarpsPerBlock * RPW;
@@ -216,8 +547,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_chunks_kernel(const 
     const int32_t end = min(first + GGLB200_LONG_CHUNK, __ldg(p.rowptr + row + 1));
     acc_t acc[VEC];
     int32_t argv[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { acc[i] = ISMAX ? Elem<T>::lowest() : (acc_t)0; argv[i] = -1; }
+    reset_acc<T, VEC, ISMAX>(acc, argv);
     reduce_range<T, VEC, LPR, WMODE, ISMAX>(acc, argv, p, xk, head, col_active, first, end - first, lane);
     if (col_active) {
       acc_t* pv = reinterpret_cast<acc_t*>(p.part_val) + c * p.K + kcol;
@@ -242,14 +572,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_finalize_kernel(cons
   if (kcol >= p.K) return;
   const int32_t max_chunks = __ldg(p.plan + 2);
   const int32_t n_long = min(__ldg(p.plan + 1), __ldg(p.plan + 3));
-  const int32_t* long_tab = p.plan + 4 + 2 * (int64_t)max_chunks;
+  const int32_t* long_tab = p.plan + plan_long_off(max_chunks);
   const int64_t groups = (int64_t)gridDim.x * kWarpsPerBlock * RPW;
   for (int64_t l = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * RPW + lane / LPR; l < n_long; l += groups) {
     const int32_t row = __ldg(long_tab + 3 * l), c0 = __ldg(long_tab + 3 * l + 1), nch = __ldg(long_tab + 3 * l + 2);
+    if (c0 + nch > p.ws_chunks) continue;  // workspace contract violated by the caller: stay memory-safe
     acc_t acc[VEC];
     int32_t argv[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { acc[i] = ISMAX ? Elem<T>::lowest() : (acc_t)0; argv[i] = -1; }
+    reset_acc<T, VEC, ISMAX>(acc, argv);
     for (int32_t j = 0; j < nch; ++j) {
       const acc_t* pv = reinterpret_cast<const acc_t*>(p.part_val) + (int64_t)(c0 + j) * p.K + kcol;
 #pragma unroll
@@ -268,20 +598,56 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_finalize_kernel(cons
 }
 
 // ---- host-side launch ------------------------------------------------------------------------------
+int tune_ring();  // tuning knob (env GGLB200_RING = bulk (default) | ldgsts | none), api.cu
+
 template <typename T, int VEC, int LPR, int WMODE, bool ISMAX>
 int launch_config(const SpmmArgs& p) {
-  constexpr int RPW = 32 / LPR;
+  constexpr int GPW = 32 / LPR;
   const int tiles = (int)((p.K + (int64_t)LPR * VEC - 1) / ((int64_t)LPR * VEC));
-  const int64_t rows_per_block = (int64_t)kWarpsPerBlock * RPW;
-  const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
-  if (blocks > 0) {
-    GGL_REQUIRE(blocks < INT32_MAX && tiles <= 65535, GGL_EUNSUPPORTED, "spmm: grid too large (%lld x %d)", (long long)blocks, tiles);
-    spmm_rows_kernel<T, VEC, LPR, WMODE, ISMAX><<<dim3((unsigned)blocks, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(p);
-    GGL_LAUNCHED("spmm_rows");
+  GGL_REQUIRE(tiles <= 65535, GGL_EUNSUPPORTED, "spmm: K=%lld needs too many column tiles", (long long)p.K);
+  if constexpr (sizeof(T) * VEC == 16 && LPR >= 4) {
+    const int mode = tune_ring();
+    if (mode != 0) {
+      using Cfg = RingCfg<LPR>;
+      const int64_t rowbytes = ((p.K * (int64_t)sizeof(T) + 15) / 16) * 16;
+      const int32_t pitch = (int32_t)(rowbytes < LPR * 16 ? rowbytes : LPR * 16);
+      const size_t smem = (size_t)kRingWarps * GPW * Cfg::STAGES * Cfg::R * pitch + (size_t)kRingWarps * GPW * Cfg::STAGES * 8;
+      static bool attr_set = false;
+      if (!attr_set) {
+        GGL_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        GGL_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        attr_set = true;
+      }
+      const int64_t groups = p.n_tiles + (p.has_long ? p.ws_chunks : 0);
+      const int64_t blocks = (groups + (int64_t)kRingWarps * GPW - 1) / ((int64_t)kRingWarps * GPW);
+      GGL_REQUIRE(blocks < INT32_MAX, GGL_EUNSUPPORTED, "spmm: grid too large");
+      SpmmArgs q = p;
+      if (!p.has_long) q.ws_chunks = 0;
+      if (mode == 1)
+        spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 1><<<dim3((unsigned)blocks, tiles), kRingWarps * 32, smem, p.stream>>>(q, pitch);
+      else
+        spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 0><<<dim3((unsigned)blocks, tiles), kRingWarps * 32, smem, p.stream>>>(q, pitch);
+      GGL_LAUNCHED("spmm_ring");
+      if (p.has_long) {
+        spmm_finalize_kernel<T, VEC, LPR, ISMAX><<<dim3(kSMs, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(q);
+        GGL_LAUNCHED("spmm_finalize");
+      }
+      return GGL_OK;
+    }
   }
-  if (p.plan != nullptr && p.E > GGLB200_LONG_ROW) {
-    const int g = kSMs * 4;
-    spmm_chunks_kernel<T, VEC, LPR, WMODE, ISMAX><<<dim3(g, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(p);
+  const int64_t groups_per_block = (int64_t)kWarpsPerBlock * GPW;
+  const int64_t blocks = (p.n_tiles + groups_per_block - 1) / groups_per_block;
+  GGL_REQUIRE(blocks < INT32_MAX, GGL_EUNSUPPORTED, "spmm: grid too large");
+  spmm_tiles_kernel<T, VEC, LPR, WMODE, ISMAX><<<dim3((unsigned)blocks, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(p);
+  GGL_LAUNCHED("spmm_tiles");
+  if (p.has_long) {
+    static int occ_chunks = 0;  // resident blocks per SM of the chunk kernel (persistent grid)
+    if (occ_chunks == 0) {
+      int o = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, spmm_chunks_kernel<T, VEC, LPR, WMODE, ISMAX>, kWarpsPerBlock * 32, 0) != cudaSuccess || o < 1) o = 2;
+      occ_chunks = o;
+    }
+    spmm_chunks_kernel<T, VEC, LPR, WMODE, ISMAX><<<dim3(kSMs * occ_chunks, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(p);
     GGL_LAUNCHED("spmm_chunks");
     spmm_finalize_kernel<T, VEC, LPR, ISMAX><<<dim3(kSMs, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(p);
     GGL_LAUNCHED("spmm_finalize");

@@ -71,6 +71,9 @@ extern "C" {
  * of such rows differ from the serial order by rounding only). */
 #define GGLB200_LONG_ROW    1024
 #define GGLB200_LONG_CHUNK   512
+/* The row kernel works on "edge tiles": tile t owns the rows whose first edge lies in
+ * [t*TILE_EDGES, (t+1)*TILE_EDGES) -- equal work per warp regardless of the degree distribution. */
+#define GGLB200_TILE_EDGES   256
 
 GGL_API int         gglb200_abi_version(void);
 GGL_API const char* gglb200_last_error(void);
@@ -120,12 +123,18 @@ GGL_API int gglb200_permute_rows(const void* in, const int32_t* perm, void* out,
  *   arg      NULL, or int64 [n_rows, K] (MAX only): col[i*] of the winning edge; `arg_empty` for
  *            rows without edges (segment_max: N, cpu/segment_max_cpu.cpp:27; spmm_max: 0,
  *            cpu/spmm_max_cpu.cpp:23-24).  For the segment ops col := perm, so this is the edge id.
- *   plan     the array gglb200_csr_build produced for this rowptr
- *   workspace gglb200_spmm_workspace_bytes(E_upper, K) bytes (partials of long rows)
+ *   plan     the array gglb200_csr_build produced for this rowptr (required)
+ *   workspace partials of split rows.  gglb200_spmm_workspace_bytes(E, K, reduce) is always sufficient; a
+ *            caller that has read plan[0] (= number of chunks, once after gglb200_csr_build) may pass the
+ *            smaller gglb200_spmm_workspace_bytes_for_chunks(plan[0], K, reduce).  NULL is allowed ONLY when
+ *            no row has more than GGLB200_LONG_ROW edges (plan[1] == 0): rows are then never split.  A
+ *            workspace smaller than plan[0] chunks is a contract violation (kernels stay memory-safe but
+ *            rows whose chunks do not fit are left unwritten).
  *   dtype    GGL_F32 / GGL_BF16 / GGL_F16 accumulate in fp32; GGL_F64 in fp64; integer types in int64
  *            truncated to the type (w must be NULL for non-floating dtypes).
  * ------------------------------------------------------------------------------------------- */
 GGL_API size_t gglb200_spmm_workspace_bytes(int64_t E, int64_t K, int reduce);
+GGL_API size_t gglb200_spmm_workspace_bytes_for_chunks(int64_t n_chunks, int64_t K, int reduce);
 GGL_API int    gglb200_spmm_csr(int reduce,
                         const int32_t* rowptr, const int32_t* col, const int32_t* plan,
                         const float* w, const int32_t* wperm, int32_t heads,
