@@ -21,6 +21,7 @@ SIGNATURES = {
     'gglb200_abi_version': (_int, []),
     'gglb200_last_error': (_c.c_char_p, []),
     'gglb200_launch_count': (_i64, []),
+    'gglb200_set_l2_fetch_granularity': (_int, [_int, _c.POINTER(_int)]),
     'gglb200_csr_build_workspace_bytes': (_sz, [_i64, _i64]),
     'gglb200_csr_plan_ints': (_sz, [_i64]),
     'gglb200_csr_build': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -72,6 +73,20 @@ def check(status, what=''):
     if status != 0:
         msg = load().gglb200_last_error().decode('utf-8', 'replace')
         raise GglError('libgglb200 %s failed (status %d): %s' % (what, status, msg))
+
+
+_tuned_devices = set()
+
+
+def tune_device(device_index):
+    """Once per device: 32-byte L2 fetch granularity for the random row gathers (env GGLB200_L2_FETCH=32|64|128,
+    0 leaves the driver default untouched).  Must be called with `device_index` current."""
+    if device_index in _tuned_devices:
+        return
+    _tuned_devices.add(device_index)
+    want = int(os.environ.get('GGLB200_L2_FETCH', '32'))
+    if want:
+        check(load().gglb200_set_l2_fetch_granularity(want, None), 'set_l2_fetch_granularity')
 
 
 def launch_count():

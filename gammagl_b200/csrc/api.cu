@@ -22,6 +22,14 @@ int set_error(int code, const char* fmt, ...) {
 
 int64_t plan_max_chunks_host(int64_t E) { return plan_max_chunks(E); }
 
+int tune_ring_warps() {
+  static int v = [] {
+    const char* e = getenv("GGLB200_RING_WARPS");
+    return (e && e[0] == '4') ? 4 : 1;
+  }();
+  return v;
+}
+
 int tune_ring() {  // 1 = bulk-copy ring (default), 2 = cp.async (LDGSTS) ring, 0 = register-staged kernels
   static int v = [] {
     const char* e = getenv("GGLB200_RING");
@@ -41,6 +49,15 @@ extern "C" const char* gglb200_last_error(void) { return error_buffer(); }
 extern "C" int64_t gglb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 static size_t bytes_per_chunk(int64_t K, int reduce) { return (size_t)K * (8 + (reduce == GGL_MAX ? 4 : 0)); }
+
+extern "C" int gglb200_set_l2_fetch_granularity(int bytes, int* previous) {
+  GGL_REQUIRE(bytes == 32 || bytes == 64 || bytes == 128, GGL_EINVAL, "l2 fetch granularity must be 32, 64 or 128");
+  size_t old = 0;
+  GGL_CUDA(cudaDeviceGetLimit(&old, cudaLimitMaxL2FetchGranularity));
+  if (previous) *previous = (int)old;
+  GGL_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+  return GGL_OK;
+}
 
 extern "C" size_t gglb200_spmm_workspace_bytes_for_chunks(int64_t n_chunks, int64_t K, int reduce) {
   if (n_chunks <= 0 || K <= 0) return 0;

@@ -321,7 +321,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) spmm_tiles_kernel(cons
 // Consumption is in stream order from shared memory (ld.shared.v4 of the lane's own 16-byte column), with a
 // branch-free fast path for slots that lie inside one row.  Groups [0, ws_chunks) of the launch reduce
 // long-row chunks into partials, the remaining groups are edge tiles.
-constexpr int kRingWarps = 4;
 template <int LPR> struct RingCfg {
   static constexpr int R = LPR >= 8 ? 8 : LPR;                      // rows per slot
   static constexpr int STAGES = LPR >= 16 ? 4 : 3;                  // LAG*R <= 2*LPR (index batches A,B,C)
@@ -354,7 +353,7 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <typename T, int VEC, int LPR, int WMODE, bool ISMAX, int COPY>
+template <typename T, int VEC, int LPR, int WMODE, bool ISMAX, int COPY, int kRingWarps>
 __global__ void __launch_bounds__(kRingWarps * 32) spmm_ring_kernel(const SpmmArgs p, const int32_t pitch /* bytes per row slot */) {
   static_assert(sizeof(T) * VEC == 16, "ring kernel moves 16 bytes per lane");
   using acc_t = typename Elem<T>::acc_t;
@@ -598,7 +597,40 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_finalize_kernel(cons
 }
 
 // ---- host-side launch ------------------------------------------------------------------------------
-int tune_ring();  // tuning knob (env GGLB200_RING = bulk (default) | ldgsts | none), api.cu
+int tune_ring();        // tuning knob (env GGLB200_RING = bulk (default) | ldgsts | none), api.cu
+int tune_ring_warps();  // tuning knob (env GGLB200_RING_WARPS = 1 (default) | 4): warps per block of the ring kernel
+
+// One-warp blocks make the hardware block scheduler the dynamic tile scheduler: a warp that finishes (or finds
+// an empty tile) frees its ring immediately, so skewed graphs do not hold shared memory behind one long tile.
+template <typename T, int VEC, int LPR, int WMODE, bool ISMAX, int WARPS>
+int launch_ring(const SpmmArgs& p, int tiles, int mode) {
+  constexpr int GPW = 32 / LPR;
+  using Cfg = RingCfg<LPR>;
+  const int64_t rowbytes = ((p.K * (int64_t)sizeof(T) + 15) / 16) * 16;
+  const int32_t pitch = (int32_t)(rowbytes < LPR * 16 ? rowbytes : LPR * 16);
+  const size_t smem = (size_t)WARPS * GPW * Cfg::STAGES * Cfg::R * pitch + (size_t)WARPS * GPW * Cfg::STAGES * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GGL_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 1, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    GGL_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 0, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    attr_set = true;
+  }
+  const int64_t groups = p.n_tiles + (p.has_long ? p.ws_chunks : 0);
+  const int64_t blocks = (groups + (int64_t)WARPS * GPW - 1) / ((int64_t)WARPS * GPW);
+  GGL_REQUIRE(blocks < INT32_MAX, GGL_EUNSUPPORTED, "spmm: grid too large");
+  SpmmArgs q = p;
+  if (!p.has_long) q.ws_chunks = 0;
+  if (mode == 1)
+    spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 1, WARPS><<<dim3((unsigned)blocks, tiles), WARPS * 32, smem, p.stream>>>(q, pitch);
+  else
+    spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 0, WARPS><<<dim3((unsigned)blocks, tiles), WARPS * 32, smem, p.stream>>>(q, pitch);
+  GGL_LAUNCHED("spmm_ring");
+  if (p.has_long) {
+    spmm_finalize_kernel<T, VEC, LPR, ISMAX><<<dim3(kSMs, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(q);
+    GGL_LAUNCHED("spmm_finalize");
+  }
+  return GGL_OK;
+}
 
 template <typename T, int VEC, int LPR, int WMODE, bool ISMAX>
 int launch_config(const SpmmArgs& p) {
@@ -608,31 +640,8 @@ int launch_config(const SpmmArgs& p) {
   if constexpr (sizeof(T) * VEC == 16 && LPR >= 4) {
     const int mode = tune_ring();
     if (mode != 0) {
-      using Cfg = RingCfg<LPR>;
-      const int64_t rowbytes = ((p.K * (int64_t)sizeof(T) + 15) / 16) * 16;
-      const int32_t pitch = (int32_t)(rowbytes < LPR * 16 ? rowbytes : LPR * 16);
-      const size_t smem = (size_t)kRingWarps * GPW * Cfg::STAGES * Cfg::R * pitch + (size_t)kRingWarps * GPW * Cfg::STAGES * 8;
-      static bool attr_set = false;
-      if (!attr_set) {
-        GGL_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-        GGL_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-        attr_set = true;
-      }
-      const int64_t groups = p.n_tiles + (p.has_long ? p.ws_chunks : 0);
-      const int64_t blocks = (groups + (int64_t)kRingWarps * GPW - 1) / ((int64_t)kRingWarps * GPW);
-      GGL_REQUIRE(blocks < INT32_MAX, GGL_EUNSUPPORTED, "spmm: grid too large");
-      SpmmArgs q = p;
-      if (!p.has_long) q.ws_chunks = 0;
-      if (mode == 1)
-        spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 1><<<dim3((unsigned)blocks, tiles), kRingWarps * 32, smem, p.stream>>>(q, pitch);
-      else
-        spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 0><<<dim3((unsigned)blocks, tiles), kRingWarps * 32, smem, p.stream>>>(q, pitch);
-      GGL_LAUNCHED("spmm_ring");
-      if (p.has_long) {
-        spmm_finalize_kernel<T, VEC, LPR, ISMAX><<<dim3(kSMs, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(q);
-        GGL_LAUNCHED("spmm_finalize");
-      }
-      return GGL_OK;
+      if (tune_ring_warps() == 4) return launch_ring<T, VEC, LPR, WMODE, ISMAX, 4>(p, tiles, mode);
+      return launch_ring<T, VEC, LPR, WMODE, ISMAX, 1>(p, tiles, mode);
     }
   }
   const int64_t groups_per_block = (int64_t)kWarpsPerBlock * GPW;
