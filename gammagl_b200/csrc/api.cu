@@ -22,6 +22,16 @@ int set_error(int code, const char* fmt, ...) {
 
 int64_t plan_max_chunks_host(int64_t E) { return plan_max_chunks(E); }
 
+int tile_edges() {
+  static int v = [] {
+    const char* e = getenv("GGLB200_TILE_EDGES");
+    int t = e ? atoi(e) : GGLB200_TILE_EDGES;
+    if (t < 64 || t > 8192 || (t & (t - 1))) t = GGLB200_TILE_EDGES;
+    return t;
+  }();
+  return v;
+}
+
 int tune_ring_warps() {
   static int v = [] {
     const char* e = getenv("GGLB200_RING_WARPS");

@@ -52,8 +52,10 @@ constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
 constexpr int kPlanHeader = 8;
 __host__ __device__ inline int64_t plan_max_long(int64_t E) { return E / GGLB200_LONG_ROW + 1; }
 __host__ __device__ inline int64_t plan_max_chunks(int64_t E) { return E / GGLB200_LONG_CHUNK + plan_max_long(E) + 1; }
-__host__ __device__ inline int64_t plan_n_tiles(int64_t E) {
-  int64_t t = (E + GGLB200_TILE_EDGES - 1) / GGLB200_TILE_EDGES;
+int tile_edges();  // edges per tile: GGLB200_TILE_EDGES unless overridden by env GGLB200_TILE_EDGES (tuning), api.cu
+inline int64_t plan_n_tiles(int64_t E) {
+  const int64_t te = tile_edges();
+  int64_t t = (E + te - 1) / te;
   return t < 1 ? 1 : t;
 }
 __host__ __device__ inline int64_t plan_chunk_off() { return kPlanHeader; }

@@ -78,20 +78,20 @@ __global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ r
   }
 }
 
-__global__ void plan_init_kernel(int32_t* plan, int32_t max_chunks, int32_t max_long, int32_t n_tiles) {
+__global__ void plan_init_kernel(int32_t* plan, int32_t max_chunks, int32_t max_long, int32_t n_tiles, int32_t te) {
   plan[0] = 0; plan[1] = 0; plan[2] = max_chunks; plan[3] = max_long;
-  plan[4] = n_tiles; plan[5] = GGLB200_TILE_EDGES; plan[6] = 0; plan[7] = 0;
+  plan[4] = n_tiles; plan[5] = te; plan[6] = 0; plan[7] = 0;
 }
 
 // tile_row[t] = lower_bound(rowptr[0..N], t * TILE_EDGES) clipped to N; tile_row[n_tiles] = N
 __global__ void __launch_bounds__(256) tile_rows_kernel(const int32_t* __restrict__ rowptr, int32_t* __restrict__ tile_row,
-                                                        int64_t N, int64_t n_tiles) {
+                                                        int64_t N, int64_t n_tiles, int64_t te) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; t <= n_tiles; t += stride) {
     if (t == n_tiles) { tile_row[t] = (int32_t)N; continue; }
     if (t == 0) { tile_row[0] = 0; continue; }
-    const int64_t target = t * GGLB200_TILE_EDGES;
+    const int64_t target = t * te;
     int64_t lo = 0, hi = N;  // first r in [0,N] with rowptr[r] >= target
     while (lo < hi) {
       int64_t mid = (lo + hi) >> 1;
@@ -167,11 +167,11 @@ extern "C" int gglb200_csr_build(const int64_t* key, const int64_t* other, int64
 
   const int64_t n_tiles = plan_n_tiles(E);
   int32_t* tile_row = plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E));
-  plan_init_kernel<<<1, 1, 0, stream>>>(plan, (int32_t)plan_max_chunks(E), (int32_t)plan_max_long(E), (int32_t)n_tiles);
+  plan_init_kernel<<<1, 1, 0, stream>>>(plan, (int32_t)plan_max_chunks(E), (int32_t)plan_max_long(E), (int32_t)n_tiles, (int32_t)tile_edges());
   GGL_LAUNCHED("plan_init");
   if (E == 0) {
     GGL_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * (size_t)(N + 1), stream));
-    tile_rows_kernel<<<1, 256, 0, stream>>>(rowptr, tile_row, N, n_tiles);
+    tile_rows_kernel<<<1, 256, 0, stream>>>(rowptr, tile_row, N, n_tiles, (int64_t)tile_edges());
     GGL_LAUNCHED("tile_rows");
     return GGL_OK;
   }
@@ -203,7 +203,7 @@ extern "C" int gglb200_csr_build(const int64_t* key, const int64_t* other, int64
   }
   plan_kernel<<<grid_for(N), 256, 0, stream>>>(rowptr, plan, N);
   GGL_LAUNCHED("plan");
-  tile_rows_kernel<<<grid_for(n_tiles + 1), 256, 0, stream>>>(rowptr, tile_row, N, n_tiles);
+  tile_rows_kernel<<<grid_for(n_tiles + 1), 256, 0, stream>>>(rowptr, tile_row, N, n_tiles, (int64_t)tile_edges());
   GGL_LAUNCHED("tile_rows");
   return GGL_OK;
 }

@@ -1,0 +1,241 @@
+"""Host-side mirror of the callers of the path: MessagePassing and the four drop-in target layers.
+
+`tensorlayerx` (the reference's nn substrate) is not available offline, so these are plain `torch.nn.Module`s that
+restate, line for line in meaning, the `forward` of
+
+    MessagePassing   /root/reference/gammagl/layers/conv/message_passing.py:35-167
+    GCNConv          /root/reference/gammagl/layers/conv/gcn_conv.py:78-108   (+ utils/degree.py:10-40)
+    SAGEConv         /root/reference/gammagl/layers/conv/sage_conv.py:56-108  (mean / gcn / pool)
+    GATConv          /root/reference/gammagl/layers/conv/gat_conv.py:98-122   (+ utils/softmax.py:29-35)
+    GINConv          /root/reference/gammagl/layers/conv/gin_conv.py:49-63
+
+with the same constructor arguments, argument names and weight layout (`Linear` weight stored [in, out] as in
+tensorlayerx, tests/layers/conv/test_gcn_conv.py:14-17).  `fused=True` (default) routes propagate() through the
+fused kernels (gspmm / bspmm / segment_softmax) -- the `message_aggregate` plug point the reference left commented
+out (gcn_conv.py:110-115, gat_conv.py:124-129); `fused=False` runs the reference's own message + aggregate
+decomposition on the B200 segment operators (materialised [E,K] messages).  Both are parity-tested.
+The dense X.W products stay torch.matmul (cuBLAS): tensor cores live there, outside the aggregation metric.
+"""
+import math
+
+import torch
+
+from . import mpops
+
+
+class Linear(torch.nn.Module):
+    """tlx.layers.Linear: y = x @ W (+ b), W stored [in_features, out_features]."""
+
+    def __init__(self, in_features, out_features, bias=False):
+        super().__init__()
+        w = torch.empty(in_features, out_features)
+        bound = math.sqrt(6.0 / (in_features + out_features))  # xavier_uniform
+        torch.nn.init.uniform_(w, -bound, bound)
+        self.weights = torch.nn.Parameter(w)
+        self.biases = torch.nn.Parameter(torch.zeros(out_features)) if bias else None
+
+    def forward(self, x):
+        y = x @ self.weights
+        return y if self.biases is None else y + self.biases
+
+
+class MessagePassing(torch.nn.Module):
+    """message_passing.py:35-167.  propagate() takes the fused branch when the subclass did not override
+    `message` (the base message is gather x weight, exactly what gspmm fuses) and `fused` is on."""
+
+    def __init__(self, fused=True):
+        super().__init__()
+        self.fused = fused
+
+    def message(self, x, edge_index, edge_weight=None):
+        msg = x[edge_index[0, :]]                                           # message_passing.py:56
+        if edge_weight is not None:
+            return msg * edge_weight.unsqueeze(-1)                          # message_passing.py:57-59
+        return msg
+
+    def aggregate(self, msg, edge_index, num_nodes=None, aggr='sum'):
+        dst_index = edge_index[1, :]                                        # message_passing.py:84
+        if aggr == 'sum':
+            return mpops.unsorted_segment_sum(msg, dst_index, num_nodes)
+        elif aggr == 'mean':
+            return mpops.unsorted_segment_mean(msg, dst_index, num_nodes)
+        elif aggr == 'max':
+            return mpops.unsorted_segment_max(msg, dst_index, num_nodes)
+        raise NotImplementedError('Not support for this opearator')
+
+    def message_aggregate(self, x, edge_index, edge_weight=None, aggr='sum'):
+        if edge_weight is not None and edge_weight.dim() == 2 and x.dim() == 3:
+            return mpops.bspmm(edge_index, edge_weight, x, aggr)            # per-head weights (GAT)
+        return mpops.gspmm(edge_index, edge_weight, x, aggr)                # message_passing.py:99-104
+
+    def update(self, x):
+        return x
+
+    def propagate(self, x, edge_index, aggr='sum', **kwargs):
+        if kwargs.get('num_nodes') is None:
+            kwargs['num_nodes'] = x.shape[0]                                # message_passing.py:141-142
+        edge_weight = kwargs.get('edge_weight')
+        base_message = type(self).message is MessagePassing.message
+        square = kwargs['num_nodes'] == x.shape[0]                          # gspmm output rows = x rows (no bipartite)
+        if self.fused and base_message and square:
+            out = self.message_aggregate(x, edge_index, edge_weight=edge_weight, aggr=aggr)
+        else:
+            if base_message:
+                msg = self.message(x, edge_index, edge_weight)
+            else:
+                msg = self.message(x, edge_index)
+            out = self.aggregate(msg, edge_index, num_nodes=kwargs['num_nodes'], aggr=aggr)
+        return self.update(out)
+
+
+def degree(index, num_nodes=None, dtype=torch.float32):
+    """utils/degree.py:10-40: unsorted_segment_sum of ones."""
+    N = int(index.max().item()) + 1 if num_nodes is None else num_nodes
+    one = torch.ones((index.shape[0],), dtype=dtype, device=index.device)
+    return mpops.unsorted_segment_sum(one, index, N)
+
+
+def calc_gcn_norm(edge_index, num_nodes, edge_weight=None):
+    """utils/norm.py:5-30."""
+    src, dst = edge_index[0], edge_index[1]
+    if edge_weight is None:
+        edge_weight = torch.ones((edge_index.shape[1], 1), device=edge_index.device)
+    deg = mpops.unsorted_segment_sum(edge_weight, src, num_nodes).reshape(-1)
+    dis = deg.pow(-0.5)
+    return dis[src] * edge_weight.reshape(-1) * dis[dst]
+
+
+def add_self_loops(edge_index, num_nodes=None):
+    """utils/loop.py:107-150 (unweighted form): append (i, i) for every node."""
+    N = int(edge_index.max().item()) + 1 if num_nodes is None else num_nodes
+    loops = torch.arange(N, device=edge_index.device, dtype=edge_index.dtype)
+    return torch.cat([edge_index, torch.stack([loops, loops])], dim=1)
+
+
+class GCNConv(MessagePassing):
+    def __init__(self, in_channels, out_channels, norm='both', add_bias=True, fused=True):
+        super().__init__(fused)
+        if norm not in ['left', 'right', 'none', 'both']:
+            raise ValueError('Invalid norm value. Must be either "none", "both", "right" or "left".'
+                             ' But got "{}".'.format(norm))
+        self.in_channels, self.out_channels, self.add_bias, self._norm = in_channels, out_channels, add_bias, norm
+        self.linear = Linear(in_channels, out_channels, bias=False)
+        self.bias = torch.nn.Parameter(torch.zeros(1, out_channels)) if add_bias else None
+
+    def forward(self, x, edge_index, edge_weight=None, num_nodes=None):
+        x = self.linear(x)                                                  # gcn_conv.py:79
+        src, dst = edge_index[0], edge_index[1]
+        if edge_weight is None:
+            edge_weight = torch.ones((edge_index.shape[1],), device=x.device)
+        edge_weight = edge_weight.reshape(-1)
+        weights = edge_weight
+        num_nodes = x.shape[0]
+        if self._norm in ['left', 'both']:                                  # gcn_conv.py:88-94
+            deg = degree(src, num_nodes=num_nodes, dtype=torch.float32)
+            norm = deg.pow(-0.5) if self._norm == 'both' else 1.0 / deg
+            weights = norm[src] * edge_weight
+        if self._norm in ['right', 'both']:                                 # gcn_conv.py:96-102
+            deg = degree(dst, num_nodes=num_nodes, dtype=torch.float32)
+            norm = deg.pow(-0.5) if self._norm == 'both' else 1.0 / deg
+            weights = weights.reshape(-1) * norm[dst]
+        out = self.propagate(x, edge_index, edge_weight=weights, num_nodes=num_nodes)
+        if self.add_bias:
+            out = out + self.bias
+        return out
+
+
+class SAGEConv(MessagePassing):
+    def __init__(self, in_channels, out_channels, activation=None, aggr='mean', add_bias=True, fused=True):
+        super().__init__(fused)
+        if aggr not in ('mean', 'gcn', 'pool'):
+            raise NotImplementedError("aggr '%s' (lstm) is outside the aggregation path" % aggr)
+        self.aggr, self.act, self.in_feat = aggr, activation, in_channels
+        self.fc_neigh = Linear(in_channels, out_channels)
+        if aggr != 'gcn':
+            self.fc_self = Linear(in_channels, out_channels)
+        if aggr == 'pool':
+            self.pool = Linear(in_channels, in_channels)
+        self.add_bias = add_bias
+        self.bias = torch.nn.Parameter(torch.zeros(1, out_channels)) if add_bias else None
+
+    def forward(self, feat, edge):
+        src_feat, dst_feat = feat if isinstance(feat, tuple) else (feat, feat)
+        num_nodes = int(dst_feat.shape[0])
+        if self.aggr == 'mean':                                             # sage_conv.py:79-81
+            src_feat = self.fc_neigh(src_feat)
+            out = self.propagate(src_feat, edge, edge_weight=None, num_nodes=num_nodes, aggr='mean')
+        elif self.aggr == 'gcn':                                            # sage_conv.py:82-88
+            src_feat = self.fc_neigh(src_feat)
+            n = int(1 + edge[0].max().item())
+            edge = add_self_loops(edge, n)
+            weight = calc_gcn_norm(edge, n)
+            out = self.propagate(src_feat, edge, edge_weight=weight, num_nodes=n, aggr='sum')
+            out = out[:num_nodes]
+        else:                                                               # pool, sage_conv.py:89-92
+            src_feat = torch.relu(self.pool(src_feat))
+            out = self.propagate(src_feat, edge, edge_weight=None, num_nodes=num_nodes, aggr='max')
+            out = self.fc_neigh(out)
+        if self.aggr != 'gcn':
+            out = out + self.fc_self(dst_feat)
+        if self.add_bias:
+            out = out + self.bias
+        if self.act is not None:
+            out = self.act(out)
+        return out
+
+
+class GATConv(MessagePassing):
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout_rate=0., add_bias=True,
+                 fused=True):
+        super().__init__(fused)
+        self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
+        self.negetive_slop, self.dropout_rate, self.add_bias = negative_slope, dropout_rate, add_bias
+        self.w = torch.nn.Parameter(torch.nn.init.trunc_normal_(torch.empty(in_channels, out_channels * heads), std=0.05))
+        self.att = torch.nn.Parameter(torch.nn.init.trunc_normal_(torch.empty(1, heads, out_channels * 2), std=0.05))
+        self.dropout = torch.nn.Dropout(dropout_rate)
+        if add_bias:
+            self.bias = torch.nn.Parameter(torch.zeros(heads * out_channels if concat else out_channels))
+
+    def forward(self, x, edge_index, num_nodes=None):
+        x = (x @ self.w).reshape(-1, self.heads, self.out_channels)         # gat_conv.py:99-100
+        num_nodes = x.shape[0] if num_nodes is None else num_nodes
+        node_src, node_dst = edge_index[0, :], edge_index[1, :]
+        # e = leaky_relu(sum_c concat(x[src], x[dst]) * att): the per-node halves are reduced before the gather
+        # (same arithmetic association per half; avoids materialising [E, H, 2C])
+        a_src, a_dst = self.att[..., :self.out_channels], self.att[..., self.out_channels:]
+        if self.fused:
+            e = (x * a_src).sum(-1)[node_src] + (x * a_dst).sum(-1)[node_dst]
+        else:
+            feat = torch.cat((x[node_src], x[node_dst]), dim=-1)            # gat_conv.py:103-108
+            e = (feat * self.att).sum(-1)
+        e = torch.nn.functional.leaky_relu(e, self.negetive_slop)
+        if self.fused:
+            alpha = self.dropout(mpops.segment_softmax(e, node_dst, num_nodes))
+        else:                                                               # utils/softmax.py:29-35
+            mx = mpops.unsorted_segment_max(e, node_dst, num_nodes)
+            ex = torch.exp(e - mx[node_dst])
+            den = mpops.unsorted_segment_sum(ex, node_dst, num_nodes)
+            alpha = self.dropout(ex / (den[node_dst] + 1e-16))
+        x = self.propagate(x, edge_index, num_nodes=num_nodes, edge_weight=alpha)   # gat_conv.py:112 (bspmm when fused)
+        x = x.reshape(-1, self.heads * self.out_channels) if self.concat else x.mean(dim=1)
+        if self.add_bias:
+            x = x + self.bias
+        return x
+
+
+class GINConv(MessagePassing):
+    def __init__(self, nn, eps=0., train_eps=False, fused=True):
+        super().__init__(fused)
+        self.nn = nn
+        if train_eps:
+            self.eps = torch.nn.Parameter(torch.tensor([float(eps)]))
+        else:
+            self.register_buffer('eps', torch.tensor([float(eps)]))
+
+    def forward(self, x, edge_index, size=None):
+        if not isinstance(x, (list, tuple)):
+            x = (x, x)
+        out = self.propagate(x=x[0], edge_index=edge_index)                 # gin_conv.py:54 (sum, no weights)
+        if x[1] is not None:
+            out = out + (1 + self.eps) * x[1]
+        return self.nn(out)

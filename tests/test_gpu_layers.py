@@ -1,0 +1,172 @@
+"""GPU tests of the layer mirror (gammagl_b200/layers.py): fused path vs the reference's own message+aggregate
+decomposition vs a dense fp64 restatement of gcn_conv.py:78-108 / sage_conv.py:56-108 / gat_conv.py:98-122 /
+gin_conv.py:49-63 -- forward and parameter/input gradients, fp32 tolerance 1e-5 relative (north_star)."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def graph(N, E, seed):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, N, (E,), generator=g)
+    dst = torch.randint(0, N - N // 10, (E,), generator=g)
+    loops = torch.arange(N)
+    return torch.stack([torch.cat([src, loops]), torch.cat([dst, loops])])   # self loops: no zero degrees
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def run(layer, *args):
+    out = layer(*args)
+    g = torch.Generator().manual_seed(99)
+    go = torch.randn(out.shape, generator=g).to(out.device, out.dtype)
+    layer.zero_grad()
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.requires_grad:
+            a.grad = None
+    out.backward(go)
+    grads = [p.grad.clone() for p in layer.parameters() if p.grad is not None]
+    return out, grads, go
+
+
+def dense_adj(ei, w, N):
+    A = torch.zeros(N, N, dtype=torch.float64)
+    A.index_put_((ei[1], ei[0]), w.double(), accumulate=True)
+    return A
+
+
+@pytest.mark.parametrize('norm', ['both', 'left', 'right', 'none'])
+def test_gcn_conv(norm):
+    from gammagl_b200.layers import GCNConv
+    N, E, F, H = 300, 4000, 33, 20
+    ei = graph(N, E, 1)
+    x = torch.randn(N, F, generator=torch.Generator().manual_seed(2))
+    fused = GCNConv(F, H, norm=norm).to(DEV)
+    unfused = copy.deepcopy(fused)
+    unfused.fused = False
+    xf = x.to(DEV).requires_grad_(True)
+    xu = x.to(DEV).requires_grad_(True)
+    of, gf, go = run(fused, xf, ei.to(DEV))
+    ou, gu, _ = run(unfused, xu, ei.to(DEV))
+    # dense fp64 reference
+    W = fused.linear.weights.detach().double().cpu().requires_grad_(True)
+    b = fused.bias.detach().double().cpu().requires_grad_(True)
+    xd = x.double().requires_grad_(True)
+    src, dst = ei
+    ew = torch.ones(ei.shape[1], dtype=torch.float64)
+    if norm in ('left', 'both'):
+        deg = torch.bincount(src, minlength=N).double()
+        ew = (deg.pow(-0.5) if norm == 'both' else 1 / deg)[src] * ew
+    if norm in ('right', 'both'):
+        deg = torch.bincount(dst, minlength=N).double()
+        ew = ew * (deg.pow(-0.5) if norm == 'both' else 1 / deg)[dst]
+    od = dense_adj(ei, ew, N) @ (xd @ W) + b
+    od.backward(go.double().cpu())
+    assert rel(of, od) < 1e-5 and rel(ou, od) < 1e-5
+    assert rel(xf.grad, xd.grad) < 1e-5 and rel(xu.grad, xd.grad) < 1e-5
+    assert rel(fused.linear.weights.grad, W.grad) < 1e-5 and rel(unfused.linear.weights.grad, W.grad) < 1e-5
+    assert rel(fused.bias.grad, b.grad) < 1e-5 and rel(unfused.bias.grad, b.grad) < 1e-5
+
+
+@pytest.mark.parametrize('aggr', ['mean', 'gcn', 'pool'])
+def test_sage_conv(aggr):
+    from gammagl_b200.layers import SAGEConv
+    N, E, F, H = 250, 3000, 24, 12
+    ei = graph(N, E, 3)[:, :E] if aggr == 'gcn' else graph(N, E, 3)
+    if aggr == 'pool':
+        # duplicate (src,dst) pairs: the reference's gspmm-max backward credits EVERY parallel edge of the winning
+        # source (cpu/spmm_max_cpu.cpp:84-96) while segment_max credits the first edge only -- both are reproduced
+        # exactly, so the fused and unfused layers agree only on a coalesced graph.
+        ei = torch.unique(ei, dim=1)
+    if aggr == 'gcn':
+        ei[0, 0] = N - 1          # the layer sizes the graph by 1 + max(src) (sage_conv.py:84-86)
+    x = torch.randn(N, F, generator=torch.Generator().manual_seed(4))
+    fused = SAGEConv(F, H, aggr=aggr).to(DEV)
+    unfused = copy.deepcopy(fused)
+    unfused.fused = False
+    xf = x.to(DEV).requires_grad_(True)
+    xu = x.to(DEV).requires_grad_(True)
+    of, gf, go = run(fused, xf, ei.to(DEV))
+    ou, gu, _ = run(unfused, xu, ei.to(DEV))
+    assert rel(of, ou) < 1e-5
+    assert rel(xf.grad, xu.grad) < 1e-5
+    for a, b in zip(gf, gu):
+        assert rel(a, b) < 1e-5
+    if aggr == 'mean':
+        Wn = fused.fc_neigh.weights.detach().double().cpu()
+        Ws = fused.fc_self.weights.detach().double().cpu()
+        A = dense_adj(ei, torch.ones(ei.shape[1]), N)
+        deg = A.sum(1, keepdim=True).clamp_min(1)
+        od = (A / deg) @ (x.double() @ Wn) + x.double() @ Ws + fused.bias.detach().double().cpu()
+        assert rel(of, od) < 1e-5
+
+
+@pytest.mark.parametrize('heads,concat', [(8, True), (4, False), (1, True)])
+def test_gat_conv(heads, concat):
+    from gammagl_b200.layers import GATConv
+    N, E, F, C = 200, 3000, 17, 8
+    ei = graph(N, E, 5)
+    x = torch.randn(N, F, generator=torch.Generator().manual_seed(6))
+    fused = GATConv(F, C, heads=heads, concat=concat).to(DEV)
+    with torch.no_grad():
+        fused.w.mul_(8)
+        fused.att.mul_(8)        # make the attention non-trivial
+    unfused = copy.deepcopy(fused)
+    unfused.fused = False
+    xf = x.to(DEV).requires_grad_(True)
+    xu = x.to(DEV).requires_grad_(True)
+    of, gf, go = run(fused, xf, ei.to(DEV))
+    ou, gu, _ = run(unfused, xu, ei.to(DEV))
+    # dense fp64 reference of gat_conv.py:98-122
+    W = fused.w.detach().double().cpu().requires_grad_(True)
+    att = fused.att.detach().double().cpu().requires_grad_(True)
+    xd = x.double().requires_grad_(True)
+    h = (xd @ W).reshape(N, heads, C)
+    src, dst = ei
+    e = (torch.cat((h[src], h[dst]), -1) * att).sum(-1)
+    e = torch.nn.functional.leaky_relu(e, 0.2)
+    mx = torch.full((N, heads), -1e300, dtype=torch.float64).scatter_reduce(0, dst[:, None].expand(-1, heads), e, 'amax')
+    ex = torch.exp(e - mx[dst].detach())
+    den = torch.zeros(N, heads, dtype=torch.float64).index_add_(0, dst, ex)
+    alpha = ex / (den[dst] + 1e-16)
+    od = torch.zeros(N, heads, C, dtype=torch.float64).index_add_(0, dst, h[src] * alpha.unsqueeze(-1))
+    od = od.reshape(N, heads * C) if concat else od.mean(1)
+    od = od + fused.bias.detach().double().cpu()
+    od.backward(go.double().cpu())
+    assert rel(of, od) < 2e-5 and rel(ou, od) < 2e-5
+    assert rel(xf.grad, xd.grad) < 1e-4 and rel(xu.grad, xd.grad) < 1e-4
+    assert rel(fused.w.grad, W.grad) < 1e-4 and rel(fused.att.grad, att.grad) < 1e-4
+
+
+def test_gin_conv_and_bare_message_passing():
+    from gammagl_b200.layers import GINConv, Linear, MessagePassing
+    N, E, F = 180, 2500, 10
+    ei = graph(N, E, 7)
+    x = torch.randn(N, F, generator=torch.Generator().manual_seed(8))
+    nn = torch.nn.Sequential(Linear(F, 16), torch.nn.ReLU(), Linear(16, 5))
+    gin = GINConv(nn, eps=0.3, train_eps=True).to(DEV)
+    xf = x.to(DEV).requires_grad_(True)
+    of, gf, go = run(gin, xf, ei.to(DEV))
+    A = dense_adj(ei, torch.ones(ei.shape[1]), N)
+    xd = x.double().requires_grad_(True)
+    hd = A @ xd + 1.3 * xd
+    W1, W2 = nn[0].weights.detach().double().cpu(), nn[2].weights.detach().double().cpu()
+    od = torch.relu(hd @ W1) @ W2
+    od.backward(go.double().cpu())
+    assert rel(of, od) < 1e-5 and rel(xf.grad, xd.grad) < 1e-5
+    # bare MessagePassing, reference KAT (tests/layers/conv/test_message_passing.py:12-24)
+    mp = MessagePassing()
+    xk = torch.arange(0, 8, dtype=torch.float32, device=DEV).reshape(4, 2)
+    eik = torch.tensor([[0, 1, 2, 2, 3], [1, 2, 1, 0, 3]], device=DEV)
+    assert mp.propagate(xk, eik, aggr='sum').cpu().tolist() == [[4.0, 5.0], [4.0, 6.0], [2.0, 3.0], [6.0, 7.0]]
+    assert mp.propagate(xk, eik, aggr='mean').cpu().tolist() == [[4.0, 5.0], [2.0, 3.0], [2.0, 3.0], [6.0, 7.0]]
+    assert mp.propagate(xk, eik, aggr='max').cpu().tolist() == [[4.0, 5.0], [4.0, 5.0], [2.0, 3.0], [6.0, 7.0]]
+    mp.fused = False
+    assert mp.propagate(xk, eik, aggr='sum').cpu().tolist() == [[4.0, 5.0], [4.0, 6.0], [2.0, 3.0], [6.0, 7.0]]
