@@ -33,6 +33,8 @@ WORKLOADS = {
     # name: (N, E incl. self loops, K, description)
     'c3': (2449029, 123718280, 100, 'GCN aggregation fwd+bwd, synthetic ogbn-products shape (2.45M nodes / 123.7M edges / feat 100)'),
     'c2': (1000000, 50000000, 128, 'gspmm fwd+bwd microbench, synthetic 1M nodes / 50M edges / feat 128'),
+    # per-GPU shard of the ogbn-papers100M shape (111M nodes / 1.6B edges / feat 128 over 8 GPUs); weak scaling
+    'c5part': (13882495, 201960734, 128, 'GCN aggregation fwd+bwd, 1-D node partition + halo all-to-all, ogbn-papers100M shape per-GPU shard (13.9M nodes / 202M edges / feat 128 per GPU)'),
 }
 
 
@@ -43,7 +45,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
-    ap.add_argument('--graph', default='rmat', choices=['rmat', 'uniform'])
+    ap.add_argument('--graph', default='rmat', choices=['rmat', 'uniform', 'block'],
+                    help='block (c5part only): 80%% of the edges have a source on the owning GPU')
     ap.add_argument('--dtype', default='f32', choices=['f32', 'bf16'])
     ap.add_argument('--scale', type=float, default=1.0, help='shrink N and E (debug only; reported in config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -371,9 +374,111 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_c5part(args):
+    """Partitioned full-graph aggregation (gammagl_b200/partition.py): every rank owns n nodes and the E_g edges that
+    point into them; one step = forward (halo all-to-all + SpMM) + backward (SpMM^T + reverse all-to-all + add)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    else:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29531')
+        dist.init_process_group('gloo', rank=0, world_size=1)
+    from gammagl_b200 import _lib, mpops, partition as P
+    _lib.load()
+    n, Eg, K, desc = WORKLOADS['c5part']
+    n, Eg = int(n * args.scale), int(Eg * args.scale)
+    N = n * world
+    kind = 'uniform' if args.graph == 'rmat' else args.graph
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    lo, hi = P.owned_range(N, world, rank)
+    dst = torch.randint(lo, hi, (Eg,), generator=g, device=dev)
+    src = torch.randint(0, N, (Eg,), generator=g, device=dev)
+    if kind == 'block':
+        loc = torch.rand(Eg, generator=g, device=dev) < 0.8
+        src = torch.where(loc, torch.randint(lo, hi, (Eg,), generator=g, device=dev), src)
+        del loc
+    ei = torch.stack([src, dst])
+    del src, dst
+    w = torch.rand(Eg, generator=g, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    plan = P.HaloPlan(ei, N)
+    plan.csr()
+    torch.cuda.synchronize()
+    plan_ms = (time.perf_counter() - t0) * 1e3
+    del ei
+    x = torch.randn(hi - lo, K, generator=g, device=dev).requires_grad_(True)
+    gout = torch.randn(hi - lo, K, generator=g, device=dev)
+
+    def step():
+        x.grad = None
+        P.dist_gspmm_sum(plan, x, w).backward(gout)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.15)
+    mpops.PROFILE = []
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    prof, mpops.PROFILE = mpops.PROFILE, None
+    clocks = sampler.stop()
+    t = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
+    halo = torch.tensor([float(plan.n_halo)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(halo, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    kern_ms = [a.elapsed_time(b) for (_, a, b) in prof]
+    kavg = sum(kern_ms) / max(1, len(kern_ms))
+    alg = Eg * (K * 4 + 8) + (hi - lo) * (K * 4 + 4)
+    peak, peak_src = measured_peak()
+    if rank == 0:
+        line = {
+            'metric': 'edges aggregated/sec (SpMM+scatter fwd+bwd)', 'value': world * 2 * Eg / (ms * 1e-3), 'unit': 'edges/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': desc, 'graph': kind, 'N_total': N, 'E_total': Eg * world, 'K': K, 'scale': args.scale,
+                       'parallelism': '1-D node partition x%d, halo all-to-all (NCCL) per pass' % world,
+                       'halo_rows_per_gpu_max': int(halo.item()), 'halo_bytes_per_pass_per_gpu': int(halo.item()) * K * 4,
+                       'plan_build_ms': plan_ms, 'l2': 'inputs exceed the 126 MB L2; no explicit flush'},
+            'roofline': {'bound': 'hbm', 'achieved': alg / (kavg * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                         'frac': alg / (kavg * 1e-3) / 1e9 / peak, 'traffic': None, 'kernel': 'spmm_ring_kernel (local SpMM only)',
+                         'algorithmic_bytes_per_launch': alg, 'avg_launch_ms': kavg, 'peak_source': peak_src},
+            'exchange': {'ms_per_step_not_in_spmm': ms - 2 * kavg,
+                         'note': 'pack + all_to_all + index_add, forward and backward; not overlapped with the SpMM in round 1'},
+            'e2e': None, 'cpu_baseline': None, 'gpu_launches': int(launches), 'clocks': clocks,
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.workload == 'c5part':
+        run_c5part(a)
     else:
         run_b200(a)
