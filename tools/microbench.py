@@ -1,0 +1,92 @@
+"""Per-operator microbenchmarks on one B200 (CUDA events, 5 warm-ups + 10 reps, median): time, edges/s and achieved
+algorithmic GB/s (SURVEY.md 8d formulas) for every kernel on the path.  Output: one JSON object per line.
+Usage: python tools/microbench.py [c2|c3|c4]"""
+import json
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, '.')
+import bench  # noqa: E402
+from gammagl_b200 import _lib, mpops  # noqa: E402
+from gammagl_b200.csr import build_csr, graph_of  # noqa: E402
+
+dev = torch.device('cuda', 0)
+PEAK = bench.measured_peak()[0]
+
+
+def timeit(fn, reps=10, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def report(name, ms, E, bytes_alg, **kw):
+    print(json.dumps(dict(op=name, ms=round(ms, 4), edges_per_s=E / ms * 1e3, alg_GBps=bytes_alg / ms / 1e6,
+                          frac_of_measured_hbm=bytes_alg / ms / 1e6 / PEAK, **kw)), flush=True)
+
+
+def main(cfg):
+    if cfg == 'c4':      # Reddit shape, GAT 8 heads x 8 channels
+        N, E, H, C = 232965, 114615892, 8, 8
+    elif cfg == 'c2':
+        N, E, H, C = 1000000, 50000000, 8, 16
+    else:
+        N, E, H, C = 2449029, 123718280, 4, 25
+    K = H * C
+    ei = bench.gen_graph(torch, N, E, 'rmat', 7, dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(N, K, generator=g, device=dev)
+    w = torch.rand(E, generator=g, device=dev)
+    wh = torch.rand(E, H, generator=g, device=dev)
+    gr = graph_of(ei, N)
+    s = 4
+    spmm_b = E * (K * s + 8) + N * (K * s + 4)
+    report('csr_build(dst)', timeit(lambda: build_csr(ei[1], ei[0], N), reps=5, warm=2), E, E * 16 * 4, cfg=cfg)
+    fwd = gr.fwd
+    bwd = gr.bwd
+    for red, code in (('sum', _lib.GGL_SUM), ('mean', _lib.GGL_MEAN), ('max', _lib.GGL_MAX)):
+        report('gspmm_%s fwd K=%d' % (red, K), timeit(lambda: mpops.spmm_csr(fwd, fwd.col, x, code, w=w, wperm=fwd.perm,
+               want_arg=(red == 'max'))), E, spmm_b + (N * K * 8 if red == 'max' else 0), cfg=cfg)
+    report('gspmm_sum bwd_x (transposed CSR)', timeit(lambda: mpops.spmm_csr(bwd, bwd.col, x, _lib.GGL_SUM, w=w, wperm=bwd.perm)), E, spmm_b, cfg=cfg)
+    report('gspmm_sum fwd unweighted', timeit(lambda: mpops.spmm_csr(fwd, fwd.col, x, _lib.GGL_SUM)), E, spmm_b - 4 * E, cfg=cfg)
+    xb = x.bfloat16()
+    report('gspmm_sum fwd bf16', timeit(lambda: mpops.spmm_csr(fwd, fwd.col, xb, _lib.GGL_SUM, w=w, wperm=fwd.perm)), E,
+           E * (K * 2 + 8) + N * (K * 2 + 4), cfg=cfg)
+    # bspmm family (GAT)
+    bs_b = E * (K * s + 4 * H + 4) + N * K * s
+    report('bspmm fwd H=%d C=%d' % (H, C), timeit(lambda: mpops.spmm_csr(fwd, fwd.col, x, _lib.GGL_SUM, w=wh, wperm=fwd.perm, heads=H)), E, bs_b, cfg=cfg)
+    report('bspmm bwd_x', timeit(lambda: mpops.spmm_csr(bwd, bwd.col, x, _lib.GGL_SUM, w=wh, wperm=bwd.perm, heads=H)), E, bs_b, cfg=cfg)
+    lib = _lib.load()
+    from gammagl_b200.csr import _ptr, _stream
+    gw = torch.empty(E, H, device=dev)
+    report('bspmm bwd_w (SDDMM)', timeit(lambda: _lib.check(lib.gglb200_bspmm_bwd_w(_ptr(fwd.rowptr), _ptr(fwd.col), _ptr(fwd.perm), _ptr(x), _ptr(x), _ptr(gw), N, E, H, C, _stream(dev)))), E, bs_b, cfg=cfg)
+    alpha = torch.empty(E, H, device=dev)
+    report('edge_softmax fwd H=%d' % H, timeit(lambda: _lib.check(lib.gglb200_edge_softmax_fwd(_ptr(fwd.rowptr), _ptr(fwd.perm), _ptr(wh), _ptr(alpha), N, E, H, _stream(dev)))), E, E * (2 * 4 * H + 4), cfg=cfg)
+    gl = torch.empty(E, H, device=dev)
+    report('edge_softmax bwd', timeit(lambda: _lib.check(lib.gglb200_edge_softmax_bwd(_ptr(fwd.rowptr), _ptr(fwd.perm), _ptr(alpha), _ptr(wh), _ptr(gl), N, E, H, _stream(dev)))), E, E * (3 * 4 * H + 4), cfg=cfg)
+    # segment ops on a materialised message (the reference's unfused path); K limited so that [E,K] fits comfortably
+    Ks = min(K, 32)
+    msg = torch.randn(E, Ks, generator=g, device=dev)
+    dst = ei[1].contiguous()
+    mpops.unsorted_segment_sum(msg, dst, N)  # builds + caches the segment CSR
+    seg_b = E * (Ks * s + 8) + N * Ks * s
+    for red, f in (('sum', mpops.unsorted_segment_sum), ('mean', mpops.unsorted_segment_mean), ('max', mpops.unsorted_segment_max)):
+        report('unsorted_segment_%s fwd K=%d' % (red, Ks), timeit(lambda: f(msg, dst, N)), E, seg_b, cfg=cfg)
+    go = torch.randn(N, Ks, generator=g, device=dev)
+    m2 = msg.clone().requires_grad_(True)
+    o = mpops.unsorted_segment_sum(m2, dst, N)
+    report('unsorted_segment_sum bwd (row gather)', timeit(lambda: o.backward(go, retain_graph=True)), E, seg_b, cfg=cfg)
+    ones = torch.ones(E, device=dev)
+    report('degree: unsorted_segment_sum(ones[E]) K=1', timeit(lambda: mpops.unsorted_segment_sum(ones, dst, N)), E, E * 12 + N * 4, cfg=cfg)
+
+
+if __name__ == '__main__':
+    main(sys.argv[1] if len(sys.argv) > 1 else 'c3')
