@@ -32,20 +32,10 @@ int tile_edges() {
   return v;
 }
 
-int tune_ring_warps() {
-  static int v = [] {
-    const char* e = getenv("GGLB200_RING_WARPS");
-    return (e && e[0] == '4') ? 4 : 1;
-  }();
-  return v;
-}
-
-int tune_ring() {  // 1 = bulk-copy ring (default), 2 = cp.async (LDGSTS) ring, 0 = register-staged kernels
+int tune_ring() {  // 1 = bulk-copy ring (default), 0 = register-staged kernels (env GGLB200_RING=none)
   static int v = [] {
     const char* e = getenv("GGLB200_RING");
-    if (e && e[0] == 'n') return 0;
-    if (e && e[0] == 'l') return 2;
-    return 1;
+    return (e && e[0] == 'n') ? 0 : 1;
   }();
   return v;
 }
@@ -81,10 +71,10 @@ extern "C" size_t gglb200_spmm_workspace_bytes(int64_t E, int64_t K, int reduce)
 
 extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
                                 const float* w, const int32_t* wperm, int32_t heads, const void* x, void* out,
-                                int64_t* arg, int64_t arg_empty, int64_t n_rows, int64_t E, int64_t K, int dtype,
+                                int64_t* arg, int64_t arg_empty, int64_t n_rows, int64_t n_src, int64_t E, int64_t K, int dtype,
                                 void* workspace, size_t workspace_bytes, void* stream) {
   GGL_REQUIRE(reduce == GGL_SUM || reduce == GGL_MEAN || reduce == GGL_MAX, GGL_EINVAL, "spmm: unknown reduce %d", reduce);
-  GGL_REQUIRE(n_rows >= 0 && E >= 0 && K >= 0, GGL_EINVAL, "spmm: negative size");
+  GGL_REQUIRE(n_rows >= 0 && n_src >= 0 && E >= 0 && K >= 0, GGL_EINVAL, "spmm: negative size");
   GGL_REQUIRE(n_rows < INT32_MAX && E < INT32_MAX, GGL_ERANGE, "spmm: n_rows/E exceed int32");
   if (n_rows == 0 || K == 0) return GGL_OK;
   GGL_REQUIRE(rowptr && out && plan, GGL_EINVAL, "spmm: rowptr/out/plan must not be NULL");
@@ -95,7 +85,7 @@ extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t
 
   SpmmArgs p;
   p.reduce = reduce; p.rowptr = rowptr; p.col = col; p.plan = plan; p.w = w; p.wperm = wperm; p.heads = heads;
-  p.x = x; p.out = out; p.arg = arg; p.arg_empty = arg_empty; p.n_rows = n_rows; p.E = E; p.K = K;
+  p.x = x; p.out = out; p.arg = arg; p.arg_empty = arg_empty; p.n_rows = n_rows; p.E = E; p.K = K; p.n_src = n_src;
   p.part_val = nullptr; p.part_arg = nullptr; p.stream = (cudaStream_t)stream;
   p.n_tiles = plan_n_tiles(E);
   p.tile_row = plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E));

@@ -48,6 +48,7 @@ struct SpmmArgs {
   int64_t* arg;             // MAX only, may be NULL
   int64_t arg_empty;
   int64_t n_rows, E, K;
+  int64_t n_src;            // rows of x (bounds the superset copies of unaligned rows)
   void* part_val;           // workspace: [ws_chunks, K] acc_t
   int32_t* part_arg;        // workspace: [ws_chunks, K] int32 (MAX)
   cudaStream_t stream;
@@ -311,33 +312,35 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) spmm_tiles_kernel(cons
   while (rc.r < rc.r_end) next_row();  // last row of the tile + trailing empty rows
 }
 
-// ---- kernel 1b: shared-memory ring tile kernel (lanes own 16 bytes of a row) --------------------------------
-// Each lane group owns a ring of STAGES slots x R feature rows in shared memory and keeps it LAG = STAGES-1
-// slots ahead of consumption, so up to LAG*R rows per group are in flight without holding registers.
-//   COPY == 1 (default): one lane per row issues a bulk async copy (cp.async.bulk, the TMA-class UBLKCP path:
-//             one instruction moves the whole 16-byte-aligned row; completion is counted in bytes on an
-//             mbarrier per stage);
-//   COPY == 0: every lane copies its own 16 bytes with cp.async (LDGSTS) and waits with wait_group.
-// Consumption is in stream order from shared memory (ld.shared.v4 of the lane's own 16-byte column), with a
-// branch-free fast path for slots that lie inside one row.  Groups [0, ws_chunks) of the launch reduce
-// long-row chunks into partials, the remaining groups are edge tiles.
+// ---- kernel 1b: shared-memory ring tile kernel -------------------------------------------------------------------
+// Each lane group owns a ring of STAGES slots x R feature rows in shared memory and keeps it LAG = STAGES-1 slots
+// ahead of consumption, so up to LAG*R rows per group are in flight without holding registers.  One lane per row
+// issues a bulk async copy (cp.async.bulk.shared::cluster.global -- the TMA-class UBLKCP path: one instruction moves
+// the whole row; completion is counted in bytes on one mbarrier per stage).  Consumption is in stream order from
+// shared memory (each lane reads its own VB-byte column), with a branch-free fast path for slots inside one row.
+//
+// Rows that are not 16-byte aligned / sized (bf16 K=100 -> 200 B, fp32 K=47 -> 188 B ...) are fetched as the aligned
+// 16-byte SUPERSET [addr & ~15, +CB) with CB = roundup16(row bytes + 15); lanes then read at offset (addr & 15).  The
+// last one or two rows of x, whose superset would cross the end of the tensor, are not staged: their lanes read
+// global memory directly at consume time (`a0 > lim`).
+//
+// Blocks are ONE warp: the hardware block scheduler is the dynamic tile scheduler -- a finished or empty tile
+// frees its ring at once, so skewed graphs do not park shared memory behind one long tile (RMAT 13.1 -> 8.4 ms).
+// Groups [0, ws_chunks) of the launch reduce long-row chunks into partials, the remaining groups are edge tiles.
 template <int LPR> struct RingCfg {
   static constexpr int R = LPR >= 8 ? 8 : LPR;                      // rows per slot
   static constexpr int STAGES = LPR >= 16 ? 4 : 3;                  // LAG*R <= 2*LPR (index batches A,B,C)
   static constexpr int LAG = STAGES - 1;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -352,42 +355,58 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> lds_pack(uint32_t addr) {
+  Pack<T, VEC> v;
+  constexpr int B = sizeof(T) * VEC;
+  uint32_t* q = reinterpret_cast<uint32_t*>(&v);
+  if constexpr (B == 16) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "r"(addr));
+  else if constexpr (B == 8) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(q[0]), "=r"(q[1]) : "r"(addr));
+  else if constexpr (B == 4) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q[0]) : "r"(addr));
+  else {
+    uint16_t h;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+    *reinterpret_cast<uint16_t*>(&v) = h;
+  }
+  return v;
+}
 
-template <typename T, int VEC, int LPR, int WMODE, bool ISMAX, int COPY, int kRingWarps>
-__global__ void __launch_bounds__(kRingWarps * 32) spmm_ring_kernel(const SpmmArgs p, const int32_t pitch /* bytes per row slot */) {
-  static_assert(sizeof(T) * VEC == 16, "ring kernel moves 16 bytes per lane");
+template <typename T, int VEC, int LPR, int WMODE, bool ISMAX>
+__global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const int32_t pitch /* bytes per row slot */,
+                                                       const uint64_t x_end_al /* align_down(x + n_src*K*sizeof(T), 16) */) {
   using acc_t = typename Elem<T>::acc_t;
   using Cfg = RingCfg<LPR>;
+  constexpr int VB = (int)sizeof(T) * VEC;   // bytes a lane owns per row
+  constexpr bool ALIGNED = VB == 16;         // rows are 16-byte aligned and sized: no superset, no tail rows
   constexpr int GPW = 32 / LPR, R = Cfg::R, STAGES = Cfg::STAGES, LAG = Cfg::LAG;
   extern __shared__ __align__(16) unsigned char ring_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int sub = lane & (LPR - 1);
   const int gbase = lane & ~(LPR - 1);
   const unsigned gmask = group_mask<LPR>(lane);
-  const int gib = warp * GPW + lane / LPR;  // group index in the block
-  const int64_t g = (int64_t)blockIdx.x * (kRingWarps * GPW) + gib;
+  const int gib = lane / LPR;  // group index in the (one-warp) block
+  const int64_t g = (int64_t)blockIdx.x * GPW + gib;
   const int32_t kcol = ((int32_t)blockIdx.y * LPR + sub) * VEC;
   const bool col_active = kcol < p.K;
   const int32_t head = (WMODE == 2 && col_active) ? kcol / (int32_t)(p.K / p.heads) : 0;
   const int64_t K = p.K;
   const T* xt = reinterpret_cast<const T*>(p.x) + (int64_t)blockIdx.y * LPR * VEC;  // first column of this column tile
-  const T* xk = reinterpret_cast<const T*>(p.x) + kcol;
-  // bytes of one row inside this column tile (multiple of 16)
-  const uint32_t rowb = (uint32_t)min((int64_t)LPR * 16, K * (int64_t)sizeof(T) - (int64_t)blockIdx.y * LPR * 16);
+  // bytes of one row inside this column tile, and the bytes copied per row
+  const uint32_t rowb = (uint32_t)min((int64_t)LPR * VB, K * (int64_t)sizeof(T) - (int64_t)blockIdx.y * LPR * VB);
+  const uint32_t cb = ALIGNED ? rowb : ((rowb + 15u + 15u) & ~15u);
+  const uint64_t lim = x_end_al - cb;  // a superset copy starting above `lim` would cross the end of x
 
-  // shared memory: data rings of all groups, then (COPY==1) STAGES mbarriers per group
+  // shared memory: data rings of all groups, then STAGES mbarriers per group
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(ring_smem);
   const uint32_t ring = smem0 + (uint32_t)(gib * (STAGES * R)) * pitch;
-  const uint32_t bars = smem0 + (uint32_t)(kRingWarps * GPW * STAGES * R) * pitch + (uint32_t)gib * STAGES * 8;
-  if constexpr (COPY == 1) {
-    if (sub == 0) {
+  const uint32_t bars = smem0 + (uint32_t)(GPW * STAGES * R) * pitch + (uint32_t)gib * STAGES * 8;
+  if (sub == 0) {
 #pragma unroll
-      for (int i = 0; i < STAGES; ++i) mbar_init(bars + i * 8, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncwarp(gmask);
+    for (int i = 0; i < STAGES; ++i) mbar_init(bars + i * 8, ALIGNED ? 1 : R);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  __syncwarp(gmask);
 
   // ---- what does this group stream? ----
   int32_t r0 = 0, r1 = 0, e0, e_end;
@@ -441,22 +460,23 @@ __global__ void __launch_bounds__(kRingWarps * 32) spmm_ring_kernel(const SpmmAr
       const int32_t d = pos0 / LPR - bA;  // 0, 1 or 2
       const int32_t colsrc = d == 0 ? A.col : (d == 1 ? B.col : C.col);
       const uint32_t dst = ring + (uint32_t)((s % STAGES) * R) * pitch;
-      if constexpr (COPY == 1) {
-        const uint32_t bar = bars + (uint32_t)(s % STAGES) * 8;
-        const int32_t nv = min(R, n - pos0);
-        const int32_t c = __shfl_sync(gmask, colsrc, gbase + ((pos0 + sub) & (LPR - 1)));  // lane u copies row u
-        __syncwarp(gmask);  // every lane of the group has finished reading this stage (slot s - STAGES)
+      const uint32_t bar = bars + (uint32_t)(s % STAGES) * 8;
+      const int32_t nv = min(R, n - pos0);
+      const int32_t c = __shfl_sync(gmask, colsrc, gbase + ((pos0 + sub) & (LPR - 1)));  // lane u copies row u
+      __syncwarp(gmask);  // every lane of the group has finished reading this stage (slot s - STAGES)
+      if constexpr (ALIGNED) {
         if (sub == 0) mbar_arrive_expect_tx(bar, (uint32_t)nv * rowb);
         if (sub < nv) bulk_copy_g2s(dst + (uint32_t)sub * pitch, xt + (int64_t)c * K, rowb, bar);
-      } else {
-#pragma unroll
-        for (int u = 0; u < R; ++u) {
-          const int32_t c = __shfl_sync(gmask, colsrc, gbase + ((pos0 + u) & (LPR - 1)));
-          if (pos0 + u < n && col_active) cp_async16(dst + u * pitch + sub * 16, xk + (int64_t)c * K);
+      } else if (sub < R) {
+        const uint64_t a0 = (uint64_t)(xt + (int64_t)c * K) & ~(uint64_t)15;
+        if (sub < nv && a0 <= lim) {
+          mbar_arrive_expect_tx(bar, cb);
+          bulk_copy_g2s(dst + (uint32_t)sub * pitch, (const void*)a0, cb, bar);
+        } else {
+          mbar_arrive(bar);
         }
       }
     }
-    if constexpr (COPY == 0) cp_async_commit();
   };
 
 #pragma unroll
@@ -474,26 +494,31 @@ __global__ void __launch_bounds__(kRingWarps * 32) spmm_ring_kernel(const SpmmAr
 #pragma unroll
     for (int u = 0; u < R; ++u) {
       wv[u] = 1.f; cc[u] = 0;
-      if constexpr (ISMAX) cc[u] = __shfl_sync(gmask, A.col, gbase + ((pos0 + u) & (LPR - 1)));
+      if constexpr (ISMAX || !ALIGNED) cc[u] = __shfl_sync(gmask, A.col, gbase + ((pos0 + u) & (LPR - 1)));
       if constexpr (WMODE == 1) wv[u] = __shfl_sync(gmask, A.w, gbase + ((pos0 + u) & (LPR - 1)));
       if constexpr (WMODE == 2) {
         const int32_t eid = __shfl_sync(gmask, A.eid, gbase + ((pos0 + u) & (LPR - 1)));
         wv[u] = __ldg(p.w + (int64_t)eid * p.heads + head);
       }
     }
-    if constexpr (COPY == 1) mbar_wait(bars + (uint32_t)(s % STAGES) * 8, (uint32_t)(s / STAGES) & 1u);
-    else cp_async_wait<LAG>();  // slot s has landed (only this lane's own copies matter)
-    const uint32_t src = ring + (uint32_t)((s % STAGES) * R) * pitch + (uint32_t)sub * 16;
+    mbar_wait(bars + (uint32_t)(s % STAGES) * 8, (uint32_t)(s / STAGES) & 1u);
+    const uint32_t src = ring + (uint32_t)((s % STAGES) * R) * pitch + (uint32_t)sub * VB;
+    // the lane's VB bytes of the row at stream position pos0+u
+    auto fetch = [&](int u) {
+      if constexpr (ALIGNED) {
+        return lds_pack<T, VEC>(src + u * pitch);
+      } else {
+        const T* rp = xt + (int64_t)cc[u] * K;
+        const uint64_t a = (uint64_t)rp;
+        if ((a & ~(uint64_t)15) <= lim) return lds_pack<T, VEC>(src + u * pitch + (uint32_t)(a & 15));
+        return ld_gather<T, VEC>(rp + sub * VEC);  // tail row of x: not staged
+      }
+    };
     if (pos0 + R <= n && e0 + pos0 + R <= rc.cur_end) {
       // fast path: the whole slot lies inside the current row
       if (col_active) {
 #pragma unroll
-        for (int u = 0; u < R; ++u) {
-          Pack<T, VEC> v;
-          uint32_t* q = reinterpret_cast<uint32_t*>(&v);
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "r"(src + u * pitch));
-          accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v, wv[u], cc[u]);
-        }
+        for (int u = 0; u < R; ++u) accumulate<T, VEC, WMODE, ISMAX>(acc, argv, fetch(u), wv[u], cc[u]);
       }
     } else {
 #pragma unroll
@@ -501,17 +526,11 @@ __global__ void __launch_bounds__(kRingWarps * 32) spmm_ring_kernel(const SpmmAr
         const int32_t pos = pos0 + u;
         if (pos < n) {  // group-uniform
           while (e0 + pos == rc.cur_end) next_row();
-          if (col_active) {
-            Pack<T, VEC> v;
-            uint32_t* q = reinterpret_cast<uint32_t*>(&v);
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "r"(src + u * pitch));
-            accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v, wv[u], cc[u]);
-          }
+          if (col_active) accumulate<T, VEC, WMODE, ISMAX>(acc, argv, fetch(u), wv[u], cc[u]);
         }
       }
     }
   }
-  if constexpr (COPY == 0) cp_async_wait<0>();
   if (chunk >= 0) {
     if (col_active) {
       acc_t* pv = reinterpret_cast<acc_t*>(p.part_val) + chunk * K + kcol;
@@ -597,33 +616,30 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_finalize_kernel(cons
 }
 
 // ---- host-side launch ------------------------------------------------------------------------------
-int tune_ring();        // tuning knob (env GGLB200_RING = bulk (default) | ldgsts | none), api.cu
-int tune_ring_warps();  // tuning knob (env GGLB200_RING_WARPS = 1 (default) | 4): warps per block of the ring kernel
+int tune_ring();  // tuning knob (env GGLB200_RING = bulk (default) | none -> register-staged kernels), api.cu
 
-// One-warp blocks make the hardware block scheduler the dynamic tile scheduler: a warp that finishes (or finds
-// an empty tile) frees its ring immediately, so skewed graphs do not hold shared memory behind one long tile.
-template <typename T, int VEC, int LPR, int WMODE, bool ISMAX, int WARPS>
-int launch_ring(const SpmmArgs& p, int tiles, int mode) {
+template <typename T, int VEC, int LPR, int WMODE, bool ISMAX>
+int launch_ring(const SpmmArgs& p, int tiles) {
   constexpr int GPW = 32 / LPR;
+  constexpr int VB = (int)sizeof(T) * VEC;
   using Cfg = RingCfg<LPR>;
-  const int64_t rowbytes = ((p.K * (int64_t)sizeof(T) + 15) / 16) * 16;
-  const int32_t pitch = (int32_t)(rowbytes < LPR * 16 ? rowbytes : LPR * 16);
-  const size_t smem = (size_t)WARPS * GPW * Cfg::STAGES * Cfg::R * pitch + (size_t)WARPS * GPW * Cfg::STAGES * 8;
+  const int64_t rowbytes = p.K * (int64_t)sizeof(T);
+  const int64_t tileb = rowbytes < (int64_t)LPR * VB ? rowbytes : (int64_t)LPR * VB;   // widest column tile
+  const int32_t pitch = (int32_t)(VB == 16 ? tileb : ((tileb + 15 + 15) & ~(int64_t)15));
+  const size_t smem = (size_t)GPW * Cfg::STAGES * Cfg::R * pitch + (size_t)GPW * Cfg::STAGES * 8;
+  GGL_REQUIRE(smem <= 200 * 1024, GGL_EUNSUPPORTED, "spmm: ring of %zu bytes does not fit shared memory", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    GGL_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 1, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    GGL_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 0, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    GGL_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const int64_t groups = p.n_tiles + (p.has_long ? p.ws_chunks : 0);
-  const int64_t blocks = (groups + (int64_t)WARPS * GPW - 1) / ((int64_t)WARPS * GPW);
+  const int64_t blocks = (groups + GPW - 1) / GPW;
   GGL_REQUIRE(blocks < INT32_MAX, GGL_EUNSUPPORTED, "spmm: grid too large");
   SpmmArgs q = p;
   if (!p.has_long) q.ws_chunks = 0;
-  if (mode == 1)
-    spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 1, WARPS><<<dim3((unsigned)blocks, tiles), WARPS * 32, smem, p.stream>>>(q, pitch);
-  else
-    spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX, 0, WARPS><<<dim3((unsigned)blocks, tiles), WARPS * 32, smem, p.stream>>>(q, pitch);
+  const uint64_t x_end_al = ((uint64_t)p.x + (uint64_t)p.n_src * (uint64_t)rowbytes) & ~(uint64_t)15;
+  spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX><<<dim3((unsigned)blocks, tiles), 32, smem, p.stream>>>(q, pitch, x_end_al);
   GGL_LAUNCHED("spmm_ring");
   if (p.has_long) {
     spmm_finalize_kernel<T, VEC, LPR, ISMAX><<<dim3(kSMs, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(q);
@@ -637,12 +653,10 @@ int launch_config(const SpmmArgs& p) {
   constexpr int GPW = 32 / LPR;
   const int tiles = (int)((p.K + (int64_t)LPR * VEC - 1) / ((int64_t)LPR * VEC));
   GGL_REQUIRE(tiles <= 65535, GGL_EUNSUPPORTED, "spmm: K=%lld needs too many column tiles", (long long)p.K);
-  if constexpr (sizeof(T) * VEC == 16 && LPR >= 4) {
-    const int mode = tune_ring();
-    if (mode != 0) {
-      if (tune_ring_warps() == 4) return launch_ring<T, VEC, LPR, WMODE, ISMAX, 4>(p, tiles, mode);
-      return launch_ring<T, VEC, LPR, WMODE, ISMAX, 1>(p, tiles, mode);
-    }
+  // floating rows of at least 4 lanes stream through the shared-memory ring; the rest (K <= 4 elements per row,
+  // f64, integers) through the register-staged kernels
+  if constexpr (Elem<T>::is_float && sizeof(T) <= 4 && LPR >= 4) {
+    if (tune_ring() != 0) return launch_ring<T, VEC, LPR, WMODE, ISMAX>(p, tiles);
   }
   const int64_t groups_per_block = (int64_t)kWarpsPerBlock * GPW;
   const int64_t blocks = (p.n_tiles + groups_per_block - 1) / groups_per_block;
@@ -685,7 +699,33 @@ static inline int lpr_for(int64_t K, int vec) {
   return l;
 }
 
-// entry points per element type (explicitly instantiated in spmm_f32.cu / spmm_bf16.cu / spmm_misc.cu)
+// vector-width dispatch shared by the 16-bit floating types
+template <typename T>
+int launch_16bit(const SpmmArgs& p) {
+  const int64_t K = p.K;
+  const int64_t C = p.heads > 1 ? K / p.heads : K;
+  const uintptr_t al = (uintptr_t)p.x | (uintptr_t)p.out;
+  int vec = 1;
+  if (K > 4) {
+    if (K % 8 == 0 && C % 8 == 0 && al % 16 == 0) vec = 8;
+    else if (K % 4 == 0 && C % 4 == 0 && al % 8 == 0) vec = 4;
+    else if (K % 2 == 0 && C % 2 == 0 && al % 4 == 0) vec = 2;
+  }
+  const int lpr = lpr_for(K, vec);
+  if (vec == 8) {
+    if (lpr <= 4) return launch_modes<T, 8, 4>(p, true);
+    if (lpr == 8) return launch_modes<T, 8, 8>(p, true);
+    if (lpr == 16) return launch_modes<T, 8, 16>(p, true);
+    return launch_modes<T, 8, 32>(p, true);
+  }
+  if (vec == 4) return launch_modes<T, 4, 32>(p, true);
+  if (vec == 2) return launch_modes<T, 2, 32>(p, true);
+  if (lpr == 1) return launch_modes<T, 1, 1>(p, true);
+  if (lpr <= 4) return launch_modes<T, 1, 4>(p, true);
+  return launch_modes<T, 1, 32>(p, true);
+}
+
+// entry points per element type (explicitly instantiated in spmm_f32.cu / spmm_bf16.cu / spmm_f16.cu / spmm_misc.cu)
 template <typename T> int launch_spmm(const SpmmArgs& p);
 
 }  // namespace ggl

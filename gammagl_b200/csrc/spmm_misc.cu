@@ -1,5 +1,5 @@
 // spmm_misc.cu -- the remaining element types the reference's segment ops accept
-// (AT_DISPATCH_ALL_TYPES_AND2(Half,BFloat16), cpu/segment_sum_cpu.cpp:32-34): f16, f64 and the integer
+// (AT_DISPATCH_ALL_TYPES_AND2(Half,BFloat16), cpu/segment_sum_cpu.cpp:32-34): f64 and the integer
 // types (degree() counts in int64, gammagl/utils/degree.py:30-40).  Scalar lanes; correctness first.
 #include "spmm_impl.cuh"
 
@@ -13,7 +13,6 @@ static int launch_scalar(const SpmmArgs& p) {
   return launch_modes<T, 1, 32>(p, W);
 }
 
-template <> int launch_spmm<__half>(const SpmmArgs& p) { return launch_scalar<__half, true>(p); }
 template <> int launch_spmm<double>(const SpmmArgs& p) { return launch_scalar<double, false>(p); }
 template <> int launch_spmm<int8_t>(const SpmmArgs& p) { return launch_scalar<int8_t, false>(p); }
 template <> int launch_spmm<uint8_t>(const SpmmArgs& p) { return launch_scalar<uint8_t, false>(p); }

@@ -58,7 +58,7 @@ def spmm_csr(csr, col, x2d, reduce, w=None, wperm=None, heads=1, want_arg=False,
             ev0.record()
         _lib.check(lib.gglb200_spmm_csr(reduce, _ptr(csr.rowptr), _ptr(col), _ptr(csr.plan),
                                         _ptr(w), _ptr(wperm), heads, _ptr(x2d), _ptr(out), _ptr(arg), arg_empty,
-                                        n_rows, csr.E, K, _dtype_code(x2d), _ptr(ws), ws_bytes, _stream(dev)),
+                                        n_rows, x2d.shape[0], csr.E, K, _dtype_code(x2d), _ptr(ws), ws_bytes, _stream(dev)),
                    'spmm_csr')
         if PROFILE is not None:
             ev1 = torch.cuda.Event(enable_timing=True)

@@ -125,7 +125,8 @@ GGL_API int gglb200_permute_rows(const void* in, const int32_t* perm, void* out,
  *            [E]    when heads == 1   (gspmm,  cpu/spmm_sum_cpu.cpp:31-38)
  *            [E,H]  when heads == H   (bspmm,  cpu/bspmm_sum_cpu.cpp:43-55; K = H*C, head of k = k / C)
  *            indexed by i (already in CSR order) when wperm == NULL, else by wperm[i].
- *   x        [n_src, K] dtype, row major;  out [n_rows, K] dtype (written fully, no pre-zeroing needed)
+ *   x        [n_src, K] dtype, row major (every col[i] < n_src);  out [n_rows, K] dtype (written fully, no
+ *            pre-zeroing needed).  n_src bounds the 16-byte-aligned superset copies of unaligned rows.
  *   arg      NULL, or int64 [n_rows, K] (MAX only): col[i*] of the winning edge; `arg_empty` for
  *            rows without edges (segment_max: N, cpu/segment_max_cpu.cpp:27; spmm_max: 0,
  *            cpu/spmm_max_cpu.cpp:23-24).  For the segment ops col := perm, so this is the edge id.
@@ -145,7 +146,7 @@ GGL_API int    gglb200_spmm_csr(int reduce,
                         const int32_t* rowptr, const int32_t* col, const int32_t* plan,
                         const float* w, const int32_t* wperm, int32_t heads,
                         const void* x, void* out, int64_t* arg, int64_t arg_empty,
-                        int64_t n_rows, int64_t E, int64_t K, int dtype,
+                        int64_t n_rows, int64_t n_src, int64_t E, int64_t K, int dtype,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
