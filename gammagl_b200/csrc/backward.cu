@@ -18,17 +18,40 @@ static int grid_for(int64_t n, int block = 256) {
   return (int)g;
 }
 
-// Row gather, dtype-agnostic: rows are moved as W-byte words.  One warp per edge row, lanes over words.
-template <typename W>
+// Row gather, dtype-agnostic: rows are moved as W-byte words.  A group of LPR lanes (power of two >= words per row)
+// copies one edge row, 32/LPR rows per warp step, so narrow rows (K=32 fp32 = 8 uint4 words) still use every lane.
+template <typename W, int LPR>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const W* __restrict__ g, const int64_t* __restrict__ ids,
                                                           W* __restrict__ gx, int64_t E, int32_t words) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < E; e += warps) {
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane & (LPR - 1);
+  const int64_t groups = (int64_t)gridDim.x * (blockDim.x >> 5) * GPW;
+  for (int64_t e = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPR; e < E; e += groups) {
     const int64_t r = __ldg(ids + e);
     const W* src = g + r * words;
     W* dst = gx + e * words;
-    for (int32_t k = lane; k < words; k += 32) __stcs(dst + k, __ldg(src + k));
+    for (int32_t k = sub; k < words; k += LPR) __stcs(dst + k, __ldg(src + k));
+  }
+}
+
+template <typename W>
+static void launch_gather_rows(const void* g, const int64_t* ids, void* gx, int64_t E, int64_t words, cudaStream_t stream) {
+  int lpr = 1;
+  while (lpr < 32 && lpr < words) lpr <<= 1;
+  const int64_t warps = (E * lpr + 31) / 32;
+  int64_t grid = (warps + 7) / 8;
+  const int64_t cap = (int64_t)kSMs * 32;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  const W* gp = (const W*)g;
+  W* op = (W*)gx;
+  switch (lpr) {
+    case 1: gather_rows_kernel<W, 1><<<(int)grid, 256, 0, stream>>>(gp, ids, op, E, (int32_t)words); break;
+    case 2: gather_rows_kernel<W, 2><<<(int)grid, 256, 0, stream>>>(gp, ids, op, E, (int32_t)words); break;
+    case 4: gather_rows_kernel<W, 4><<<(int)grid, 256, 0, stream>>>(gp, ids, op, E, (int32_t)words); break;
+    case 8: gather_rows_kernel<W, 8><<<(int)grid, 256, 0, stream>>>(gp, ids, op, E, (int32_t)words); break;
+    case 16: gather_rows_kernel<W, 16><<<(int)grid, 256, 0, stream>>>(gp, ids, op, E, (int32_t)words); break;
+    default: gather_rows_kernel<W, 32><<<(int)grid, 256, 0, stream>>>(gp, ids, op, E, (int32_t)words); break;
   }
 }
 
@@ -149,16 +172,11 @@ extern "C" int gglb200_segment_gather_bwd(int reduce, const void* g, const int64
   if (reduce == GGL_SUM) {
     const int64_t rb = K * eb;
     const uintptr_t al = (uintptr_t)g | (uintptr_t)gx;
-    if (rb % 16 == 0 && al % 16 == 0)
-      gather_rows_kernel<uint4><<<grid, 256, 0, stream>>>((const uint4*)g, ids, (uint4*)gx, E, (int32_t)(rb / 16));
-    else if (rb % 8 == 0 && al % 8 == 0)
-      gather_rows_kernel<uint2><<<grid, 256, 0, stream>>>((const uint2*)g, ids, (uint2*)gx, E, (int32_t)(rb / 8));
-    else if (rb % 4 == 0 && al % 4 == 0)
-      gather_rows_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t*)g, ids, (uint32_t*)gx, E, (int32_t)(rb / 4));
-    else if (rb % 2 == 0 && al % 2 == 0)
-      gather_rows_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)g, ids, (uint16_t*)gx, E, (int32_t)(rb / 2));
-    else
-      gather_rows_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)g, ids, (uint8_t*)gx, E, (int32_t)rb);
+    if (rb % 16 == 0 && al % 16 == 0) launch_gather_rows<uint4>(g, ids, gx, E, rb / 16, stream);
+    else if (rb % 8 == 0 && al % 8 == 0) launch_gather_rows<uint2>(g, ids, gx, E, rb / 8, stream);
+    else if (rb % 4 == 0 && al % 4 == 0) launch_gather_rows<uint32_t>(g, ids, gx, E, rb / 4, stream);
+    else if (rb % 2 == 0 && al % 2 == 0) launch_gather_rows<uint16_t>(g, ids, gx, E, rb / 2, stream);
+    else launch_gather_rows<uint8_t>(g, ids, gx, E, rb, stream);
     GGL_LAUNCHED("gather_rows");
     return GGL_OK;
   }

@@ -271,8 +271,8 @@ class _BSpMM(torch.autograd.Function):
                 if x.dtype != torch.float32 or grad.dtype != torch.float32:
                     raise _lib.GglError('bspmm weight gradient is float32 only')
                 gw = torch.empty((g.E, H), dtype=torch.float32, device=dev)
-                _lib.check(lib.gglb200_bspmm_bwd_w(_ptr(g.fwd.rowptr), _ptr(g.fwd.col), _ptr(g.fwd.perm), _ptr(x), _ptr(grad),
-                                                   _ptr(gw), N, g.E, H, C, _stream(dev)), 'bspmm_bwd_w')
+                _lib.check(lib.gglb200_bspmm_bwd_w(_ptr(g.fwd.rowptr), _ptr(g.fwd.col), _ptr(g.fwd.perm), _ptr(g.fwd.plan),
+                                                   _ptr(x), _ptr(grad), _ptr(gw), N, g.E, H, C, _stream(dev)), 'bspmm_bwd_w')
         return None, gw, gx
 
 
@@ -319,6 +319,11 @@ def bspmm(index, weight=None, x=None, reduce='sum'):
 # ------------------------------------------------------------------------------------------------
 class _EdgeSoftmax(torch.autograd.Function):
     @staticmethod
+    def _workspace(csr, H, dev):
+        need = _lib.load().gglb200_edge_softmax_workspace_bytes(csr.n_rows, H, csr.n_chunks if csr.has_long else 0)
+        return torch.empty(need, dtype=torch.uint8, device=dev), need
+
+    @staticmethod
     def forward(ctx, data, segment_ids, num_segments):
         lib = _lib.load()
         require_cuda(data, 'data')
@@ -334,11 +339,14 @@ class _EdgeSoftmax(torch.autograd.Function):
             ctx.csr = None
             return alpha
         csr = segment_csr_of(segment_ids, int(num_segments))
+        ids = segment_ids if segment_ids.dtype == torch.int64 and segment_ids.is_contiguous() else segment_ids.to(torch.int64).contiguous()
         dev = data.device
         with torch.cuda.device(dev):
-            _lib.check(lib.gglb200_edge_softmax_fwd(_ptr(csr.rowptr), _ptr(csr.perm), _ptr(data), _ptr(alpha), csr.n_rows, E, H,
-                                                    _stream(dev)), 'edge_softmax_fwd')
-        ctx.csr, ctx.H = csr, H
+            _lib.tune_device(dev.index)
+            ws, nb = _EdgeSoftmax._workspace(csr, H, dev)
+            _lib.check(lib.gglb200_edge_softmax_fwd(_ptr(csr.rowptr), _ptr(csr.perm), _ptr(csr.plan), _ptr(ids), _ptr(data),
+                                                    _ptr(alpha), csr.n_rows, E, H, _ptr(ws), nb, _stream(dev)), 'edge_softmax_fwd')
+        ctx.csr, ctx.H, ctx.ids = csr, H, ids
         ctx.save_for_backward(alpha)
         return alpha
 
@@ -353,8 +361,10 @@ class _EdgeSoftmax(torch.autograd.Function):
         dev = alpha.device
         csr = ctx.csr
         with torch.cuda.device(dev):
-            _lib.check(lib.gglb200_edge_softmax_bwd(_ptr(csr.rowptr), _ptr(csr.perm), _ptr(alpha), _ptr(galpha), _ptr(gl),
-                                                    csr.n_rows, csr.E, ctx.H, _stream(dev)), 'edge_softmax_bwd')
+            ws, nb = _EdgeSoftmax._workspace(csr, ctx.H, dev)
+            _lib.check(lib.gglb200_edge_softmax_bwd(_ptr(csr.rowptr), _ptr(csr.perm), _ptr(csr.plan), _ptr(ctx.ids), _ptr(alpha),
+                                                    _ptr(galpha), _ptr(gl), csr.n_rows, csr.E, ctx.H, _ptr(ws), nb, _stream(dev)),
+                       'edge_softmax_bwd')
         return gl, None, None
 
 

@@ -178,24 +178,30 @@ GGL_API int gglb200_spmm_max_bwd(const int32_t* rowptr_t, const int32_t* col_t, 
 /* ---------------------------------------------------------------------------------------------
  * bspmm backward wrt the per-head edge weight (SDDMM), cpu/bspmm_sum_cpu.cpp:95-107:
  *   gw[e, h] = sum_c x[src_e, h, c] * g[dst_e, h, c]
- * evaluated over the forward CSR (rows = dst): g row is loaded once per row, x rows are gathered,
- * results are written to gw[perm[i], h].
+ * evaluated over the forward CSR (rows = dst) in pure edge tiles (plan = the CSR's plan array): x rows are
+ * bulk-copied through the shared-memory ring, the g row of the current destination stays in registers, results
+ * are written to gw[perm[i], h] (every edge exactly once; gw needs no initialisation).
  * ------------------------------------------------------------------------------------------- */
-GGL_API int gglb200_bspmm_bwd_w(const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+GGL_API int gglb200_bspmm_bwd_w(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* plan,
                         const float* x, const float* g, float* gw,
                         int64_t n_rows, int64_t E, int32_t H, int32_t C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Fused edge softmax over incoming edges (gammagl/utils/softmax.py:29-35):
- *   m[r,h] = max_i logit[perm[i],h];  p = exp(logit - m);  s = sum p;  alpha = p / (s + 1e-16)
- * fwd writes alpha[perm[i], h]; bwd: glogit = alpha * (galpha - sum_row(alpha * galpha)) (the analytic
- * gradient of the composed reference ops, with max treated as a constant shift).
+ * Edge softmax over incoming edges (gammagl/utils/softmax.py:29-35), the reference composition on the segment
+ * kernels (rowptr/perm/plan = CSR over `ids`, built with other = NULL):
+ *   m = segment_max(logit);  p = exp(logit - m[ids]);  s = segment_sum(p);  alpha = p / (s[ids] + 1e-16)
+ * bwd: glogit = alpha * (galpha - segment_sum(alpha * galpha)[ids])  (analytic gradient; the max is a constant
+ * shift).  logit / alpha / galpha / glogit are [E, H] float32 in ORIGINAL edge order; ids [E] int64.
+ * workspace: gglb200_edge_softmax_workspace_bytes(n_rows, H, n_chunks) with n_chunks = plan[0] (0 if unknown and
+ * the graph has no row above GGLB200_LONG_ROW edges; E / GGLB200_LONG_CHUNK + E / GGLB200_LONG_ROW + 2 is always safe).
  * ------------------------------------------------------------------------------------------- */
-GGL_API int gglb200_edge_softmax_fwd(const int32_t* rowptr, const int32_t* perm, const float* logit,
-                             float* alpha, int64_t n_rows, int64_t E, int32_t H, void* stream);
-GGL_API int gglb200_edge_softmax_bwd(const int32_t* rowptr, const int32_t* perm, const float* alpha,
-                             const float* galpha, float* glogit, int64_t n_rows, int64_t E, int32_t H,
-                             void* stream);
+GGL_API size_t gglb200_edge_softmax_workspace_bytes(int64_t n_rows, int32_t H, int64_t n_chunks);
+GGL_API int gglb200_edge_softmax_fwd(const int32_t* rowptr, const int32_t* perm, const int32_t* plan, const int64_t* ids,
+                             const float* logit, float* alpha, int64_t n_rows, int64_t E, int32_t H,
+                             void* workspace, size_t workspace_bytes, void* stream);
+GGL_API int gglb200_edge_softmax_bwd(const int32_t* rowptr, const int32_t* perm, const int32_t* plan, const int64_t* ids,
+                             const float* alpha, const float* galpha, float* glogit, int64_t n_rows, int64_t E,
+                             int32_t H, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,11 +67,12 @@ def main(cfg):
     lib = _lib.load()
     from gammagl_b200.csr import _ptr, _stream
     gw = torch.empty(E, H, device=dev)
-    report('bspmm bwd_w (SDDMM)', timeit(lambda: _lib.check(lib.gglb200_bspmm_bwd_w(_ptr(fwd.rowptr), _ptr(fwd.col), _ptr(fwd.perm), _ptr(x), _ptr(x), _ptr(gw), N, E, H, C, _stream(dev)))), E, bs_b, cfg=cfg)
-    alpha = torch.empty(E, H, device=dev)
-    report('edge_softmax fwd H=%d' % H, timeit(lambda: _lib.check(lib.gglb200_edge_softmax_fwd(_ptr(fwd.rowptr), _ptr(fwd.perm), _ptr(wh), _ptr(alpha), N, E, H, _stream(dev)))), E, E * (2 * 4 * H + 4), cfg=cfg)
-    gl = torch.empty(E, H, device=dev)
-    report('edge_softmax bwd', timeit(lambda: _lib.check(lib.gglb200_edge_softmax_bwd(_ptr(fwd.rowptr), _ptr(fwd.perm), _ptr(alpha), _ptr(wh), _ptr(gl), N, E, H, _stream(dev)))), E, E * (3 * 4 * H + 4), cfg=cfg)
+    report('bspmm bwd_w (SDDMM)', timeit(lambda: _lib.check(lib.gglb200_bspmm_bwd_w(_ptr(fwd.rowptr), _ptr(fwd.col), _ptr(fwd.perm), _ptr(fwd.plan), _ptr(x), _ptr(x), _ptr(gw), N, E, H, C, _stream(dev)))), E, bs_b, cfg=cfg)
+    dst_ids = ei[1].contiguous()
+    lg = wh.clone().requires_grad_(True)
+    report('segment_softmax fwd H=%d (max+exp+sum+div)' % H, timeit(lambda: mpops.segment_softmax(lg, dst_ids, N)), E, E * (2 * 4 * H + 8), cfg=cfg)
+    al = mpops.segment_softmax(lg, dst_ids, N)
+    report('segment_softmax bwd', timeit(lambda: al.backward(wh, retain_graph=True)), E, E * (3 * 4 * H + 8), cfg=cfg)
     # segment ops on a materialised message (the reference's unfused path); K limited so that [E,K] fits comfortably
     Ks = min(K, 32)
     msg = torch.randn(E, Ks, generator=g, device=dev)
