@@ -145,6 +145,29 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(self.rows)}
 
 
+def ncu_traffic(workload, graph):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
+    of this workload (profiles/ncu_r1_spmm_ring_<graph>_raw.csv); None when no capture exists for it."""
+    if workload != 'c3':
+        return None, None
+    path = os.path.join(ROOT, 'profiles', 'ncu_r1_spmm_ring_%s_raw.csv' % graph)
+    if not os.path.exists(path):
+        return None, None
+    try:
+        import csv
+        rows = list(csv.reader(open(path)))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        tot = 0.0
+        for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            i = hdr.index(name)
+            v = float(vals[i].replace(',', ''))
+            u = units[i].lower()
+            tot += v * (1e9 if u.startswith('g') else 1e6 if u.startswith('m') else 1e3 if u.startswith('k') else 1.0)
+        return tot, os.path.relpath(path, ROOT)
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -307,8 +330,10 @@ def run_b200(args):
     alg_bytes = E * (K * esz + 4 + 4) + N * (K * esz + 4)
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (kavg * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                'kernel': 'spmm_rows_kernel<float,4,32,1,false> (+chunks/finalize for rows > 1024 edges)',
+    traffic, traffic_src = ncu_traffic(args.workload, args.graph) if (args.dtype == 'f32' and args.scale == 1.0) else (None, None)
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                'traffic_source': traffic_src,
+                'kernel': 'spmm_ring_kernel<float,4,32,1,false> (bulk-copy ring; long-row chunks in the same launch) + spmm_finalize_kernel',
                 'algorithmic_bytes_per_launch': alg_bytes, 'avg_launch_ms': kavg, 'launches_timed': len(kern_ms),
                 'peak_source': peak_src,
                 'formula': 'E*(K*s+4+4) + N*(K*s+4) per SpMM pass (SURVEY.md 8d gather model)'}
@@ -323,15 +348,44 @@ def run_b200(args):
         xd = torch.empty_like(x.detach()).requires_grad_(True)
         gd = torch.empty_like(gout)
 
+        # Two copy streams besides the compute stream: uploads (H2D) and downloads (D2H) use different PCIe directions and
+        # overlap each other and the kernels; ordering is by events only (no host sync inside the step).
+        up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        ev_x, ev_g, ev_out, ev_gx = (torch.cuda.Event() for _ in range(4))
+        ev_free_x, ev_free_g = torch.cuda.Event(), torch.cuda.Event()
+        ev_free_x.record(cur)
+        ev_free_g.record(cur)
+        keep = {}
+
         def e2e_step():
-            with torch.no_grad():
-                xd.copy_(xh, non_blocking=True)
+            with torch.cuda.stream(up):
+                up.wait_event(ev_free_x)                    # previous step no longer reads xd
+                with torch.no_grad():
+                    xd.copy_(xh, non_blocking=True)
+                ev_x.record(up)
+                up.wait_event(ev_free_g)
                 gd.copy_(gh, non_blocking=True)
+                ev_g.record(up)
+            cur.wait_event(ev_x)
             xd.grad = None
             out = mpops.gspmm(ei, w, xd, 'sum')
+            ev_out.record(cur)
+            with torch.cuda.stream(down):
+                down.wait_event(ev_out)
+                oh.copy_(out.detach(), non_blocking=True)
+            cur.wait_event(ev_g)
             out.backward(gd)
-            oh.copy_(out.detach(), non_blocking=True)
-            gxh.copy_(xd.grad, non_blocking=True)
+            ev_free_x.record(cur)
+            ev_free_g.record(cur)
+            ev_gx.record(cur)
+            gx = xd.grad
+            with torch.cuda.stream(down):
+                down.wait_event(ev_gx)
+                gxh.copy_(gx, non_blocking=True)
+            out.record_stream(down)
+            gx.record_stream(down)
+            keep['last'] = (out, gx)
 
         for _ in range(3):
             e2e_step()
@@ -340,6 +394,7 @@ def run_b200(args):
         a.record()
         for _ in range(args.steps):
             e2e_step()
+        cur.wait_stream(down)
         b.record()
         barrier()
         ems = a.elapsed_time(b) / args.steps
@@ -349,8 +404,31 @@ def run_b200(args):
         nb = N * K * esz
         e2e = {'value': world * 2 * E / (float(t.item()) * 1e-3), 'unit': 'edges/s', 'ms_per_step': float(t.item()),
                'h2d_bytes_per_step': 2 * nb, 'd2h_bytes_per_step': 2 * nb,
-               'note': 'x and grad_out copied from pinned host memory, out and grad_x copied back, every step; '
-                       'graph (CSR) resident'}
+               'note': 'x and grad_out copied from pinned host memory, out and grad_x copied back, every step (uploads and '
+                       'downloads on their own streams, event-ordered); graph (CSR) resident'}
+
+    # the same GCN aggregation with the normalisation folded into row scalings (mpops.gcn_propagate): reported as an
+    # extra, the headline stays on the reference operator gspmm(edge_index, weight, x)
+    folded = None
+    if args.dtype == 'f32':
+        xf = x.detach().clone().requires_grad_(True)
+
+        def fstep():
+            xf.grad = None
+            mpops.gcn_propagate(ei, xf, 'both').backward(gout)
+        for _ in range(3):
+            fstep()
+        barrier()
+        a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a2.record()
+        for _ in range(min(args.steps, 10)):
+            fstep()
+        b2.record()
+        barrier()
+        fms = a2.elapsed_time(b2) / min(args.steps, 10)
+        folded = {'op': "gcn_propagate(edge_index, x, 'both') fwd+bwd (row-scale + unweighted SpMM + row-scale)",
+                  'ms_per_step': fms, 'value': 2 * E / (fms * 1e-3), 'unit': 'edges/s (this rank)'}
+        del xf
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -368,6 +446,7 @@ def run_b200(args):
                        'parallelism': 'replicas x%d (independent graphs, no collective)' % world,
                        'max_in_degree': max_in, 'max_out_degree': max_out, 'csr_build_ms': csr_ms},
             'roofline': roofline, 'e2e': e2e, 'cpu_baseline': cpu, 'gpu_launches': int(launches), 'clocks': clocks,
+            'folded_gcn_norm': folded,
         }
         print(json.dumps(line))
     if world > 1:

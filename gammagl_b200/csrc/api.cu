@@ -71,8 +71,8 @@ extern "C" size_t gglb200_spmm_workspace_bytes(int64_t E, int64_t K, int reduce)
 
 extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
                                 const float* w, const int32_t* wperm, int32_t heads, const void* x, void* out,
-                                int64_t* arg, int64_t arg_empty, int64_t n_rows, int64_t n_src, int64_t E, int64_t K, int dtype,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+                                int64_t* arg, int64_t arg_empty, const float* out_scale, int64_t n_rows, int64_t n_src,
+                                int64_t E, int64_t K, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
   GGL_REQUIRE(reduce == GGL_SUM || reduce == GGL_MEAN || reduce == GGL_MAX, GGL_EINVAL, "spmm: unknown reduce %d", reduce);
   GGL_REQUIRE(n_rows >= 0 && n_src >= 0 && E >= 0 && K >= 0, GGL_EINVAL, "spmm: negative size");
   GGL_REQUIRE(n_rows < INT32_MAX && E < INT32_MAX, GGL_ERANGE, "spmm: n_rows/E exceed int32");
@@ -82,10 +82,12 @@ extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t
   GGL_REQUIRE(heads >= 1, GGL_EINVAL, "spmm: heads must be >= 1");
   GGL_REQUIRE(heads == 1 || (w != nullptr && K % heads == 0), GGL_EINVAL, "spmm: heads=%d needs w and K %% heads == 0 (K=%lld)", heads, (long long)K);
   GGL_REQUIRE(arg == nullptr || reduce == GGL_MAX, GGL_EINVAL, "spmm: arg is only produced by GGL_MAX");
+  GGL_REQUIRE(out_scale == nullptr || (reduce == GGL_SUM && (dtype == GGL_F32 || dtype == GGL_BF16 || dtype == GGL_F16)), GGL_EINVAL,
+              "spmm: out_scale needs GGL_SUM and a floating dtype");
 
   SpmmArgs p;
   p.reduce = reduce; p.rowptr = rowptr; p.col = col; p.plan = plan; p.w = w; p.wperm = wperm; p.heads = heads;
-  p.x = x; p.out = out; p.arg = arg; p.arg_empty = arg_empty; p.n_rows = n_rows; p.E = E; p.K = K; p.n_src = n_src;
+  p.x = x; p.out = out; p.arg = arg; p.arg_empty = arg_empty; p.out_scale = out_scale; p.n_rows = n_rows; p.E = E; p.K = K; p.n_src = n_src;
   p.part_val = nullptr; p.part_arg = nullptr; p.stream = (cudaStream_t)stream;
   p.n_tiles = plan_n_tiles(E);
   p.tile_row = plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E));

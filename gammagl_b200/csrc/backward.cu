@@ -144,6 +144,39 @@ __global__ void __launch_bounds__(256) spmm_max_bwd_kernel(const int32_t* __rest
   }
 }
 
+// out[r,:] = scale[r] * x[r,:]  (pre-scaling of the folded GCN normalisation; float4 fast path for fp32)
+template <typename T>
+__global__ void __launch_bounds__(256) scale_rows_by_vec_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                                                                T* __restrict__ out, int64_t total, int32_t K) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; t < total; t += stride) {
+    const int64_t r = t / K;
+    out[t] = Elem<T>::from_acc(__fmul_rn(__ldg(scale + r), Elem<T>::to_acc(x[t])));
+  }
+}
+__global__ void __launch_bounds__(256) scale_rows_by_vec4_kernel(const float4* __restrict__ x, const float* __restrict__ scale,
+                                                                 float4* __restrict__ out, int64_t total4, int32_t K4) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; t < total4; t += stride) {
+    const float s = __ldg(scale + t / K4);
+    float4 v = __ldcs(x + t);
+    v.x = __fmul_rn(s, v.x); v.y = __fmul_rn(s, v.y); v.z = __fmul_rn(s, v.z); v.w = __fmul_rn(s, v.w);
+    out[t] = v;
+  }
+}
+// out[r] = deg(r)^power for deg > 0, else 0   (deg = rowptr[r+1] - rowptr[r])
+__global__ void __launch_bounds__(256) degree_power_kernel(const int32_t* __restrict__ rowptr, float* __restrict__ out, int64_t n,
+                                                           float power) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; r < n; r += stride) {
+    const float d = (float)(rowptr[r + 1] - rowptr[r]);
+    out[r] = d > 0.f ? (power == -0.5f ? rsqrtf(d) : (power == -1.f ? __fdiv_rn(1.f, d) : powf(d, power))) : 0.f;
+  }
+}
+
 static int elem_bytes(int dtype) {
   switch (dtype) {
     case GGL_F32: case GGL_I32: return 4;
@@ -222,6 +255,38 @@ extern "C" int gglb200_scale_rows_by_count(const float* g, const int32_t* rowptr
   GGL_REQUIRE(g && rowptr && out, GGL_EINVAL, "scale_rows: NULL pointer");
   scale_rows_kernel<<<grid_for(n_rows * 32), 256, 0, stream>>>(g, rowptr, out, n_rows, (int32_t)K);
   GGL_LAUNCHED("scale_rows");
+  return GGL_OK;
+}
+
+extern "C" int gglb200_scale_rows(const void* x, const float* scale, void* out, int64_t n_rows, int64_t K, int dtype,
+                                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(n_rows >= 0 && K >= 0, GGL_EINVAL, "scale_rows: negative size");
+  if (n_rows == 0 || K == 0) return GGL_OK;
+  GGL_REQUIRE(x && scale && out, GGL_EINVAL, "scale_rows: NULL pointer");
+  const int64_t total = n_rows * K;
+  if (dtype == GGL_F32 && K % 4 == 0 && (((uintptr_t)x | (uintptr_t)out) % 16 == 0)) {
+    scale_rows_by_vec4_kernel<<<grid_for(total / 4), 256, 0, stream>>>((const float4*)x, scale, (float4*)out, total / 4, (int32_t)(K / 4));
+  } else if (dtype == GGL_F32) {
+    scale_rows_by_vec_kernel<float><<<grid_for(total), 256, 0, stream>>>((const float*)x, scale, (float*)out, total, (int32_t)K);
+  } else if (dtype == GGL_BF16) {
+    scale_rows_by_vec_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, stream>>>((const __nv_bfloat16*)x, scale, (__nv_bfloat16*)out, total, (int32_t)K);
+  } else if (dtype == GGL_F16) {
+    scale_rows_by_vec_kernel<__half><<<grid_for(total), 256, 0, stream>>>((const __half*)x, scale, (__half*)out, total, (int32_t)K);
+  } else {
+    return set_error(GGL_EUNSUPPORTED, "scale_rows: floating dtypes only (got %d)", dtype);
+  }
+  GGL_LAUNCHED("scale_rows_by_vec");
+  return GGL_OK;
+}
+
+extern "C" int gglb200_degree_power(const int32_t* rowptr, float* out, int64_t n_rows, float power, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(n_rows >= 0, GGL_EINVAL, "degree_power: negative size");
+  if (n_rows == 0) return GGL_OK;
+  GGL_REQUIRE(rowptr && out, GGL_EINVAL, "degree_power: NULL pointer");
+  degree_power_kernel<<<grid_for(n_rows), 256, 0, stream>>>(rowptr, out, n_rows, power);
+  GGL_LAUNCHED("degree_power");
   return GGL_OK;
 }
 

@@ -200,7 +200,7 @@ static int ew_grid(int64_t n) {
 // segment reduction of x[E,H] over the segment CSR (col = perm) into out[n_rows,H]
 static int segment_reduce_f32(int reduce, const int32_t* rowptr, const int32_t* perm, const int32_t* plan, const float* x,
                               float* out, int64_t n_rows, int64_t E, int32_t H, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  return gglb200_spmm_csr(reduce, rowptr, perm, plan, nullptr, nullptr, 1, x, out, nullptr, 0, n_rows, E, E, H, GGL_F32, ws,
+  return gglb200_spmm_csr(reduce, rowptr, perm, plan, nullptr, nullptr, 1, x, out, nullptr, 0, nullptr, n_rows, E, E, H, GGL_F32, ws,
                           ws_bytes, (void*)stream);
 }
 

@@ -47,6 +47,7 @@ struct SpmmArgs {
   void* out;
   int64_t* arg;             // MAX only, may be NULL
   int64_t arg_empty;
+  const float* out_scale;   // NULL, or [n_rows] fp32: out[r,:] = out_scale[r] * reduce(...) (folded GCN normalisation)
   int64_t n_rows, E, K;
   int64_t n_src;            // rows of x (bounds the superset copies of unaligned rows)
   void* part_val;           // workspace: [ws_chunks, K] acc_t
@@ -157,6 +158,13 @@ __device__ __forceinline__ void finish_row(typename Elem<T>::acc_t (&acc)[VEC], 
                                            int64_t row, int32_t kcol, int32_t deg) {
   using acc_t = typename Elem<T>::acc_t;
   Pack<T, VEC> o;
+  if constexpr (Elem<T>::is_float && sizeof(T) <= 4) {
+    if (p.out_scale) {
+      const float sc = __ldg(p.out_scale + row);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = mul_rn(acc[i], sc);
+    }
+  }
   if (p.reduce == GGL_MEAN) {
     if constexpr (Elem<T>::is_float) {
       if (deg > 1) {

@@ -113,8 +113,9 @@ def add_self_loops(edge_index, num_nodes=None):
 
 
 class GCNConv(MessagePassing):
-    def __init__(self, in_channels, out_channels, norm='both', add_bias=True, fused=True):
+    def __init__(self, in_channels, out_channels, norm='both', add_bias=True, fused=True, fold_norm=True):
         super().__init__(fused)
+        self.fold_norm = fold_norm
         if norm not in ['left', 'right', 'none', 'both']:
             raise ValueError('Invalid norm value. Must be either "none", "both", "right" or "left".'
                              ' But got "{}".'.format(norm))
@@ -124,6 +125,9 @@ class GCNConv(MessagePassing):
 
     def forward(self, x, edge_index, edge_weight=None, num_nodes=None):
         x = self.linear(x)                                                  # gcn_conv.py:79
+        if self.fused and self.fold_norm and edge_weight is None:
+            out = mpops.gcn_propagate(edge_index, x, self._norm)           # same math, no per-edge weight stream
+            return out + self.bias if self.add_bias else out
         src, dst = edge_index[0], edge_index[1]
         if edge_weight is None:
             edge_weight = torch.ones((edge_index.shape[1],), device=x.device)

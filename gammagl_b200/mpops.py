@@ -42,7 +42,7 @@ def _dtype_code(t):
         raise _lib.GglError('unsupported dtype %s' % t.dtype)
 
 
-def spmm_csr(csr, col, x2d, reduce, w=None, wperm=None, heads=1, want_arg=False, arg_empty=0, n_rows=None):
+def spmm_csr(csr, col, x2d, reduce, w=None, wperm=None, heads=1, want_arg=False, arg_empty=0, n_rows=None, out_scale=None):
     """Launch the aggregation kernel family on a Csr.  x2d: [n_src, K] contiguous.  Returns (out, arg)."""
     lib = _lib.load()
     n_rows = csr.n_rows if n_rows is None else n_rows
@@ -57,7 +57,7 @@ def spmm_csr(csr, col, x2d, reduce, w=None, wperm=None, heads=1, want_arg=False,
             ev0 = torch.cuda.Event(enable_timing=True)
             ev0.record()
         _lib.check(lib.gglb200_spmm_csr(reduce, _ptr(csr.rowptr), _ptr(col), _ptr(csr.plan),
-                                        _ptr(w), _ptr(wperm), heads, _ptr(x2d), _ptr(out), _ptr(arg), arg_empty,
+                                        _ptr(w), _ptr(wperm), heads, _ptr(x2d), _ptr(out), _ptr(arg), arg_empty, _ptr(out_scale),
                                         n_rows, x2d.shape[0], csr.E, K, _dtype_code(x2d), _ptr(ws), ws_bytes, _stream(dev)),
                    'spmm_csr')
         if PROFILE is not None:
@@ -292,6 +292,64 @@ def c_bspmm_sum(index, weight, x):
     return _BSpMM.apply(index, weight, x)
 
 
+class _GcnPropagate(torch.autograd.Function):
+    """out = D_dst^a . A . D_src^b . x with the degree powers GCNConv uses (gcn_conv.py:88-102), evaluated as
+    row-scale -> unweighted SpMM -> row-scale: no per-edge weight stream.  Same math as
+    gspmm(edge_index, norm_src[src] * norm_dst[dst], x); rounding differs in the last ulp (one product per row instead
+    of one per edge), so this path is checked at 1e-5 relative, not bit-exactly."""
+
+    @staticmethod
+    def forward(ctx, x, edge_index, norm):
+        lib = _lib.load()
+        require_cuda(x, 'x')
+        require_cuda(edge_index, 'edge_index')
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            raise _lib.GglError('gcn_propagate needs a floating x')
+        x = x.contiguous()
+        N = x.shape[0]
+        g = graph_of(edge_index, N)
+        dev = x.device
+        x2d = x.view(N, -1)
+        K = x2d.shape[1]
+        with torch.cuda.device(dev):
+            ns = nd = None
+            if norm in ('both', 'left'):       # source side: out-degree (degree(src), gcn_conv.py:89)
+                ns = torch.empty(N, dtype=torch.float32, device=dev)
+                _lib.check(lib.gglb200_degree_power(_ptr(g.bwd.rowptr), _ptr(ns), N, -0.5 if norm == 'both' else -1.0, _stream(dev)), 'degree_power')
+            if norm in ('both', 'right'):      # destination side: in-degree (degree(dst), gcn_conv.py:97)
+                nd = torch.empty(N, dtype=torch.float32, device=dev)
+                _lib.check(lib.gglb200_degree_power(_ptr(g.fwd.rowptr), _ptr(nd), N, -0.5 if norm == 'both' else -1.0, _stream(dev)), 'degree_power')
+            xs = x2d
+            if ns is not None:
+                xs = torch.empty_like(x2d)
+                _lib.check(lib.gglb200_scale_rows(_ptr(x2d), _ptr(ns), _ptr(xs), N, K, _dtype_code(x2d), _stream(dev)), 'scale_rows')
+            out, _ = spmm_csr(g.fwd, g.fwd.col, xs, _lib.GGL_SUM, out_scale=nd)
+        ctx.graph, ctx.ns, ctx.nd, ctx.shape = g, ns, nd, tuple(x.shape)
+        return out.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        g = ctx.graph
+        grad = grad_out.contiguous().view(g.N, -1)
+        K = grad.shape[1]
+        dev = grad.device
+        with torch.cuda.device(dev):
+            gs = grad
+            if ctx.nd is not None:
+                gs = torch.empty_like(grad)
+                _lib.check(lib.gglb200_scale_rows(_ptr(grad), _ptr(ctx.nd), _ptr(gs), g.N, K, _dtype_code(grad), _stream(dev)), 'scale_rows')
+            gx, _ = spmm_csr(g.bwd, g.bwd.col, gs, _lib.GGL_SUM, out_scale=ctx.ns)
+        return gx.view(ctx.shape), None, None
+
+
+def gcn_propagate(edge_index, x, norm='both'):
+    """GCNConv's normalised propagate with unit edge weights (gcn_conv.py:78-104 after the Linear), weight-stream free."""
+    if norm not in ('both', 'left', 'right', 'none'):
+        raise ValueError('Invalid norm value. Must be either "none", "both", "right" or "left".')
+    return _GcnPropagate.apply(x, edge_index, norm)
+
+
 def gspmm(index, weight=None, x=None, reduce='sum'):
     """Generalized SpMM: out[dst] (+|mean|max)= weight[e] * x[src]  (torch.py:302-351)."""
     if weight is None:
@@ -375,4 +433,4 @@ def segment_softmax(data, segment_ids, num_segments):
 
 __all__ = ['use_ext', 'unsorted_segment_sum', 'unsorted_segment_mean', 'unsorted_segment_max', 'segment_sum',
            'segment_mean', 'segment_max', 'gspmm', 'bspmm', 'c_segment_sum', 'c_segment_mean', 'c_segment_max',
-           'c_spmm_sum', 'c_spmm_mean', 'c_spmm_max', 'c_bspmm_sum', 'segment_softmax']
+           'c_spmm_sum', 'c_spmm_mean', 'c_spmm_max', 'c_bspmm_sum', 'segment_softmax', 'gcn_propagate']

@@ -130,6 +130,9 @@ GGL_API int gglb200_permute_rows(const void* in, const int32_t* perm, void* out,
  *   arg      NULL, or int64 [n_rows, K] (MAX only): col[i*] of the winning edge; `arg_empty` for
  *            rows without edges (segment_max: N, cpu/segment_max_cpu.cpp:27; spmm_max: 0,
  *            cpu/spmm_max_cpu.cpp:23-24).  For the segment ops col := perm, so this is the edge id.
+ *   out_scale NULL, or fp32 [n_rows] (GGL_SUM, floating dtypes): out[r,:] = out_scale[r] * sum(...).  With
+ *            gglb200_scale_rows on the input this evaluates D_dst^a A D_src^b x -- GCNConv's normalised propagate
+ *            (layers/conv/gcn_conv.py:88-104) -- WITHOUT a per-edge weight stream (no w[perm[i]] gather).
  *   plan     the array gglb200_csr_build produced for this rowptr (required)
  *   workspace partials of split rows.  gglb200_spmm_workspace_bytes(E, K, reduce) is always sufficient; a
  *            caller that has read plan[0] (= number of chunks, once after gglb200_csr_build) may pass the
@@ -145,7 +148,7 @@ GGL_API size_t gglb200_spmm_workspace_bytes_for_chunks(int64_t n_chunks, int64_t
 GGL_API int    gglb200_spmm_csr(int reduce,
                         const int32_t* rowptr, const int32_t* col, const int32_t* plan,
                         const float* w, const int32_t* wperm, int32_t heads,
-                        const void* x, void* out, int64_t* arg, int64_t arg_empty,
+                        const void* x, void* out, int64_t* arg, int64_t arg_empty, const float* out_scale,
                         int64_t n_rows, int64_t n_src, int64_t E, int64_t K, int dtype,
                         void* workspace, size_t workspace_bytes, void* stream);
 
@@ -169,6 +172,10 @@ GGL_API int gglb200_segment_max_bwd(const void* g, const int64_t* arg, const int
  *   max:   gx[s,k] = sum over edges (s -> d) with argsrc[d,k] == s of w * g[d,k]
  *          (cpu/spmm_max_cpu.cpp:84-96; parallel edges count twice, as there).
  * ------------------------------------------------------------------------------------------- */
+/* Folded GCN normalisation helpers: out[r,:] = scale[r] * x[r,:] (floating dtypes), and
+ * out[r] = deg(r)^power with deg = rowptr[r+1]-rowptr[r], 0 for isolated rows (utils/degree.py + tlx.pow(deg, -0.5)). */
+GGL_API int gglb200_scale_rows(const void* x, const float* scale, void* out, int64_t n_rows, int64_t K, int dtype, void* stream);
+GGL_API int gglb200_degree_power(const int32_t* rowptr, float* out, int64_t n_rows, float power, void* stream);
 GGL_API int gglb200_scale_rows_by_count(const float* g, const int32_t* rowptr, float* out, int64_t n_rows,
                                 int64_t K, void* stream);
 GGL_API int gglb200_spmm_max_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* w,

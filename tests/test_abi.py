@@ -42,13 +42,13 @@ def test_version_and_sizes():
 
 def test_argument_validation_without_gpu():
     lib = _lib.load()
-    st = lib.gglb200_spmm_csr(7, None, None, None, None, None, 1, None, None, None, 0, 4, 4, 4, 4, 0, None, 0, None)
+    st = lib.gglb200_spmm_csr(7, None, None, None, None, None, 1, None, None, None, 0, None, 4, 4, 4, 4, 0, None, 0, None)
     assert st == -1 and b'unknown reduce' in lib.gglb200_last_error()
     st = lib.gglb200_csr_build(None, None, -1, 4, None, None, None, None, None, 0, None)
     assert st == -1
     st = lib.gglb200_csr_build(None, None, 1 << 31, 4, None, None, None, None, None, 0, None)
     assert st == -4
-    st = lib.gglb200_spmm_csr(0, None, None, None, None, None, 1, None, None, None, 0, 4, 4, 4, 4, 99, None, 0, None)
+    st = lib.gglb200_spmm_csr(0, None, None, None, None, None, 1, None, None, None, 0, None, 4, 4, 4, 4, 99, None, 0, None)
     assert st == -1  # NULL rowptr is caught before the dtype switch
     try:
         _lib.check(st, 'spmm')
