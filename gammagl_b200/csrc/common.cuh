@@ -47,8 +47,10 @@ constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
 //   [4] n_tiles   [5] GGLB200_TILE_EDGES  [6..7] reserved
 //   [8 .. 8+2*max_chunks)            chunk table: {row, first_edge}          (rows > GGLB200_LONG_ROW edges)
 //   [.. +3*max_long)                 long-row table: {row, first_chunk, n_chunks}
-//   [.. +n_tiles+1)                  tile table: tile_row[t] = first row whose first edge is >= t*TILE_EDGES
-//                                    (tile_row[n_tiles] = N): tile t owns rows [tile_row[t], tile_row[t+1])
+//   [.. +2*(n_tiles+1)) (8-byte aligned)  tile table, int2 per tile: {r0 | long_last << 31, e0} with r0 = first row whose
+//                                    first edge is >= t*TILE_EDGES and e0 = rowptr[r0]; entry n_tiles = {N, E}.  Tile t
+//                                    owns rows [r0(t), r0(t+1)) = edges [e0(t), e0(t+1)); long_last marks tiles whose
+//                                    last owned row has more than GGLB200_LONG_ROW edges (left to the chunk path)
 constexpr int kPlanHeader = 8;
 __host__ __device__ inline int64_t plan_max_long(int64_t E) { return E / GGLB200_LONG_ROW + 1; }
 __host__ __device__ inline int64_t plan_max_chunks(int64_t E) { return E / GGLB200_LONG_CHUNK + plan_max_long(E) + 1; }
@@ -61,7 +63,7 @@ inline int64_t plan_n_tiles(int64_t E) {
 __host__ __device__ inline int64_t plan_chunk_off() { return kPlanHeader; }
 __host__ __device__ inline int64_t plan_long_off(int64_t max_chunks) { return kPlanHeader + 2 * max_chunks; }
 __host__ __device__ inline int64_t plan_tile_off(int64_t max_chunks, int64_t max_long) {
-  return kPlanHeader + 2 * max_chunks + 3 * max_long;
+  return (kPlanHeader + 2 * max_chunks + 3 * max_long + 1) & ~(int64_t)1;
 }
 
 // ---- element traits ------------------------------------------------------------------------------

@@ -83,21 +83,26 @@ __global__ void plan_init_kernel(int32_t* plan, int32_t max_chunks, int32_t max_
   plan[4] = n_tiles; plan[5] = te; plan[6] = 0; plan[7] = 0;
 }
 
-// tile_row[t] = lower_bound(rowptr[0..N], t * TILE_EDGES) clipped to N; tile_row[n_tiles] = N
-__global__ void __launch_bounds__(256) tile_rows_kernel(const int32_t* __restrict__ rowptr, int32_t* __restrict__ tile_row,
+// tile table entry t = {r0 | long_last << 31, rowptr[r0]} with r0 = lower_bound(rowptr[0..N], t * TILE_EDGES); entry n_tiles = {N, E}
+__device__ __forceinline__ int64_t first_row_at(const int32_t* __restrict__ rowptr, int64_t N, int64_t target) {
+  int64_t lo = 0, hi = N;  // first r in [0,N] with rowptr[r] >= target
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)rowptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(256) tile_rows_kernel(const int32_t* __restrict__ rowptr, int32_t* __restrict__ tile_tab,
                                                         int64_t N, int64_t n_tiles, int64_t te) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; t <= n_tiles; t += stride) {
-    if (t == n_tiles) { tile_row[t] = (int32_t)N; continue; }
-    if (t == 0) { tile_row[0] = 0; continue; }
-    const int64_t target = t * te;
-    int64_t lo = 0, hi = N;  // first r in [0,N] with rowptr[r] >= target
-    while (lo < hi) {
-      int64_t mid = (lo + hi) >> 1;
-      if ((int64_t)rowptr[mid] < target) lo = mid + 1; else hi = mid;
-    }
-    tile_row[t] = (int32_t)lo;
+    if (t == n_tiles) { tile_tab[2 * t] = (int32_t)N; tile_tab[2 * t + 1] = rowptr[N]; continue; }
+    const int64_t r0 = t == 0 ? 0 : first_row_at(rowptr, N, t * te);
+    const int64_t r1 = t + 1 == n_tiles ? N : first_row_at(rowptr, N, (t + 1) * te);
+    const bool long_last = r1 > r0 && rowptr[r1] - rowptr[r1 - 1] > GGLB200_LONG_ROW;
+    tile_tab[2 * t] = (int32_t)r0 | (long_last ? (int32_t)0x80000000 : 0);
+    tile_tab[2 * t + 1] = rowptr[r0];
   }
 }
 
@@ -143,7 +148,7 @@ using namespace ggl;
 
 extern "C" size_t gglb200_csr_plan_ints(int64_t E) {
   if (E < 0) E = 0;
-  return (size_t)(kPlanHeader + 2 * plan_max_chunks(E) + 3 * plan_max_long(E) + plan_n_tiles(E) + 1);
+  return (size_t)(plan_tile_off(plan_max_chunks(E), plan_max_long(E)) + 2 * (plan_n_tiles(E) + 1));
 }
 
 extern "C" size_t gglb200_csr_build_workspace_bytes(int64_t E, int64_t N) {

@@ -51,8 +51,9 @@ __global__ void __launch_bounds__(32) sddmm_ring_kernel(const int32_t* __restric
   const int32_t e0 = (int32_t)(tile * tile_edges);
   const int32_t e_end = min(e0 + tile_edges, E);
   if (e0 >= e_end) return;
-  int32_t r = __ldg(tile_row + tile);
-  if (r >= n_rows || __ldg(rowptr + r) > e0) --r;  // the row that contains edge e0 (empty rows are skipped below)
+  const int2 te = __ldg(reinterpret_cast<const int2*>(tile_row) + tile);  // {first row starting at/after e0 | flag, its first edge}
+  int32_t r = te.x & 0x7fffffff;
+  if (r >= n_rows || te.y > e0) --r;  // the row that contains edge e0 (empty rows are skipped below)
   RowCursor<LPR> rc;
   rc.init(rowptr, r, n_rows, e0, sub, gbase, gmask);
 

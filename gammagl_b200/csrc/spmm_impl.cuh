@@ -227,14 +227,14 @@ struct RowCursor {
 // Tile prologue shared by both tile kernels: rows [r0, r1) and the flat edge range [e0, e1) of tile `tile`.
 // A long row (has_long && deg > LONG_ROW) can only be the last row a tile owns; it is left to the chunk path.
 __device__ __forceinline__ bool tile_ranges(const SpmmArgs& p, int64_t tile, int32_t& r0, int32_t& r1, int32_t& e0, int32_t& e1) {
-  r0 = __ldg(p.tile_row + tile);
-  r1 = __ldg(p.tile_row + tile + 1);
+  const int2 a = __ldg(reinterpret_cast<const int2*>(p.tile_row) + tile);       // {r0 | long_last << 31, e0}
+  const int2 b = __ldg(reinterpret_cast<const int2*>(p.tile_row) + tile + 1);
+  r0 = a.x & 0x7fffffff; e0 = a.y;
+  r1 = b.x & 0x7fffffff; e1 = b.y;
   if (r0 >= r1) return false;
-  e0 = __ldg(p.rowptr + r0);
-  e1 = __ldg(p.rowptr + r1);
-  if (p.has_long) {
-    const int32_t last = __ldg(p.rowptr + r1 - 1);
-    if (e1 - last > GGLB200_LONG_ROW) { e1 = last; --r1; }
+  if (a.x < 0 && p.has_long) {  // the last owned row is long: leave it to the chunk path
+    --r1;
+    e1 = __ldg(p.rowptr + r1);
   }
   return r0 < r1;
 }
@@ -446,20 +446,26 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
   const int32_t n = e_end - e0;                 // edges in the stream
   const int32_t nslots = (n + R - 1) / R;
 
-  // index batches of LPR stream positions: A = batch bA (being consumed), B = bA+1, C = bA+2
+  // index batches of LPR stream positions: A = batch bA (being consumed), B = bA+1, C = bA+2.  The weight gather
+  // w[perm[i]] depends on the perm load, so it is issued one batch AFTER its index (when the batch moves from C to
+  // B): an in-order warp never waits on the perm -> w chain.
   struct Batch { int32_t col, eid; float w; };
-  auto load_batch = [&](int32_t b) {
+  auto load_index = [&](int32_t b) {
     Batch t; t.col = 0; t.eid = 0; t.w = 1.f;
     const int32_t pos = b * LPR + sub;
     if (pos < n) {
       const int32_t idx = e0 + pos;
       t.col = ld_stream_i32(p.col + idx);
       if constexpr (WMODE != 0) t.eid = p.wperm ? ld_stream_i32(p.wperm + idx) : idx;
-      if constexpr (WMODE == 1) t.w = p.wperm ? __ldg(p.w + t.eid) : ld_stream_f32(p.w + t.eid);
     }
     return t;
   };
-  Batch A = load_batch(0), B = load_batch(1), C = load_batch(2);
+  auto load_weight = [&](Batch& t, int32_t b) {
+    if constexpr (WMODE == 1) {
+      if (b * LPR + sub < n) t.w = p.wperm ? __ldg(p.w + t.eid) : ld_stream_f32(p.w + t.eid);
+    }
+  };
+  Batch A = load_index(0), B = load_index(1), C = load_index(2);
   int32_t bA = 0;
 
   auto issue = [&](int32_t s) {  // start the copies of slot s
@@ -488,12 +494,15 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
   };
 
 #pragma unroll
-  for (int s = 0; s < LAG; ++s) issue(s);
+  for (int s = 0; s < LAG; ++s) issue(s);   // the first copies need only A.col / B.col
+  load_weight(A, 0);
+  load_weight(B, 1);
   for (int32_t s = 0; s < nslots; ++s) {
     const int32_t pos0 = s * R;
     if (pos0 / LPR != bA) {  // the consumer enters the next index batch
       A = B; B = C; ++bA;
-      C = load_batch(bA + 2);
+      load_weight(B, bA + 1);
+      C = load_index(bA + 2);
     }
     issue(s + LAG);
     // per-edge scalars of this slot, fetched in convergent code
