@@ -32,6 +32,15 @@ int tile_edges() {
   return v;
 }
 
+int tune_ring_stages() {
+  static int v = [] {
+    const char* e = getenv("GGLB200_RING_STAGES");
+    int t = e ? atoi(e) : 0;
+    return (t == 2 || t == 3) ? t : 0;
+  }();
+  return v;
+}
+
 int tune_ring() {  // 1 = bulk-copy ring (default), 0 = register-staged kernels (env GGLB200_RING=none)
   static int v = [] {
     const char* e = getenv("GGLB200_RING");

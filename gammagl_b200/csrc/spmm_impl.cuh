@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) spmm_tiles_kernel(cons
 // Groups [0, ws_chunks) of the launch reduce long-row chunks into partials, the remaining groups are edge tiles.
 template <int LPR> struct RingCfg {
   static constexpr int R = LPR >= 8 ? 8 : LPR;                      // rows per slot
-  static constexpr int STAGES = LPR >= 16 ? 4 : 3;                  // LAG*R <= 2*LPR (index batches A,B,C)
+  static constexpr int STAGES = 3;                                  // default ring depth; (STAGES-1)*R <= 2*LPR (index batches A,B,C)
   static constexpr int LAG = STAGES - 1;
 };
 
@@ -381,12 +381,14 @@ __device__ __forceinline__ Pack<T, VEC> lds_pack(uint32_t addr) {
 
 template <typename T, int VEC, int LPR, int WMODE, bool ISMAX>
 __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const int32_t pitch /* bytes per row slot */,
-                                                       const uint64_t x_end_al /* align_down(x + n_src*K*sizeof(T), 16) */) {
+                                                       const uint64_t x_end_al /* align_down(x + n_src*K*sizeof(T), 16) */,
+                                                       const int32_t STAGES /* ring depth: 2 or 3 */) {
   using acc_t = typename Elem<T>::acc_t;
   using Cfg = RingCfg<LPR>;
   constexpr int VB = (int)sizeof(T) * VEC;   // bytes a lane owns per row
   constexpr bool ALIGNED = VB == 16;         // rows are 16-byte aligned and sized: no superset, no tail rows
-  constexpr int GPW = 32 / LPR, R = Cfg::R, STAGES = Cfg::STAGES, LAG = Cfg::LAG;
+  constexpr int GPW = 32 / LPR, R = Cfg::R;
+  const int32_t LAG = STAGES - 1;
   extern __shared__ __align__(16) unsigned char ring_smem[];
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LPR - 1);
@@ -409,7 +411,6 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
   const uint32_t ring = smem0 + (uint32_t)(gib * (STAGES * R)) * pitch;
   const uint32_t bars = smem0 + (uint32_t)(GPW * STAGES * R) * pitch + (uint32_t)gib * STAGES * 8;
   if (sub == 0) {
-#pragma unroll
     for (int i = 0; i < STAGES; ++i) mbar_init(bars + i * 8, ALIGNED ? 1 : R);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -468,13 +469,16 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
   Batch A = load_index(0), B = load_index(1), C = load_index(2);
   int32_t bA = 0;
 
+  int32_t istage = 0;  // ring stage of the next slot to issue (issue() is called once per slot, in order)
   auto issue = [&](int32_t s) {  // start the copies of slot s
+    const int32_t stg = istage;
+    istage = istage + 1 == STAGES ? 0 : istage + 1;
     if (s < nslots) {  // group-uniform
       const int32_t pos0 = s * R;
       const int32_t d = pos0 / LPR - bA;  // 0, 1 or 2
       const int32_t colsrc = d == 0 ? A.col : (d == 1 ? B.col : C.col);
-      const uint32_t dst = ring + (uint32_t)((s % STAGES) * R) * pitch;
-      const uint32_t bar = bars + (uint32_t)(s % STAGES) * 8;
+      const uint32_t dst = ring + (uint32_t)(stg * R) * pitch;
+      const uint32_t bar = bars + (uint32_t)stg * 8;
       const int32_t nv = min(R, n - pos0);
       const int32_t c = __shfl_sync(gmask, colsrc, gbase + ((pos0 + sub) & (LPR - 1)));  // lane u copies row u
       __syncwarp(gmask);  // every lane of the group has finished reading this stage (slot s - STAGES)
@@ -493,10 +497,11 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
     }
   };
 
-#pragma unroll
   for (int s = 0; s < LAG; ++s) issue(s);   // the first copies need only A.col / B.col
   load_weight(A, 0);
   load_weight(B, 1);
+  int32_t cstage = 0;
+  uint32_t cparity = 0;
   for (int32_t s = 0; s < nslots; ++s) {
     const int32_t pos0 = s * R;
     if (pos0 / LPR != bA) {  // the consumer enters the next index batch
@@ -518,8 +523,9 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
         wv[u] = __ldg(p.w + (int64_t)eid * p.heads + head);
       }
     }
-    mbar_wait(bars + (uint32_t)(s % STAGES) * 8, (uint32_t)(s / STAGES) & 1u);
-    const uint32_t src = ring + (uint32_t)((s % STAGES) * R) * pitch + (uint32_t)sub * VB;
+    mbar_wait(bars + (uint32_t)cstage * 8, cparity);
+    const uint32_t src = ring + (uint32_t)(cstage * R) * pitch + (uint32_t)sub * VB;
+    if (++cstage == STAGES) { cstage = 0; cparity ^= 1u; }
     // the lane's VB bytes of the row at stream position pos0+u
     auto fetch = [&](int u) {
       if constexpr (ALIGNED) {
@@ -633,7 +639,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_finalize_kernel(cons
 }
 
 // ---- host-side launch ------------------------------------------------------------------------------
-int tune_ring();  // tuning knob (env GGLB200_RING = bulk (default) | none -> register-staged kernels), api.cu
+int tune_ring();         // tuning knob (env GGLB200_RING = bulk (default) | none -> register-staged kernels), api.cu
+int tune_ring_stages();  // tuning knob (env GGLB200_RING_STAGES = 2 | 3; 0 = heuristic), api.cu
 
 template <typename T, int VEC, int LPR, int WMODE, bool ISMAX>
 int launch_ring(const SpmmArgs& p, int tiles) {
@@ -643,7 +650,10 @@ int launch_ring(const SpmmArgs& p, int tiles) {
   const int64_t rowbytes = p.K * (int64_t)sizeof(T);
   const int64_t tileb = rowbytes < (int64_t)LPR * VB ? rowbytes : (int64_t)LPR * VB;   // widest column tile
   const int32_t pitch = (int32_t)(VB == 16 ? tileb : ((tileb + 15 + 15) & ~(int64_t)15));
-  const size_t smem = (size_t)GPW * Cfg::STAGES * Cfg::R * pitch + (size_t)GPW * Cfg::STAGES * 8;
+  // ring depth: 3 slots of 8 rows per group; 2 for wide rows (>= 512 B), where more resident one-warp blocks beat
+  // a deeper ring (measured on C2/K=128: 2.69 vs 2.96 ms; on C3/K=100: 3 is 1 % ahead on the DRAM-bound uniform graph)
+  const int32_t stages = tune_ring_stages() ? tune_ring_stages() : (pitch >= 512 ? 2 : 3);
+  const size_t smem = (size_t)GPW * stages * Cfg::R * pitch + (size_t)GPW * stages * 8;
   GGL_REQUIRE(smem <= 200 * 1024, GGL_EUNSUPPORTED, "spmm: ring of %zu bytes does not fit shared memory", smem);
   static bool attr_set = false;
   if (!attr_set) {
@@ -656,7 +666,7 @@ int launch_ring(const SpmmArgs& p, int tiles) {
   SpmmArgs q = p;
   if (!p.has_long) q.ws_chunks = 0;
   const uint64_t x_end_al = ((uint64_t)p.x + (uint64_t)p.n_src * (uint64_t)rowbytes) & ~(uint64_t)15;
-  spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX><<<dim3((unsigned)blocks, tiles), 32, smem, p.stream>>>(q, pitch, x_end_al);
+  spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX><<<dim3((unsigned)blocks, tiles), 32, smem, p.stream>>>(q, pitch, x_end_al, stages);
   GGL_LAUNCHED("spmm_ring");
   if (p.has_long) {
     spmm_finalize_kernel<T, VEC, LPR, ISMAX><<<dim3(kSMs, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(q);
