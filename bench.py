@@ -45,6 +45,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    ap.add_argument('--peer', action='store_true',
+                    help='c5part only: fused peer-memory gather (gglb200_spmm_csr_peer) instead of pack + all-to-all')
     ap.add_argument('--graph', default='rmat', choices=['rmat', 'uniform', 'block'],
                     help='block (c5part only): 80%% of the edges have a source on the owning GPU')
     ap.add_argument('--dtype', default='f32', choices=['f32', 'bf16'])
@@ -488,8 +490,12 @@ def run_c5part(args):
     w = torch.rand(Eg, generator=g, device=dev)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    plan = P.HaloPlan(ei, N)
-    plan.csr()
+    if args.peer:
+        plan = P.PeerGraph(ei, N)
+        plan.n_halo = 0
+    else:
+        plan = P.HaloPlan(ei, N)
+        plan.csr()
     torch.cuda.synchronize()
     plan_ms = (time.perf_counter() - t0) * 1e3
     del ei
@@ -498,7 +504,10 @@ def run_c5part(args):
 
     def step():
         x.grad = None
-        P.dist_gspmm_sum(plan, x, w).backward(gout)
+        if args.peer:
+            P.peer_gcn_propagate(plan, x, 'both').backward(gout)
+        else:
+            P.dist_gspmm_sum(plan, x, w).backward(gout)
 
     def barrier():
         if world > 1:
@@ -539,7 +548,9 @@ def run_c5part(args):
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': desc, 'graph': kind, 'N_total': N, 'E_total': Eg * world, 'K': K, 'scale': args.scale,
-                       'parallelism': '1-D node partition x%d, halo all-to-all (NCCL) per pass' % world,
+                       'parallelism': ('1-D node partition x%d, fused peer-memory gather over NVLink (no collective on the data path)' % world)
+                       if args.peer else ('1-D node partition x%d, halo all-to-all (NCCL) per pass' % world),
+                       'op': 'peer_gcn_propagate (folded GCN norm, unweighted edges)' if args.peer else 'dist_gspmm_sum (per-edge weights)',
                        'halo_rows_per_gpu_max': int(halo.item()), 'halo_bytes_per_pass_per_gpu': int(halo.item()) * K * 4,
                        'plan_build_ms': plan_ms, 'l2': 'inputs exceed the 126 MB L2; no explicit flush'},
             'roofline': {'bound': 'hbm', 'achieved': alg / (kavg * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',

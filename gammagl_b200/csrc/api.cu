@@ -78,7 +78,7 @@ extern "C" size_t gglb200_spmm_workspace_bytes(int64_t E, int64_t K, int reduce)
   return gglb200_spmm_workspace_bytes_for_chunks(plan_max_chunks_host(E), K, reduce);
 }
 
-extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
+static int spmm_entry(const void* const* x_table, int32_t owner_shift, int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
                                 const float* w, const int32_t* wperm, int32_t heads, const void* x, void* out,
                                 int64_t* arg, int64_t arg_empty, const float* out_scale, int64_t n_rows, int64_t n_src,
                                 int64_t E, int64_t K, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
@@ -87,7 +87,7 @@ extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t
   GGL_REQUIRE(n_rows < INT32_MAX && E < INT32_MAX, GGL_ERANGE, "spmm: n_rows/E exceed int32");
   if (n_rows == 0 || K == 0) return GGL_OK;
   GGL_REQUIRE(rowptr && out && plan, GGL_EINVAL, "spmm: rowptr/out/plan must not be NULL");
-  GGL_REQUIRE(E == 0 || (col && x), GGL_EINVAL, "spmm: col/x must not be NULL when E > 0");
+  GGL_REQUIRE(E == 0 || (col && (x || x_table)), GGL_EINVAL, "spmm: col/x must not be NULL when E > 0");
   GGL_REQUIRE(heads >= 1, GGL_EINVAL, "spmm: heads must be >= 1");
   GGL_REQUIRE(heads == 1 || (w != nullptr && K % heads == 0), GGL_EINVAL, "spmm: heads=%d needs w and K %% heads == 0 (K=%lld)", heads, (long long)K);
   GGL_REQUIRE(arg == nullptr || reduce == GGL_MAX, GGL_EINVAL, "spmm: arg is only produced by GGL_MAX");
@@ -96,7 +96,7 @@ extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t
 
   SpmmArgs p;
   p.reduce = reduce; p.rowptr = rowptr; p.col = col; p.plan = plan; p.w = w; p.wperm = wperm; p.heads = heads;
-  p.x = x; p.out = out; p.arg = arg; p.arg_empty = arg_empty; p.out_scale = out_scale; p.n_rows = n_rows; p.E = E; p.K = K; p.n_src = n_src;
+  p.x = x; p.x_table = x_table; p.owner_shift = owner_shift; p.out = out; p.arg = arg; p.arg_empty = arg_empty; p.out_scale = out_scale; p.n_rows = n_rows; p.E = E; p.K = K; p.n_src = n_src;
   p.part_val = nullptr; p.part_arg = nullptr; p.stream = (cudaStream_t)stream;
   p.n_tiles = plan_n_tiles(E);
   p.tile_row = plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E));
@@ -123,4 +123,22 @@ extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t
     case GGL_I64: return launch_spmm<int64_t>(p);
     default: return set_error(GGL_EUNSUPPORTED, "spmm: unknown dtype %d", dtype);
   }
+}
+
+extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
+                                const float* w, const int32_t* wperm, int32_t heads, const void* x, void* out,
+                                int64_t* arg, int64_t arg_empty, const float* out_scale, int64_t n_rows, int64_t n_src,
+                                int64_t E, int64_t K, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  return spmm_entry(nullptr, 0, reduce, rowptr, col, plan, w, wperm, heads, x, out, arg, arg_empty, out_scale, n_rows, n_src, E, K,
+                    dtype, workspace, workspace_bytes, stream);
+}
+
+extern "C" int gglb200_spmm_csr_peer(int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
+                                     const float* w, const int32_t* wperm, int32_t heads, const void* const* x_table,
+                                     int32_t owner_shift, void* out, const float* out_scale, int64_t n_rows, int64_t E,
+                                     int64_t K, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  GGL_REQUIRE(x_table != nullptr && owner_shift >= 1 && owner_shift <= 30, GGL_EINVAL, "spmm_peer: bad x_table / owner_shift");
+  GGL_REQUIRE(reduce == GGL_SUM || reduce == GGL_MEAN, GGL_EUNSUPPORTED, "spmm_peer: sum / mean only");
+  return spmm_entry(x_table, owner_shift, reduce, rowptr, col, plan, w, wperm, heads, nullptr, out, nullptr, 0, out_scale, n_rows,
+                    (int64_t)1 << owner_shift, E, K, dtype, workspace, workspace_bytes, stream);
 }

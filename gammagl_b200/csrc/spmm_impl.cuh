@@ -44,6 +44,8 @@ struct SpmmArgs {
   const int32_t* wperm;     // NULL => w already in CSR order
   int32_t heads;            // 1 => w[E]; H => w[E,H]
   const void* x;
+  const void* const* x_table;  // NULL, or device array of per-rank base pointers of x (peer memory over NVLink)
+  int32_t owner_shift;      // peer mode: col = owner << owner_shift | local row
   void* out;
   int64_t* arg;             // MAX only, may be NULL
   int64_t arg_empty;
@@ -484,7 +486,17 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
       __syncwarp(gmask);  // every lane of the group has finished reading this stage (slot s - STAGES)
       if constexpr (ALIGNED) {
         if (sub == 0) mbar_arrive_expect_tx(bar, (uint32_t)nv * rowb);
-        if (sub < nv) bulk_copy_g2s(dst + (uint32_t)sub * pitch, xt + (int64_t)c * K, rowb, bar);
+        if (sub < nv) {
+          const T* rowp;
+          if (p.x_table) {  // 1-D node partition: the row lives in the HBM of GPU `owner`; fetched over NVLink by the same bulk copy
+            const int32_t owner = c >> p.owner_shift, local = c & ((1 << p.owner_shift) - 1);
+            rowp = reinterpret_cast<const T*>(__ldg(reinterpret_cast<const unsigned long long*>(p.x_table) + owner)) +
+                   (int64_t)blockIdx.y * LPR * VEC + (int64_t)local * K;
+          } else {
+            rowp = xt + (int64_t)c * K;
+          }
+          bulk_copy_g2s(dst + (uint32_t)sub * pitch, rowp, rowb, bar);
+        }
       } else if (sub < R) {
         const uint64_t a0 = (uint64_t)(xt + (int64_t)c * K) & ~(uint64_t)15;
         if (sub < nv && a0 <= lim) {
@@ -683,8 +695,13 @@ int launch_config(const SpmmArgs& p) {
   // floating rows of at least 4 lanes stream through the shared-memory ring; the rest (K <= 4 elements per row,
   // f64, integers) through the register-staged kernels
   if constexpr (Elem<T>::is_float && sizeof(T) <= 4 && LPR >= 4) {
-    if (tune_ring() != 0) return launch_ring<T, VEC, LPR, WMODE, ISMAX>(p, tiles);
+    if (tune_ring() != 0 || p.x_table) {
+      GGL_REQUIRE(p.x_table == nullptr || (sizeof(T) * VEC == 16 && !ISMAX), GGL_EUNSUPPORTED,
+                  "spmm: peer-memory gather needs 16-byte aligned rows (K*sizeof(T) %% 16 == 0) and sum/mean");
+      return launch_ring<T, VEC, LPR, WMODE, ISMAX>(p, tiles);
+    }
   }
+  GGL_REQUIRE(p.x_table == nullptr, GGL_EUNSUPPORTED, "spmm: peer-memory gather is not available for this dtype / row width");
   const int64_t groups_per_block = (int64_t)kWarpsPerBlock * GPW;
   const int64_t blocks = (p.n_tiles + groups_per_block - 1) / groups_per_block;
   GGL_REQUIRE(blocks < INT32_MAX, GGL_EUNSUPPORTED, "spmm: grid too large");

@@ -163,3 +163,145 @@ def dist_gspmm_sum(plan, x_local, weight=None, reduce_fn=None):
     """out_local[i] = sum over in-edges (j -> i) of weight[e] * x[j], x partitioned by rows over the group.
     weight: [E_g] fp32 aligned with the rank's local edge list (or None)."""
     return _DistSpMMSum.apply(x_local, weight, plan, reduce_fn or _cuda_reduce)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Peer-memory variant: ONE kernel does gather + transfer + reduce (no pack / all-to-all / halo buffer)
+# ----------------------------------------------------------------------------------------------------------------------
+OWNER_SHIFT = 27    # col = owner << 27 | local row : up to 134 M rows per GPU, 16 GPUs
+
+
+def _encode(ids, B):
+    return (torch.div(ids, B, rounding_mode='floor') << OWNER_SHIFT) | (ids % B)
+
+
+class PeerGraph:
+    """1-D node partition whose aggregation kernel reads remote feature rows straight from the owner's HBM over
+    NVLink (gglb200_spmm_csr_peer): the bulk async copies that stage rows into shared memory simply carry peer
+    addresses, so the transfer overlaps the reduction tile by tile.  Feature shards live in symmetric memory
+    (torch.distributed._symmetric_memory: CUDA IPC mappings of every rank's buffer); the only synchronisation per
+    pass is a device-side barrier before (all shards written) and after (all shards read).
+
+    Forward uses the in-edges of the owned nodes (rows = local dst, col = encoded global src); backward uses their
+    out-edges (rows = local src, col = encoded global dst), obtained once at plan time by an all-to-all of the
+    edge list -- so the backward pass is a pull as well and needs no scatter / reduction across GPUs."""
+
+    def __init__(self, edge_index_local, N, group=None):
+        from .csr import build_csr
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.N = int(N)
+        self.B = rows_per_rank(self.N, self.world)
+        if self.B >= (1 << OWNER_SHIFT) or self.world > 16:
+            raise ValueError('PeerGraph supports up to 16 GPUs and 2^27 rows per GPU')
+        self.lo, self.hi = owned_range(self.N, self.world, self.rank)
+        self.n_local = self.hi - self.lo
+        src, dst = edge_index_local[0], edge_index_local[1]
+        dev = src.device
+        self.E = int(src.numel())
+        self.fwd = build_csr(dst - self.lo, _encode(src, self.B), self.n_local)
+        # out-edges of the owned nodes: bucket the local edge list by the owner of its source and exchange
+        owner = torch.div(src, self.B, rounding_mode='floor')
+        order = torch.argsort(owner, stable=True)
+        counts = torch.bincount(owner, minlength=self.world)
+        cnt_out = torch.empty_like(counts)
+        _all_to_all(cnt_out, counts, None, None, self.group)
+        send_counts = [int(c) for c in counts.tolist()]
+        recv_counts = [int(c) for c in cnt_out.tolist()]
+        pairs = torch.stack([src[order], dst[order]], dim=1).contiguous()          # [E, 2]
+        got = pairs.new_empty((sum(recv_counts), 2))
+        _all_to_all(got, pairs, recv_counts, send_counts, self.group)
+        self.E_out = int(got.shape[0])
+        self.bwd = build_csr(got[:, 0] - self.lo, _encode(got[:, 1], self.B), self.n_local)
+        self.device = dev
+        self._bufs = {}
+
+    def _symm(self, tag, K, dtype):
+        """Symmetric [B, K] buffer + handle (allocated once per (tag, K, dtype); collective call)."""
+        import torch.distributed._symmetric_memory as symm
+        key = (tag, K, dtype)
+        if key not in self._bufs:
+            name = self.group.group_name
+            try:
+                symm.enable_symm_mem_for_group(name)
+            except Exception:
+                pass
+            t = symm.empty((self.B, K), dtype=dtype, device=self.device)
+            hdl = symm.rendezvous(t, self.group)
+            self._bufs[key] = (t, hdl)
+        return self._bufs[key]
+
+    def _pull(self, csr, tag, x_local, in_scale, out_scale):
+        from . import _lib, mpops
+        from .csr import _ptr, _stream
+        lib = _lib.load()
+        K = x_local.shape[1]
+        buf, hdl = self._symm(tag, K, x_local.dtype)
+        dev = x_local.device
+        with torch.cuda.device(dev):
+            _lib.tune_device(dev.index)
+            shard = buf[:self.n_local]
+            if in_scale is not None:
+                _lib.check(lib.gglb200_scale_rows(_ptr(x_local), _ptr(in_scale), _ptr(shard), self.n_local, K,
+                                                  mpops._dtype_code(x_local), _stream(dev)), 'scale_rows')
+            else:
+                shard.copy_(x_local)
+            hdl.barrier(channel=0)                       # every shard is complete
+            out = torch.empty((self.n_local, K), dtype=x_local.dtype, device=dev)
+            ws, nb = csr.workspace(K, _lib.GGL_SUM)
+            if mpops.PROFILE is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            _lib.check(lib.gglb200_spmm_csr_peer(_lib.GGL_SUM, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.plan), None, None, 1,
+                                                 ctypes_ptr(hdl.buffer_ptrs_dev), OWNER_SHIFT, _ptr(out), _ptr(out_scale),
+                                                 self.n_local, csr.E, K, mpops._dtype_code(x_local), _ptr(ws), nb, _stream(dev)),
+                       'spmm_csr_peer')
+            if mpops.PROFILE is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                mpops.PROFILE.append((self.n_local, ev0, ev1))
+            hdl.barrier(channel=1)                       # every rank has finished reading the shards
+        return out
+
+    def degree_norms(self, power=-0.5):
+        """(deg_out^power, deg_in^power) of the owned nodes (0 for isolated ones), from the two local CSRs."""
+        from . import _lib
+        from .csr import _ptr, _stream
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            ns = torch.empty(self.n_local, dtype=torch.float32, device=self.device)
+            nd = torch.empty(self.n_local, dtype=torch.float32, device=self.device)
+            _lib.check(lib.gglb200_degree_power(_ptr(self.bwd.rowptr), _ptr(ns), self.n_local, power, _stream(self.device)), 'degree_power')
+            _lib.check(lib.gglb200_degree_power(_ptr(self.fwd.rowptr), _ptr(nd), self.n_local, power, _stream(self.device)), 'degree_power')
+        return ns, nd
+
+
+def ctypes_ptr(v):
+    import ctypes
+    return ctypes.c_void_p(int(v))
+
+
+class _PeerGcnPropagate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_local, graph, ns, nd):
+        ctx.graph, ctx.ns, ctx.nd = graph, ns, nd
+        return graph._pull(graph.fwd, 'x', x_local.contiguous(), ns, nd)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g = ctx.graph
+        return g._pull(g.bwd, 'g', grad_out.contiguous(), ctx.nd, ctx.ns), None, None, None
+
+
+def peer_gcn_propagate(graph, x_local, norm='both'):
+    """out_local = (D_in^-1/2 A D_out^-1/2 x)[owned rows] for norm='both' (GCNConv with unit edge weights), or the plain
+    neighbourhood sum for norm='none'; x is partitioned by rows over the group; forward and backward are single fused
+    gather+reduce kernels over peer memory."""
+    if norm == 'both':
+        ns, nd = graph.degree_norms(-0.5)
+    elif norm == 'none':
+        ns = nd = None
+    else:
+        raise ValueError("norm must be 'both' or 'none'")
+    return _PeerGcnPropagate.apply(x_local, graph, ns, nd)

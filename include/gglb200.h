@@ -152,6 +152,17 @@ GGL_API int    gglb200_spmm_csr(int reduce,
                         int64_t n_rows, int64_t n_src, int64_t E, int64_t K, int dtype,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Multi-GPU variant (1-D node partition): the same kernel with x spread over the GPUs of one node.
+ * x_table is a DEVICE array of P base pointers (x shard of every rank, mapped into this process: CUDA IPC /
+ * symmetric memory; all shards [rows_r, K] with the same K and dtype) and col[i] = owner << owner_shift | local_row.
+ * Remote rows are fetched by the same bulk async copies straight from the owner's HBM over NVLink, so the
+ * transfer overlaps the reduction tile by tile -- no pack / all-to-all / halo buffer.  Requires K*sizeof(dtype) % 16
+ * == 0, GGL_SUM or GGL_MEAN.  The caller orders the kernel after every rank has finished writing its shard. */
+GGL_API int gglb200_spmm_csr_peer(int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
+                          const float* w, const int32_t* wperm, int32_t heads, const void* const* x_table,
+                          int32_t owner_shift, void* out, const float* out_scale, int64_t n_rows, int64_t E,
+                          int64_t K, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Backward helpers of the segment ops (src/segment_sum.cpp:43-54, src/segment_mean.cpp:44-63,
  * src/segment_max.cpp:48-61).

@@ -65,3 +65,74 @@ def test_partitioned_aggregation_two_ranks_one_gpu():
     deg = np.bincount(ei[1], minlength=N)
     assert np.array_equal(out[deg <= 1024], ref[deg <= 1024])          # unsplit rows bit-exact across the partition
     assert np.max(np.abs(gx - gref)) <= 1e-5 * np.max(np.abs(gref))
+
+
+def _peer_worker(rank, world, init_file, N, E, K, seed, q):
+    from gammagl_b200 import partition as P
+    multi = torch.cuda.device_count() >= world          # one GPU per rank + NCCL when the box has them
+    torch.cuda.set_device(rank if multi else 0)
+    dist.init_process_group('nccl' if multi else 'gloo', init_method='file://' + init_file, rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(seed)
+        ei = torch.randint(0, N, (2, E), generator=g)
+        x = torch.randn(N, K, generator=g)
+        gout = torch.randn(N, K, generator=g)
+        lo, hi = P.owned_range(N, world, rank)
+        m = (ei[1] >= lo) & (ei[1] < hi)
+        try:
+            graph = P.PeerGraph(ei[:, m].cuda(), N)
+            res = {}
+            for norm in ('none', 'both'):
+                x_local = x[lo:hi].cuda().requires_grad_(True)
+                out = P.peer_gcn_propagate(graph, x_local, norm)
+                out.backward(gout[lo:hi].cuda())
+                torch.cuda.synchronize()
+                res[norm] = (out.detach().cpu().numpy(), x_local.grad.cpu().numpy())
+            q.put((rank, 'ok', res))
+        except Exception as e:  # symmetric memory may be unavailable for two ranks on one device
+            import traceback
+            q.put((rank, 'error', traceback.format_exc()[-1500:]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_gather_two_ranks():
+    """gglb200_spmm_csr_peer: remote rows bulk-copied from the other rank's shard (symmetric memory / CUDA IPC).
+    Needs two GPUs (torch's symmetric memory refuses two ranks on one device): skipped on a 1-GPU box, exercised by
+    `gpurun --gpus 2 -- python -m pytest tests/test_gpu_partition.py -m gpu`."""
+    from oracle import oracle as O
+    N, E, K, world, seed = 4000, 90000, 100, 2, 9
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    with tempfile.TemporaryDirectory() as d:
+        procs = [ctx.Process(target=_peer_worker, args=(r, world, os.path.join(d, 'rdzv'), N, E, K, seed, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=300) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+    res.sort(key=lambda t: t[0])
+    if any(r[1] != 'ok' for r in res):
+        pytest.skip('symmetric memory not usable in this environment: ' + str([r[2] for r in res if r[1] != 'ok'][0]))
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, N, (2, E), generator=g)
+    x = torch.randn(N, K, generator=g)
+    gout = torch.randn(N, K, generator=g)
+    src, dst = ei.numpy()
+    for norm in ('none', 'both'):
+        w = np.ones(E, dtype=np.float32)
+        if norm == 'both':
+            ns = np.bincount(src, minlength=N).astype(np.float64) ** -0.5
+            nd = np.bincount(dst, minlength=N).astype(np.float64) ** -0.5
+            ns[~np.isfinite(ns)] = 0
+            nd[~np.isfinite(nd)] = 0
+            w = (ns[src] * nd[dst]).astype(np.float32)
+        ref, _ = O.spmm_fwd('sum', ei.numpy(), w, x.numpy())
+        gref = O.spmm_bwd('sum', ei.numpy(), w, gout.numpy())
+        out = np.concatenate([r[2][norm][0] for r in res])
+        gx = np.concatenate([r[2][norm][1] for r in res])
+        assert np.max(np.abs(out - ref)) <= 1e-5 * np.max(np.abs(ref)), norm
+        assert np.max(np.abs(gx - gref)) <= 1e-5 * np.max(np.abs(gref)), norm
+        if norm == 'none':
+            assert np.array_equal(out, ref)        # same per-row edge order as the serial loop => bit-exact
