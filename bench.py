@@ -554,10 +554,13 @@ def run_c5part(args):
                        'halo_rows_per_gpu_max': int(halo.item()), 'halo_bytes_per_pass_per_gpu': int(halo.item()) * K * 4,
                        'plan_build_ms': plan_ms, 'l2': 'inputs exceed the 126 MB L2; no explicit flush'},
             'roofline': {'bound': 'hbm', 'achieved': alg / (kavg * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-                         'frac': alg / (kavg * 1e-3) / 1e9 / peak, 'traffic': None, 'kernel': 'spmm_ring_kernel (local SpMM only)',
+                         'frac': alg / (kavg * 1e-3) / 1e9 / peak, 'traffic': None,
+                         'kernel': 'spmm_ring_kernel' + (' (peer-memory gather: remote rows over NVLink inside the kernel; NVLink-bound on '
+                                                         'low-locality graphs, see nvlink_GBps_in)' if args.peer else ' (local SpMM only)'),
                          'algorithmic_bytes_per_launch': alg, 'avg_launch_ms': kavg, 'peak_source': peak_src},
             'exchange': {'ms_per_step_not_in_spmm': ms - 2 * kavg,
-                         'note': 'pack + all_to_all + index_add, forward and backward; not overlapped with the SpMM in round 1'},
+                         'note': ('row scaling + 2 device-side barriers per pass; remote rows are fetched inside the SpMM kernel'
+                                  if args.peer else 'pack + all_to_all + index_add, forward and backward; not overlapped with the SpMM')},
             'e2e': None, 'cpu_baseline': None, 'gpu_launches': int(launches), 'clocks': clocks,
         }
         print(json.dumps(line))

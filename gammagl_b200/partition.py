@@ -222,11 +222,6 @@ class PeerGraph:
         import torch.distributed._symmetric_memory as symm
         key = (tag, K, dtype)
         if key not in self._bufs:
-            name = self.group.group_name
-            try:
-                symm.enable_symm_mem_for_group(name)
-            except Exception:
-                pass
             t = symm.empty((self.B, K), dtype=dtype, device=self.device)
             hdl = symm.rendezvous(t, self.group)
             self._bufs[key] = (t, hdl)
