@@ -72,3 +72,49 @@ def test_segment_ops_fullsize_k1_and_max(big):
     ref = torch.full((n, 8), float('-inf'), device=DEV).scatter_reduce(0, dst[:, None].expand(-1, 8), msg, 'amax')
     has = torch.bincount(dst, minlength=n) > 0
     assert torch.equal(mx[has], ref[has])
+
+
+def test_gat_path_fullsize_properties():
+    """C4 (Reddit shape: 232,965 nodes / 114,615,892 edges, H=8, C=8): softmax rows sum to one, the SDDMM is the adjoint
+    of bspmm in the weight argument (<bspmm(dw, x), g> == <dw, sddmm(x, g)>), bspmm is the adjoint pair with its
+    backward in x, and the layer-level fused GAT aggregation is deterministic."""
+    import bench
+    from gammagl_b200 import mpops
+    free, _ = torch.cuda.mem_get_info()
+    scale = 1.0 if free > 40e9 else 0.1
+    n, e, H, C = int(232965 * scale), int(114615892 * scale), 8, 8
+    ei = bench.gen_graph(torch, n, e, 'rmat', 99, torch.device(DEV))
+    g = torch.Generator(device=DEV).manual_seed(5)
+    logit = (torch.randn(e, H, generator=g, device=DEV) * 2).requires_grad_(True)
+    x = torch.randn(n, H, C, generator=g, device=DEV).requires_grad_(True)
+    gy = torch.randn(n, H, C, generator=g, device=DEV)
+    alpha = mpops.segment_softmax(logit, ei[1], n)
+    s = torch.zeros(n, H, device=DEV, dtype=torch.float64).index_add_(0, ei[1], alpha.detach().double())
+    has = torch.bincount(ei[1], minlength=n) > 0
+    assert float((s[has] - 1).abs().max()) < 1e-5
+    assert float(alpha.min()) >= 0.0
+    out = mpops.bspmm(ei, alpha, x)
+    out.backward(gy)
+    # adjoint in x: <bspmm(alpha, x), gy> == <x, grad_x>
+    lhs = float((out.detach().double() * gy.double()).sum())
+    rhs = float((x.detach().double() * x.grad.double()).sum())
+    nrm = float((out.detach().double().abs() * gy.double().abs()).sum())
+    assert abs(lhs - rhs) / nrm < 1e-6
+    # adjoint in the weights: bspmm is linear in alpha, so <bspmm(alpha, x), gy> == <alpha, sddmm(x, gy)>
+    from gammagl_b200 import _lib
+    from gammagl_b200.csr import _ptr, _stream, graph_of
+    gr = graph_of(ei, n)
+    gw = torch.empty(e, H, device=DEV)
+    lib = _lib.load()
+    _lib.check(lib.gglb200_bspmm_bwd_w(_ptr(gr.fwd.rowptr), _ptr(gr.fwd.col), _ptr(gr.fwd.perm), _ptr(gr.fwd.plan),
+                                       _ptr(x.detach().view(n, H * C)), _ptr(gy.view(n, H * C)), _ptr(gw), n, e, H, C,
+                                       _stream(torch.device(DEV))))
+    rhs_w = float((alpha.detach().double() * gw.double()).sum())
+    assert abs(lhs - rhs_w) / nrm < 1e-6
+    # softmax gradient: rows of glogit sum to zero (softmax is shift invariant)
+    # (measured against the row's sum of alpha * |d out / d alpha|: the individual terms cancel)
+    z = torch.zeros(n, H, device=DEV, dtype=torch.float64).index_add_(0, ei[1], logit.grad.double())
+    za = torch.zeros(n, H, device=DEV, dtype=torch.float64).index_add_(0, ei[1], (alpha.detach() * gw.abs()).double())
+    assert float((z.abs() / za.clamp_min(1e-30))[has].max()) < 1e-4
+    out2 = mpops.bspmm(ei, mpops.segment_softmax(logit.detach(), ei[1], n), x.detach())
+    assert torch.equal(out.detach(), out2)
