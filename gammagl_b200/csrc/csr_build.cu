@@ -106,6 +106,29 @@ __global__ void __launch_bounds__(256) tile_rows_kernel(const int32_t* __restric
   }
 }
 
+// ind2ptr / ptr2ind on int64, the types of gammagl/ops/sparse/sparse.py:38-75 (cpu/convert.cpp:58-128)
+__global__ void __launch_bounds__(256) ind2ptr_i64_kernel(const int64_t* __restrict__ ind, int64_t* __restrict__ ptr, int64_t E, int64_t M) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i <= E; i += stride) {
+    int64_t lo = (i == 0) ? 0 : ind[i - 1] + 1;
+    int64_t hi = (i == E) ? M : ind[i];
+    for (int64_t r = lo; r <= hi; ++r) ptr[r] = i;
+  }
+}
+__global__ void __launch_bounds__(256) ptr2ind_i64_kernel(const int64_t* __restrict__ ptr, int64_t* __restrict__ ind, int64_t M, int64_t E) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; e < E; e += stride) {
+    int64_t lo = 0, hi = M;  // last r in [0, M) with ptr[r] <= e
+    while (hi - lo > 1) {
+      int64_t mid = (lo + hi) >> 1;
+      if (ptr[mid] <= e) lo = mid; else hi = mid;
+    }
+    ind[e] = lo;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) permute_rows_kernel(const T* __restrict__ in, const int32_t* __restrict__ perm,
                                                            T* __restrict__ out, int64_t n, int32_t width) {
@@ -227,5 +250,28 @@ extern "C" int gglb200_permute_rows(const void* in, const int32_t* perm, void* o
         (const uint8_t*)in, perm, (uint8_t*)out, n, (int32_t)row_bytes);
   }
   GGL_LAUNCHED("permute_rows");
+  return GGL_OK;
+}
+
+extern "C" int gglb200_ind2ptr(const int64_t* ind, int64_t E, int64_t M, int64_t* ptr, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(E >= 0 && M >= 0, GGL_EINVAL, "ind2ptr: negative size");
+  GGL_REQUIRE(ptr && (E == 0 || ind), GGL_EINVAL, "ind2ptr: NULL pointer");
+  if (E == 0) {
+    GGL_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int64_t) * (size_t)(M + 1), stream));
+    return GGL_OK;
+  }
+  ind2ptr_i64_kernel<<<grid_for(E + 1), 256, 0, stream>>>(ind, ptr, E, M);
+  GGL_LAUNCHED("ind2ptr");
+  return GGL_OK;
+}
+
+extern "C" int gglb200_ptr2ind(const int64_t* ptr, int64_t M, int64_t E, int64_t* ind, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(E >= 0 && M >= 0, GGL_EINVAL, "ptr2ind: negative size");
+  if (E == 0) return GGL_OK;
+  GGL_REQUIRE(ptr && ind && M > 0, GGL_EINVAL, "ptr2ind: NULL pointer or no rows");
+  ptr2ind_i64_kernel<<<grid_for(E), 256, 0, stream>>>(ptr, ind, M, E);
+  GGL_LAUNCHED("ptr2ind");
   return GGL_OK;
 }

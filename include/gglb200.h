@@ -106,6 +106,11 @@ GGL_API int    gglb200_csr_build(const int64_t* key, const int64_t* other, int64
                          int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* plan,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ind2ptr / ptr2ind of gammagl/ops/sparse/sparse.py:38-75 (cpu/convert.cpp:58-128, cuda/convert.cu:41-127) on int64:
+ * ptr[M+1] from a SORTED row index ind[E] (empty rows allowed), and its inverse ind[E] from ptr[M+1]. */
+GGL_API int gglb200_ind2ptr(const int64_t* ind, int64_t E, int64_t M, int64_t* ptr, void* stream);
+GGL_API int gglb200_ptr2ind(const int64_t* ptr, int64_t M, int64_t E, int64_t* ind, void* stream);
+
 /* out[i] = in[perm[i]] for i < n; `width` consecutive elements of `elem_bytes` (4 or 8 ... any
  * multiple of 4) per index.  Used to bring edge weights into CSR order once per (graph, weight). */
 GGL_API int gglb200_permute_rows(const void* in, const int32_t* perm, void* out, int64_t n, int64_t row_bytes,

@@ -191,3 +191,9 @@ void ind2ptr_i64(const int64_t* ind, int64_t E, int64_t M, int64_t* ptr) {
   for (int64_t e = 0; e < E; ++e) ptr[ind[e] + 1]++;
   for (int64_t i = 0; i < M; ++i) ptr[i + 1] += ptr[i];
 }
+
+/* ptr2ind, gammagl/ops/sparse/cpu/convert.cpp:103-128 (CSR pointer -> row id of every element) */
+void ptr2ind_i64(const int64_t* ptr, int64_t M, int64_t E, int64_t* ind) {
+  for (int64_t i = 0; i < M; ++i)
+    for (int64_t e = ptr[i]; e < ptr[i + 1] && e < E; ++e) ind[e] = i;
+}

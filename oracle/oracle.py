@@ -162,3 +162,10 @@ def ind2ptr(ind, M):
     ptr = np.zeros(M + 1, dtype=np.int64)
     lib().ind2ptr_i64(_p(ind), _i64(ind.shape[0]), _i64(M), _p(ptr))
     return ptr
+
+
+def ptr2ind(ptr, E):
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    ind = np.zeros(E, dtype=np.int64)
+    lib().ptr2ind_i64(_p(ptr), _i64(ptr.shape[0] - 1), _i64(E), _p(ind))
+    return ind

@@ -351,3 +351,44 @@ def test_determinism_and_cache_identity(mp):
     assert rel_err(c.cpu().numpy(), ref) < 1e-5
     index.add_(0)                      # in-place op bumps _version -> cache miss, still correct
     assert torch.equal(mp.gspmm(index, w, x), a)
+
+
+def test_sparse_structures_vs_oracle(mp):
+    """gammagl_b200.sparse: ind2ptr / ptr2ind (convert.cpp:58-128), CSRAdj.from_edges (sparse_adj.py:47-67) and the
+    COO/CSR/CSC views + matmul of SparseGraph, against numpy / the oracle."""
+    from gammagl_b200 import sparse as S
+    N, E, K = 700, 9000, 24
+    index = make_graph(N, E, seed=41, hub=1500)
+    row, col = index[0], index[1]
+    srt = np.sort(row.numpy())
+    ptr = S.ind2ptr(cu(srt), N)
+    assert ptr.dtype == torch.int64 and np.array_equal(ptr.cpu().numpy(), O.ind2ptr(srt, N))
+    assert np.array_equal(S.ptr2ind(ptr, E).cpu().numpy(), O.ptr2ind(ptr.cpu().numpy(), E))
+    assert np.array_equal(S.ptr2ind(ptr, E).cpu().numpy(), srt)
+    adj = S.CSRAdj.from_edges(cu(row), cu(col), N)
+    order = np.argsort(row.numpy(), kind='stable')
+    assert np.array_equal(adj.degree.cpu().numpy(), np.bincount(row.numpy(), minlength=N))
+    assert np.array_equal(adj._sorted_eid.cpu().numpy(), order)
+    assert np.array_equal(adj._sorted_u.cpu().numpy(), row.numpy()[order])
+    assert np.array_equal(adj._sorted_v.cpu().numpy(), col.numpy()[order])
+    assert np.array_equal(adj._indptr.cpu().numpy(), O.ind2ptr(srt, N))
+    g = torch.Generator().manual_seed(2)
+    h = torch.randn(N, K, generator=g)
+    w = torch.rand(E, generator=g)
+    # A @ h with A[row, col] = w  ==  gspmm on edge_index (src = col, dst = row)
+    ref, _ = O.spmm_fwd('sum', np.stack([col.numpy(), row.numpy()]), w.numpy(), h.numpy())
+    got = adj.matmul(cu(h), cu(w)).cpu().numpy()
+    short = np.bincount(row.numpy(), minlength=N) <= 1024
+    assert np.array_equal(got[short], ref[short]) and rel_err(got, ref) < 1e-5
+    sg = S.SparseGraph.from_edge_index(cu(index), cu(w), (N, N))
+    assert rel_err(sg.matmul(cu(h)).cpu().numpy(), ref) < 1e-5
+    rp, ci, val = sg.csr()
+    assert np.array_equal(rp.cpu().numpy(), O.ind2ptr(srt, N)) and np.array_equal(ci.cpu().numpy(), col.numpy()[order])
+    assert np.array_equal(val.cpu().numpy(), w.numpy()[order])
+    cp, ri, _ = sg.csc()
+    corder = np.argsort(col.numpy(), kind='stable')
+    assert np.array_equal(ri.cpu().numpy(), row.numpy()[corder])
+    # csr2csc maps CSR element order to CSC element order
+    assert np.array_equal(val.cpu().numpy()[sg.csr2csc().cpu().numpy()], w.numpy()[corder])
+    reft, _ = O.spmm_fwd('sum', index.numpy(), w.numpy(), h.numpy())       # transposed: out[col] += w * h[row]
+    assert rel_err(sg.t().matmul(cu(h)).cpu().numpy(), reft) < 1e-5

@@ -131,3 +131,9 @@ def test_ind2ptr():
     """gammagl/ops/sparse/cpu/convert.cpp:58-90 semantics on a sorted row array with empty rows."""
     ind = np.array([0, 0, 2, 2, 2, 5], dtype=np.int64)
     assert O.ind2ptr(ind, 7).tolist() == [0, 2, 2, 5, 5, 5, 6, 6]
+
+
+def test_ptr2ind_inverts_ind2ptr():
+    ind = np.array([0, 0, 2, 2, 2, 5], dtype=np.int64)
+    ptr = O.ind2ptr(ind, 7)
+    assert np.array_equal(O.ptr2ind(ptr, 6), ind)
