@@ -137,3 +137,34 @@ def test_ptr2ind_inverts_ind2ptr():
     ind = np.array([0, 0, 2, 2, 2, 5], dtype=np.int64)
     ptr = O.ind2ptr(ind, 7)
     assert np.array_equal(O.ptr2ind(ptr, 6), ind)
+
+
+def test_oracle_vs_pure_torch_fallback_semantics():
+    """Second, independent restatement: the reference's pure-torch fallbacks
+    (/root/reference/gammagl/mpops/torch.py:10-40: scatter_add_ / scatter_reduce_(amax), empty max rows -> 0) agree with
+    the oracle everywhere except the documented empty-row value of max (lowest() in the compiled extension)."""
+    import torch
+    g = torch.Generator().manual_seed(77)
+    N, E, K = 83, 900, 6
+    ids = torch.randint(0, N - 9, (E,), generator=g)             # last 9 segments empty
+    x = torch.randn(E, K, generator=g)
+    idx = ids.view(-1, 1).expand_as(x)
+    fb_sum = torch.zeros(N, K).scatter_add_(0, idx, x)
+    cnt = torch.zeros(N).scatter_add_(0, ids, torch.ones(E)).clamp_min(1)
+    fb_mean = fb_sum / cnt.view(N, 1)
+    fb_max = torch.full((N, K), -torch.inf).scatter_reduce_(0, idx, x, reduce='amax', include_self=True)
+    fb_max = torch.where(torch.isinf(fb_max), torch.zeros_like(fb_max), fb_max)
+    o_sum = O.segment('sum', x.numpy(), ids.numpy(), N)
+    o_mean = O.segment('mean', x.numpy(), ids.numpy(), N)
+    o_max, _ = O.segment('max', x.numpy(), ids.numpy(), N)
+    assert np.allclose(o_sum, fb_sum.numpy(), rtol=1e-5, atol=1e-6)
+    assert np.allclose(o_mean, fb_mean.numpy(), rtol=1e-5, atol=1e-6)
+    nonempty = np.bincount(ids.numpy(), minlength=N) > 0
+    assert np.array_equal(o_max[nonempty], fb_max.numpy()[nonempty])
+    assert np.all(o_max[~nonempty] == np.finfo(np.float32).min) and np.all(fb_max.numpy()[~nonempty] == 0)
+    # gspmm fallback (torch.py:334-343): messages = x[src] * w, then the segment fallback over dst
+    ei = torch.randint(0, N, (2, E), generator=g)
+    xn = torch.randn(N, K, generator=g)
+    w = torch.rand(E, generator=g)
+    fb = torch.zeros(N, K).scatter_add_(0, ei[1].view(-1, 1).expand(E, K), xn[ei[0]] * w.view(-1, 1))
+    assert np.allclose(O.spmm_fwd('sum', ei.numpy(), w.numpy(), xn.numpy())[0], fb.numpy(), rtol=1e-5, atol=1e-6)
