@@ -40,6 +40,10 @@ SIGNATURES = {
     'gglb200_scale_rows_by_count': (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     'gglb200_spmm_max_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     'gglb200_bspmm_bwd_w': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
+    'gglb200_gat_workspace_bytes': (_sz, [_i64, _i32, _i32]),
+    'gglb200_gat_fwd': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _c.c_float, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _sz, _vp]),
+    'gglb200_gat_bwd_src': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _c.c_float, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _sz, _vp]),
+    'gglb200_gat_bwd_dst': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _c.c_float, _vp, _i64, _i64, _i32, _i32, _vp, _sz, _vp]),
     'gglb200_edge_softmax_workspace_bytes': (_sz, [_i64, _i32, _i64]),
     'gglb200_edge_softmax_fwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _sz, _vp]),
     'gglb200_edge_softmax_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _sz, _vp]),

@@ -190,8 +190,9 @@ class SAGEConv(MessagePassing):
 
 class GATConv(MessagePassing):
     def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout_rate=0., add_bias=True,
-                 fused=True):
+                 fused=True, fuse_attention=True):
         super().__init__(fused)
+        self.fuse_attention = fuse_attention
         self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
         self.negetive_slop, self.dropout_rate, self.add_bias = negative_slope, dropout_rate, add_bias
         self.w = torch.nn.Parameter(torch.nn.init.trunc_normal_(torch.empty(in_channels, out_channels * heads), std=0.05))
@@ -207,6 +208,12 @@ class GATConv(MessagePassing):
         # e = leaky_relu(sum_c concat(x[src], x[dst]) * att): the per-node halves are reduced before the gather
         # (same arithmetic association per half; avoids materialising [E, H, 2C])
         a_src, a_dst = self.att[..., :self.out_channels], self.att[..., self.out_channels:]
+        if (self.fused and self.fuse_attention and x.dtype == torch.float32 and num_nodes == x.shape[0]
+                and mpops.gat_fusable(self.heads, self.out_channels) and not (self.training and self.dropout_rate > 0)):
+            # logits, edge softmax and aggregation in one streaming pass per direction: no [E, H] tensor at all
+            out = mpops.gat_aggregate(edge_index, x, (x * a_src).sum(-1), (x * a_dst).sum(-1), self.negetive_slop)
+            out = out.reshape(-1, self.heads * self.out_channels) if self.concat else out.mean(dim=1)
+            return out + self.bias if self.add_bias else out
         if self.fused:
             e = (x * a_src).sum(-1)[node_src] + (x * a_dst).sum(-1)[node_dst]
         else:

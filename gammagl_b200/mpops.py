@@ -426,6 +426,85 @@ class _EdgeSoftmax(torch.autograd.Function):
         return gl, None, None
 
 
+def gat_fusable(H, C):
+    lh = C // 4
+    return C % 4 == 0 and lh >= 1 and (lh & (lh - 1)) == 0 and H * C <= 128
+
+
+class _GatAggregate(torch.autograd.Function):
+    """Fused GAT aggregation (csrc/gat_fused.cu): logits, edge softmax and the weighted neighbourhood sum in one streaming
+    pass per direction; no [E, H] tensor is ever materialised."""
+
+    @staticmethod
+    def _ws(csr, H, C, dev):
+        if not csr.has_long:
+            return None, 0
+        nb = _lib.load().gglb200_gat_workspace_bytes(csr.n_chunks, H, C)
+        return torch.empty(nb, dtype=torch.uint8, device=dev), nb
+
+    @staticmethod
+    def forward(ctx, x, s_src, s_dst, edge_index, slope):
+        lib = _lib.load()
+        for t, n in ((x, 'x'), (s_src, 's_src'), (s_dst, 's_dst'), (edge_index, 'edge_index')):
+            require_cuda(t, n)
+        N, H, C = x.shape
+        if x.dtype != torch.float32 or not gat_fusable(H, C):
+            raise _lib.GglError('gat_aggregate needs float32 x [N,H,C] with C %% 4 == 0, C/4 a power of two, H*C <= 128')
+        K = H * C
+        Hp = (H + 3) // 4 * 4
+        dev = x.device
+        g = graph_of(edge_index, N)
+        with torch.cuda.device(dev):
+            _lib.tune_device(dev.index)
+            xcat = torch.zeros((N, K + Hp), dtype=torch.float32, device=dev) if Hp != H else torch.empty((N, K + Hp), dtype=torch.float32, device=dev)
+            xcat[:, :K] = x.reshape(N, K)
+            xcat[:, K:K + H] = s_src
+            sd = s_dst.contiguous().float()
+            out = torch.empty((N, K), dtype=torch.float32, device=dev)
+            m = torch.empty((N, H), dtype=torch.float32, device=dev)
+            s = torch.empty((N, H), dtype=torch.float32, device=dev)
+            ws, nb = _GatAggregate._ws(g.fwd, H, C, dev)
+            _lib.check(lib.gglb200_gat_fwd(_ptr(g.fwd.rowptr), _ptr(g.fwd.col), _ptr(g.fwd.plan), _ptr(xcat), K + Hp, _ptr(sd),
+                                           float(slope), _ptr(out), _ptr(m), _ptr(s), N, g.E, H, C, _ptr(ws), nb, _stream(dev)),
+                       'gat_fwd')
+        ctx.graph, ctx.dims, ctx.slope = g, (N, H, C, Hp), float(slope)
+        ctx.save_for_backward(xcat, sd, out, m, s)
+        return out.view(N, H, C)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        xcat, sd, out, m, s = ctx.saved_tensors
+        N, H, C, Hp = ctx.dims
+        K = H * C
+        g = ctx.graph
+        dev = xcat.device
+        gout = grad_out.contiguous().view(N, K).float()
+        with torch.cuda.device(dev):
+            D = (out * gout).view(N, H, C).sum(-1)                           # row term of the softmax Jacobian, per node
+            gcat = torch.empty((N, K + 4 * H), dtype=torch.float32, device=dev)
+            gcat[:, :K] = gout
+            gcat[:, K:] = torch.stack([sd, m, s, D], dim=2).view(N, 4 * H)
+            gx = torch.empty((N, K), dtype=torch.float32, device=dev)
+            gs_src = torch.empty((N, H), dtype=torch.float32, device=dev)
+            gs_dst = torch.empty((N, H), dtype=torch.float32, device=dev)
+            ws, nb = _GatAggregate._ws(g.bwd, H, C, dev)
+            _lib.check(lib.gglb200_gat_bwd_src(_ptr(g.bwd.rowptr), _ptr(g.bwd.col), _ptr(g.bwd.plan), _ptr(gcat), K + 4 * H, _ptr(xcat),
+                                               K + Hp, ctx.slope, _ptr(gx), _ptr(gs_src), N, g.E, H, C, _ptr(ws), nb, _stream(dev)),
+                       'gat_bwd_src')
+            ws, nb = _GatAggregate._ws(g.fwd, H, C, dev)
+            _lib.check(lib.gglb200_gat_bwd_dst(_ptr(g.fwd.rowptr), _ptr(g.fwd.col), _ptr(g.fwd.plan), _ptr(xcat), K + Hp, _ptr(gcat),
+                                               K + 4 * H, ctx.slope, _ptr(gs_dst), N, g.E, H, C, _ptr(ws), nb, _stream(dev)),
+                       'gat_bwd_dst')
+        return gx.view(N, H, C), gs_src, gs_dst, None, None
+
+
+def gat_aggregate(edge_index, x, s_src, s_dst, negative_slope=0.2):
+    """out[i,h,:] = sum over in-edges (j -> i) of softmax_i(leaky_relu(s_src[j,h] + s_dst[i,h])) * x[j,h,:]
+    -- GATConv's attention + propagate (gat_conv.py:103-112) as one fused op; gradients for x, s_src and s_dst."""
+    return _GatAggregate.apply(x, s_src, s_dst, edge_index, negative_slope)
+
+
 def segment_softmax(data, segment_ids, num_segments):
     """softmax of `data` [E, ...] over the edges that share a segment id (gammagl/utils/softmax.py:10-36)."""
     return _EdgeSoftmax.apply(data, segment_ids, num_segments)
@@ -433,4 +512,4 @@ def segment_softmax(data, segment_ids, num_segments):
 
 __all__ = ['use_ext', 'unsorted_segment_sum', 'unsorted_segment_mean', 'unsorted_segment_max', 'segment_sum',
            'segment_mean', 'segment_max', 'gspmm', 'bspmm', 'c_segment_sum', 'c_segment_mean', 'c_segment_max',
-           'c_spmm_sum', 'c_spmm_mean', 'c_spmm_max', 'c_bspmm_sum', 'segment_softmax', 'gcn_propagate']
+           'c_spmm_sum', 'c_spmm_mean', 'c_spmm_max', 'c_bspmm_sum', 'segment_softmax', 'gcn_propagate', 'gat_aggregate']

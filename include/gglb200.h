@@ -226,6 +226,30 @@ GGL_API int gglb200_edge_softmax_bwd(const int32_t* rowptr, const int32_t* perm,
                              const float* alpha, const float* galpha, float* glogit, int64_t n_rows, int64_t E,
                              int32_t H, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused GAT aggregation (layers/conv/gat_conv.py:98-122 + utils/softmax.py:29-35) without any [E,H] tensor:
+ *   pre_e = s_src[j,h] + s_dst[i,h];  alpha = softmax_i(leaky_relu(pre));  out[i,h,:] = sum_e alpha_e x[j,h,:]
+ * fwd     forward CSR (rows = i, col = j).  xcat [N, xcat_stride] = [x (H*C) | s_src (H) | pad]; online softmax per
+ *         (row, head); writes out [N,H*C] and the softmax statistics stat_m / stat_s [N,H].
+ * bwd_src transposed CSR (rows = j, col = i).  gcat [N, H*C + 4H] = [gout | {s_dst, m, s, D} per head] with
+ *         D[i,h] = <out[i,h,:], gout[i,h,:]>; writes grad x [N,H*C] and grad s_src [N,H].
+ * bwd_dst forward CSR again; writes grad s_dst [N,H].
+ * Requires C % 4 == 0, C/4 a power of two, H*C <= 128, fp32, 16-byte aligned rows.  workspace:
+ * gglb200_gat_workspace_bytes(n_chunks of that CSR, H, C) (NULL only if the CSR has no row above GGLB200_LONG_ROW).
+ * ------------------------------------------------------------------------------------------- */
+GGL_API size_t gglb200_gat_workspace_bytes(int64_t n_chunks, int32_t H, int32_t C);
+GGL_API int gglb200_gat_fwd(const int32_t* rowptr, const int32_t* col, const int32_t* plan, const float* xcat,
+                    int64_t xcat_stride, const float* s_dst, float slope, float* out, float* stat_m, float* stat_s,
+                    int64_t n_rows, int64_t E, int32_t H, int32_t C, void* workspace, size_t workspace_bytes, void* stream);
+GGL_API int gglb200_gat_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* plan_t, const float* gcat,
+                        int64_t gcat_stride, const float* xcat, int64_t xcat_stride, float slope, float* gx,
+                        float* gs_src, int64_t n_rows, int64_t E, int32_t H, int32_t C, void* workspace,
+                        size_t workspace_bytes, void* stream);
+GGL_API int gglb200_gat_bwd_dst(const int32_t* rowptr, const int32_t* col, const int32_t* plan, const float* xcat,
+                        int64_t xcat_stride, const float* gcat, int64_t gcat_stride, float slope, float* gs_dst,
+                        int64_t n_rows, int64_t E, int32_t H, int32_t C, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,3 +118,23 @@ def test_gat_path_fullsize_properties():
     assert float((z.abs() / za.clamp_min(1e-30))[has].max()) < 1e-4
     out2 = mpops.bspmm(ei, mpops.segment_softmax(logit.detach(), ei[1], n), x.detach())
     assert torch.equal(out.detach(), out2)
+
+
+def test_fused_gat_matches_unfused_ops_fullsize():
+    """C4 size: mpops.gat_aggregate (fused, online softmax) == leaky_relu -> segment_softmax -> bspmm on the same inputs."""
+    import bench
+    from gammagl_b200 import mpops
+    free, _ = torch.cuda.mem_get_info()
+    scale = 1.0 if free > 60e9 else 0.1
+    n, e, H, C = int(232965 * scale), int(114615892 * scale), 8, 8
+    ei = bench.gen_graph(torch, n, e, 'rmat', 98, torch.device(DEV))
+    g = torch.Generator(device=DEV).manual_seed(6)
+    x = torch.randn(n, H, C, generator=g, device=DEV)
+    ss = torch.randn(n, H, generator=g, device=DEV) * 2
+    sd = torch.randn(n, H, generator=g, device=DEV) * 2
+    fused = mpops.gat_aggregate(ei, x, ss, sd, 0.2)
+    logit = torch.nn.functional.leaky_relu(ss[ei[0]] + sd[ei[1]], 0.2)
+    ref = mpops.bspmm(ei, mpops.segment_softmax(logit, ei[1], n), x)
+    err = float((fused - ref).abs().max() / ref.abs().max())
+    assert err < 2e-5, err
+    assert torch.equal(fused, mpops.gat_aggregate(ei, x, ss, sd, 0.2))      # deterministic

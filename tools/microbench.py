@@ -73,6 +73,21 @@ def main(cfg):
     report('segment_softmax fwd H=%d (max+exp+sum+div)' % H, timeit(lambda: mpops.segment_softmax(lg, dst_ids, N)), E, E * (2 * 4 * H + 8), cfg=cfg)
     al = mpops.segment_softmax(lg, dst_ids, N)
     report('segment_softmax bwd', timeit(lambda: al.backward(wh, retain_graph=True)), E, E * (3 * 4 * H + 8), cfg=cfg)
+    if mpops.gat_fusable(H, C):
+        xs3 = x.view(N, H, C).clone().requires_grad_(True)
+        ssrc = torch.randn(N, H, generator=g, device=dev).requires_grad_(True)
+        sdst = torch.randn(N, H, generator=g, device=dev).requires_grad_(True)
+        report('gat_aggregate fwd (logits+softmax+bspmm fused)', timeit(lambda: mpops.gat_aggregate(ei, xs3, ssrc, sdst, 0.2)), E, bs_b - 4 * H * E, cfg=cfg)
+        og = mpops.gat_aggregate(ei, xs3, ssrc, sdst, 0.2)
+        gy = torch.randn_like(og)
+        report('gat_aggregate bwd (2 passes: grad x, s_src | grad s_dst)', timeit(lambda: og.backward(gy, retain_graph=True)), E, 2 * (bs_b - 4 * H * E), cfg=cfg)
+        # the composition it replaces, end to end through the unfused operators
+        def unfused():
+            e = torch.nn.functional.leaky_relu(ssrc[ei[0]] + sdst[ei[1]], 0.2)
+            return mpops.bspmm(ei, mpops.segment_softmax(e, ei[1], N), xs3)
+        report('  unfused: gathers + leaky_relu + segment_softmax + bspmm fwd', timeit(unfused, reps=5, warm=2), E, bs_b, cfg=cfg)
+        ou = unfused()
+        report('  unfused: backward of the same', timeit(lambda: ou.backward(gy, retain_graph=True), reps=5, warm=2), E, 2 * bs_b, cfg=cfg)
     # segment ops on a materialised message (the reference's unfused path); K limited so that [E,K] fits comfortably
     Ks = min(K, 32)
     msg = torch.randn(E, Ks, generator=g, device=dev)
