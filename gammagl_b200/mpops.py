@@ -171,12 +171,13 @@ segment_max = unsorted_segment_max        # torch.py:271-299
 def _check_spmm_args(index, weight, x):
     require_cuda(x, 'x')
     require_cuda(index, 'index')
-    require_cuda(weight, 'weight')
-    if not (x.device == index.device == weight.device):
+    if weight is not None:
+        require_cuda(weight, 'weight')
+    if not (x.device == index.device) or (weight is not None and weight.device != x.device):
         raise _lib.GglError('Tensor device inconsistent error.')                       # src/gspmm.cpp:46
     if index.dim() != 2 or index.shape[0] != 2:
         raise ValueError('index must have shape [2, num_edges]')
-    if weight.dtype != torch.float32:
+    if weight is not None and weight.dtype != torch.float32:
         raise _lib.GglError('edge weight must be float32 (got %s)' % weight.dtype)     # spmm_sum_cpu.cpp:21-24
     if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         raise _lib.GglError('x must be float32 / bfloat16 / float16 (got %s)' % x.dtype)
@@ -190,24 +191,28 @@ class _SpMM(torch.autograd.Function):
     def forward(ctx, index, weight, x, reduce):
         _check_spmm_args(index, weight, x)
         E = index.shape[1]
-        if weight.numel() != E:
+        if weight is not None and weight.numel() != E:
             raise ValueError('weight must have num_edges elements')
         x = x.contiguous()
-        weight = weight.contiguous().view(-1)
+        # weight=None is the reference's torch.ones(E) (torch.py:332-333): 1.0 * x is exact, so the unweighted kernel
+        # gives the identical result without streaming E ones
+        weight = weight.contiguous().view(-1) if weight is not None else None
         N = x.shape[0]
         g = graph_of(index, N)
         x2d = x.view(N, -1)
-        out, arg = spmm_csr(g.fwd, g.fwd.col, x2d, reduce, w=weight, wperm=g.fwd.perm,
+        out, arg = spmm_csr(g.fwd, g.fwd.col, x2d, reduce, w=weight, wperm=g.fwd.perm if weight is not None else None,
                             want_arg=(reduce == _lib.GGL_MAX), arg_empty=0)
         ctx.graph, ctx.reduce, ctx.x_shape = g, reduce, tuple(x.shape)
-        ctx.save_for_backward(weight)
+        ctx.has_w = weight is not None
+        if weight is not None:
+            ctx.save_for_backward(weight)
         ctx.arg = arg
         return out.view(x.shape)
 
     @staticmethod
     def backward(ctx, grad_out):
         lib = _lib.load()
-        (weight,) = ctx.saved_tensors
+        weight = ctx.saved_tensors[0] if ctx.has_w else None
         g = ctx.graph
         grad = grad_out.contiguous().view(g.N, -1)
         K = grad.shape[1]
@@ -217,7 +222,7 @@ class _SpMM(torch.autograd.Function):
                 if grad.dtype != torch.float32:
                     raise _lib.GglError('gspmm(max) backward is float32 only')
                 gx = torch.empty_like(grad)
-                _lib.check(lib.gglb200_spmm_max_bwd(_ptr(g.bwd.rowptr), _ptr(g.bwd.col), _ptr(weight), _ptr(g.bwd.perm),
+                _lib.check(lib.gglb200_spmm_max_bwd(_ptr(g.bwd.rowptr), _ptr(g.bwd.col), _ptr(weight), _ptr(g.bwd.perm) if ctx.has_w else None,
                                                     _ptr(grad), _ptr(ctx.arg), _ptr(gx), g.N, K, _stream(dev)),
                            'spmm_max_bwd')
             else:
@@ -228,7 +233,7 @@ class _SpMM(torch.autograd.Function):
                     _lib.check(lib.gglb200_scale_rows_by_count(_ptr(grad), _ptr(g.fwd.rowptr), _ptr(scaled), g.N, K,
                                                                _stream(dev)), 'scale_rows_by_count')
                     grad = scaled
-                gx, _ = spmm_csr(g.bwd, g.bwd.col, grad, _lib.GGL_SUM, w=weight, wperm=g.bwd.perm)
+                gx, _ = spmm_csr(g.bwd, g.bwd.col, grad, _lib.GGL_SUM, w=weight, wperm=g.bwd.perm if ctx.has_w else None)
         return None, None, gx.view(ctx.x_shape), None
 
 
@@ -352,8 +357,6 @@ def gcn_propagate(edge_index, x, norm='both'):
 
 def gspmm(index, weight=None, x=None, reduce='sum'):
     """Generalized SpMM: out[dst] (+|mean|max)= weight[e] * x[src]  (torch.py:302-351)."""
-    if weight is None:
-        weight = torch.ones(size=(index.shape[1],), dtype=torch.float32, device=index.device)
     if reduce == 'sum':
         return c_spmm_sum(index, weight, x)
     elif reduce == 'mean':
