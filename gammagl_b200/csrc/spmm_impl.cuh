@@ -14,17 +14,20 @@
 //   * work is cut into EDGE TILES (GGLB200_TILE_EDGES edges; a row belongs to the tile its first edge falls
 //     in), so every lane group streams about the same number of edges whatever the degree distribution;
 //     the group walks its edges as ONE FLAT STREAM and flushes its accumulator at row boundaries;
-//   * the gather is latency-bound, not issue-bound (first profile: ~20 KB in flight per SM, DRAM 35 %): the
-//     16-byte configurations therefore run a per-lane cp.async ring in shared memory -- every lane keeps
-//     STAGES x R of its 16-byte row pieces in flight (~200 KB per SM) without holding registers, and
-//     consumes them in stream order from shared memory (spmm_ring_kernel);
+//   * the gather is latency-bound, not issue-bound (first profile: ~20 KB in flight per SM, DRAM 35 %): every
+//     floating configuration therefore stages rows through a shared-memory ring filled by bulk async copies
+//     (cp.async.bulk / UBLKCP, one instruction per row, mbarrier per slot) -- 16 rows per warp in flight without
+//     holding registers, one warp per block so that the hardware block scheduler balances tiles
+//     (spmm_ring_kernel);
 //   * each lane accumulates sequentially in edge order (stable CSR => ascending original edge id),
 //     multiply and add rounded separately (no FMA contraction) => fp32 sums are bit-identical to the
 //     reference's serial CPU loop; max keeps the first winner (strict <);
 //   * rows longer than GGLB200_LONG_ROW are reduced chunk-wise (GGLB200_LONG_CHUNK edges -> partials, in the
 //     same launch for the ring kernel) + a finalize kernel (ordered combine): bounded tail on power-law
 //     graphs, deterministic, no float atomics.  Such a row is always the LAST row of its tile (it outruns
-//     the tile window), so the tile stream simply stops in front of it.
+//     the tile window; flagged in the tile table), so the tile stream simply stops in front of it.
+//   * peer mode (x_table != NULL): col carries owner << shift | local row and the bulk copy reads the owner
+//     GPU's HBM over NVLink -- the 1-D node partition needs no pack / all-to-all / halo buffer.
 //   * K wider than LPR*VEC is covered by blockIdx.y column tiles.
 #pragma once
 #include "common.cuh"
