@@ -233,11 +233,7 @@ extern "C" int gglb200_bspmm_bwd_w(const int32_t* rowptr, const int32_t* col, co
     using Cfg = RingCfg<L_>;                                                                                                \
     constexpr int GPW = 32 / L_;                                                                                            \
     const size_t smem = (size_t)GPW * Cfg::STAGES * Cfg::R * pitch + (size_t)GPW * Cfg::STAGES * 8;                          \
-    static bool attr = false;                                                                                               \
-    if (!attr) {                                                                                                            \
-      GGL_CUDA(cudaFuncSetAttribute(sddmm_ring_kernel<L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));        \
-      attr = true;                                                                                                          \
-    }                                                                                                                       \
+    GGL_CUDA(cudaFuncSetAttribute(sddmm_ring_kernel<L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));          \
     const int64_t blocks = (n_tiles + GPW - 1) / GPW;                                                                       \
     sddmm_ring_kernel<L_><<<dim3((unsigned)blocks, tiles), 32, smem, stream>>>(rowptr, col, perm, tile_row, n_tiles,        \
                                                                                tile_edges(), (int32_t)E, x, g, gw,          \

@@ -670,11 +670,8 @@ int launch_ring(const SpmmArgs& p, int tiles) {
   const int32_t stages = tune_ring_stages() ? tune_ring_stages() : (pitch >= 512 ? 2 : 3);
   const size_t smem = (size_t)GPW * stages * Cfg::R * pitch + (size_t)GPW * stages * 8;
   GGL_REQUIRE(smem <= 200 * 1024, GGL_EUNSUPPORTED, "spmm: ring of %zu bytes does not fit shared memory", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GGL_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  // function attributes are per device: set on every launch (a few hundred ns) so any current device works
+  GGL_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int64_t groups = p.n_tiles + (p.has_long ? p.ws_chunks : 0);
   const int64_t blocks = (groups + GPW - 1) / GPW;
   GGL_REQUIRE(blocks < INT32_MAX, GGL_EUNSUPPORTED, "spmm: grid too large");
