@@ -14,6 +14,8 @@
 //             rows = i (forward CSR): gather [x_j | s_src_j] again, accumulates grad s_dst_i.
 // Rows above GGLB200_LONG_ROW edges are chunked exactly as in spmm: partial (m, s, acc) / partial sums per chunk and
 // an ordered combine.  Requires C % 4 == 0, C/4 a power of two, H*C <= 128.  fp32.
+#include <cstdlib>
+
 #include "spmm_impl.cuh"
 
 namespace ggl {
@@ -30,6 +32,7 @@ struct GatStream {
   int64_t src_stride;
   uint32_t rowb;
   int32_t n_rows;
+  int32_t stages;        // ring depth (2 or 3)
 };
 
 // Streams the edges of one tile (or one long-row chunk) through the shared-memory ring and drives a State:
@@ -40,7 +43,8 @@ struct GatStream {
 template <int LPR, typename State>
 __device__ __forceinline__ void ring_stream(const GatStream& a, State& st, unsigned char* smem_base, int32_t pitch) {
   using Cfg = RingCfg<LPR>;
-  constexpr int GPW = 32 / LPR, R = Cfg::R, STAGES = 3, LAG = 2;
+  constexpr int GPW = 32 / LPR, R = Cfg::R;
+  const int32_t STAGES = a.stages, LAG = a.stages - 1;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LPR - 1);
   const int gbase = lane & ~(LPR - 1);
@@ -51,7 +55,6 @@ __device__ __forceinline__ void ring_stream(const GatStream& a, State& st, unsig
   const uint32_t ring = smem0 + (uint32_t)(gib * (STAGES * R)) * pitch;
   const uint32_t bars = smem0 + (uint32_t)(GPW * STAGES * R) * pitch + (uint32_t)gib * STAGES * 8;
   if (sub == 0) {
-#pragma unroll
     for (int i = 0; i < STAGES; ++i) mbar_init(bars + i * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(256) gat_fwd_finalize_kernel(const int32_t* __
 }
 
 // ---- backward, rows = source nodes (transposed CSR): grad x and grad s_src -----------------------------------------------
-// gathered row (per destination i): [gout_i (K) | {s_dst, m, s, D}_i per head (4H)]
+// gathered row (per destination i): [gout_i (K) | {s_dst, m, 1/s, D}_i per head (4H)]
 struct GatBwdSrcState {
   int32_t kcol, head; bool active, writer; int sub; unsigned gmask;
   GatDims d;
@@ -287,7 +290,7 @@ struct GatBwdSrcState {
       g4 = lds4(row_addr + (uint32_t)kcol * 4);
       const float4 t = lds4(row_addr + (uint32_t)(d.K + 4 * head) * 4);  // {s_dst, m, s, D}
       pre = ss + t.x;
-      alpha = __expf(lrelu(pre, d.slope) - t.y) / t.z;
+      alpha = __expf(lrelu(pre, d.slope) - t.y) * t.z;   // t.z = 1 / s
       D = t.w;
       dotp = fmaf(xs.w, g4.w, fmaf(xs.z, g4.z, fmaf(xs.y, g4.y, xs.x * g4.x)));
     }
@@ -355,7 +358,7 @@ struct GatBwdDstState {
       const float4 x4 = lds4(row_addr + (uint32_t)kcol * 4);
       const float ss = lds1(row_addr + (uint32_t)(d.K + head) * 4);
       pre = ss + t.x;
-      alpha = __expf(lrelu(pre, d.slope) - t.y) / t.z;
+      alpha = __expf(lrelu(pre, d.slope) - t.y) * t.z;   // t.z = 1 / s
       dotp = fmaf(x4.w, g4.w, fmaf(x4.z, g4.z, fmaf(x4.y, g4.y, x4.x * g4.x)));
     }
     for (int off = d.LH >> 1; off > 0; off >>= 1) dotp += __shfl_xor_sync(gmask, dotp, off);
@@ -424,6 +427,10 @@ static int gat_setup(const char* who, const int32_t* rowptr, const int32_t* col,
   a->n_tiles = plan_n_tiles(E);
   a->n_rows = (int32_t)n_rows;
   a->has_long = ws != nullptr && E > GGLB200_LONG_ROW;
+  {
+    const char* e = getenv("GGLB200_GAT_STAGES");
+    a->stages = (e && e[0] == '3') ? 3 : 2;   // 2 slots: more resident one-warp blocks (C4: fwd 9.7 -> 7.6 ms, bwd 29.1 -> 21.8 ms)
+  }
   a->ws_chunks = 0;
   if (a->has_long) {
     int64_t fit = (int64_t)(ws_bytes / ((size_t)d->W * 4));
@@ -437,7 +444,7 @@ static int gat_setup(const char* who, const int32_t* rowptr, const int32_t* col,
 template <typename Kern, typename... Args>
 static int gat_launch(Kern kern, int lpr, const GatStream& a, size_t rowbytes, cudaStream_t stream, Args... args) {
   const int gpw = 32 / lpr;
-  const int R = 8, STAGES = 3;
+  const int R = 8, STAGES = a.stages;
   const int32_t pitch = (int32_t)rowbytes;
   const size_t smem = (size_t)gpw * STAGES * R * pitch + (size_t)gpw * STAGES * 8;
   GGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));

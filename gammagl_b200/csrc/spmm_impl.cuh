@@ -665,9 +665,9 @@ int launch_ring(const SpmmArgs& p, int tiles) {
   const int64_t rowbytes = p.K * (int64_t)sizeof(T);
   const int64_t tileb = rowbytes < (int64_t)LPR * VB ? rowbytes : (int64_t)LPR * VB;   // widest column tile
   const int32_t pitch = (int32_t)(VB == 16 ? tileb : ((tileb + 15 + 15) & ~(int64_t)15));
-  // ring depth: 3 slots of 8 rows per group; 2 for wide rows (>= 512 B), where more resident one-warp blocks beat
-  // a deeper ring (measured on C2/K=128: 2.69 vs 2.96 ms; on C3/K=100: 3 is 1 % ahead on the DRAM-bound uniform graph)
-  const int32_t stages = tune_ring_stages() ? tune_ring_stages() : (pitch >= 512 ? 2 : 3);
+  // ring depth: 2 slots of 8 rows per group -- more resident one-warp blocks beat a deeper ring (C2/K=128: 2.69 vs
+  // 2.96 ms, C3 RMAT 6.97 vs 7.13 ms, GAT forward 7.6 vs 9.7 ms; only the DRAM-bound uniform C3 graph is 1 % better at 3)
+  const int32_t stages = tune_ring_stages() ? tune_ring_stages() : 2;
   const size_t smem = (size_t)GPW * stages * Cfg::R * pitch + (size_t)GPW * stages * 8;
   GGL_REQUIRE(smem <= 200 * 1024, GGL_EUNSUPPORTED, "spmm: ring of %zu bytes does not fit shared memory", smem);
   // function attributes are per device: set on every launch (a few hundred ns) so any current device works

@@ -487,7 +487,7 @@ class _GatAggregate(torch.autograd.Function):
             D = (out * gout).view(N, H, C).sum(-1)                           # row term of the softmax Jacobian, per node
             gcat = torch.empty((N, K + 4 * H), dtype=torch.float32, device=dev)
             gcat[:, :K] = gout
-            gcat[:, K:] = torch.stack([sd, m, s, D], dim=2).view(N, 4 * H)
+            gcat[:, K:] = torch.stack([sd, m, 1.0 / s, D], dim=2).view(N, 4 * H)
             gx = torch.empty((N, K), dtype=torch.float32, device=dev)
             gs_src = torch.empty((N, H), dtype=torch.float32, device=dev)
             gs_dst = torch.empty((N, H), dtype=torch.float32, device=dev)

@@ -231,7 +231,7 @@ GGL_API int gglb200_edge_softmax_bwd(const int32_t* rowptr, const int32_t* perm,
  *   pre_e = s_src[j,h] + s_dst[i,h];  alpha = softmax_i(leaky_relu(pre));  out[i,h,:] = sum_e alpha_e x[j,h,:]
  * fwd     forward CSR (rows = i, col = j).  xcat [N, xcat_stride] = [x (H*C) | s_src (H) | pad]; online softmax per
  *         (row, head); writes out [N,H*C] and the softmax statistics stat_m / stat_s [N,H].
- * bwd_src transposed CSR (rows = j, col = i).  gcat [N, H*C + 4H] = [gout | {s_dst, m, s, D} per head] with
+ * bwd_src transposed CSR (rows = j, col = i).  gcat [N, H*C + 4H] = [gout | {s_dst, m, 1/s, D} per head] with
  *         D[i,h] = <out[i,h,:], gout[i,h,:]>; writes grad x [N,H*C] and grad s_src [N,H].
  * bwd_dst forward CSR again; writes grad s_dst [N,H].
  * Requires C % 4 == 0, C/4 a power of two, H*C <= 128, fp32, 16-byte aligned rows.  workspace:
