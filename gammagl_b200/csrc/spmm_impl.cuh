@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) spmm_tiles_kernel(cons
 // Groups [0, ws_chunks) of the launch reduce long-row chunks into partials, the remaining groups are edge tiles.
 template <int LPR> struct RingCfg {
   static constexpr int R = LPR >= 8 ? 8 : LPR;                      // rows per slot
-  static constexpr int STAGES = 3;                                  // default ring depth; (STAGES-1)*R <= 2*LPR (index batches A,B,C)
+  static constexpr int STAGES = 2;                                  // ring depth of the SDDMM kernel; (STAGES-1)*R <= 2*LPR (index batches A,B,C)
   static constexpr int LAG = STAGES - 1;
 };
 
