@@ -36,6 +36,7 @@ SIGNATURES = {
     'gglb200_scale_rows': (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
     'gglb200_degree_power': (_int, [_vp, _vp, _i64, _c.c_float, _vp]),
     'gglb200_segment_gather_bwd': (_int, [_int, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
+    'gglb200_segment_expand_bwd': (_int, [_int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     'gglb200_segment_max_bwd': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     'gglb200_scale_rows_by_count': (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     'gglb200_spmm_max_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),

@@ -23,14 +23,26 @@ static int grid_for(int64_t n, int block = 256) {
 template <typename W, int LPR>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const W* __restrict__ g, const int64_t* __restrict__ ids,
                                                           W* __restrict__ gx, int64_t E, int32_t words) {
-  constexpr int GPW = 32 / LPR;
-  const int lane = threadIdx.x & 31, sub = lane & (LPR - 1);
-  const int64_t groups = (int64_t)gridDim.x * (blockDim.x >> 5) * GPW;
-  for (int64_t e = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPR; e < E; e += groups) {
-    const int64_t r = __ldg(ids + e);
-    const W* src = g + r * words;
-    W* dst = gx + e * words;
-    for (int32_t k = sub; k < words; k += LPR) __stcs(dst + k, __ldg(src + k));
+  constexpr int GPW = 32 / LPR;  // rows per warp step
+  constexpr int U = 4;           // independent index -> row chains in flight per group
+  const int lane = threadIdx.x & 31, sub = lane & (LPR - 1), grp = lane / LPR;
+  const int64_t span = (int64_t)gridDim.x * (blockDim.x >> 5) * (GPW * U);
+  for (int64_t e0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (GPW * U); e0 < E; e0 += span) {
+    int64_t r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = e0 + u * GPW + grp;
+      r[u] = e < E ? __ldcs(ids + e) : (int64_t)-1;
+    }
+    for (int32_t k = sub; k < words; k += LPR) {
+      W v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (r[u] >= 0) v[u] = __ldg(g + r[u] * words + k);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (r[u] >= 0) __stcs(gx + (e0 + u * GPW + grp) * words + k, v[u]);
+    }
   }
 }
 
@@ -38,7 +50,7 @@ template <typename W>
 static void launch_gather_rows(const void* g, const int64_t* ids, void* gx, int64_t E, int64_t words, cudaStream_t stream) {
   int lpr = 1;
   while (lpr < 32 && lpr < words) lpr <<= 1;
-  const int64_t warps = (E * lpr + 31) / 32;
+  const int64_t warps = (E * lpr + 127) / 128;  // 4 rows per group per iteration
   int64_t grid = (warps + 7) / 8;
   const int64_t cap = (int64_t)kSMs * 32;
   if (grid > cap) grid = cap;
@@ -91,6 +103,119 @@ template <> __global__ void gather_rows_mean_kernel<__half>(const __half* __rest
     const float cnt = (float)(rowptr[r + 1] - rowptr[r]);
     for (int32_t k = lane; k < K; k += 32) gx[e * K + k] = __float2half_rn(__half2float(g[r * K + k]) / cnt);
   }
+}
+
+// ---- row expansion through the CSR: the same backward as gather_rows, in scatter form ------------------------------------
+// Sorted position p of the segment CSR belongs to row(p) and to message perm[p]:  gx[perm[p]] = g[row(p)].  Reading g in row
+// order touches every gradient row once (N*K*s bytes instead of E*K*s gathered bytes); the writes are whole rows.  One warp
+// per fixed tile of TILE_EDGES sorted positions (balanced whatever the degree distribution); row(p) is a binary search of
+// rowptr between the tile-table rows of this tile and the next one (a handful of L1-resident steps).
+__device__ __forceinline__ int32_t row_of_position(const int32_t* __restrict__ rowptr, int32_t lo, int32_t hi, int32_t p) {
+  while (hi - lo > 1) {  // invariant: rowptr[lo] <= p, answer in [lo, hi)
+    const int32_t m = (lo + hi) >> 1;
+    if (__ldg(rowptr + m) <= p) lo = m; else hi = m;
+  }
+  return lo;
+}
+
+struct ExpandTile {
+  int32_t p0, p1, lo, hi;
+};
+__device__ __forceinline__ ExpandTile expand_tile(const int2* __restrict__ tile_tab, int64_t t, int32_t te, int64_t E) {
+  ExpandTile x;
+  const int64_t b = t * te, e = b + te < E ? b + te : E;
+  x.p0 = (int32_t)b; x.p1 = (int32_t)e;
+  x.lo = (__ldg(&tile_tab[t].x) & 0x7fffffff) - 1;   // the row that straddles the tile start begins before r0(t)
+  if (x.lo < 0) x.lo = 0;
+  x.hi = __ldg(&tile_tab[t + 1].x) & 0x7fffffff;
+  return x;
+}
+
+template <typename W, int LPR>
+__global__ void __launch_bounds__(256) expand_rows_kernel(const W* __restrict__ g, const int32_t* __restrict__ rowptr,
+                                                          const int32_t* __restrict__ perm, const int2* __restrict__ tile_tab,
+                                                          W* __restrict__ gx, int64_t E, int32_t words, int32_t te, int64_t n_tiles) {
+  constexpr int GPW = 32 / LPR;
+  constexpr int U = 4;
+  const int lane = threadIdx.x & 31, sub = lane & (LPR - 1), grp = lane / LPR;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps) {
+    const ExpandTile x = expand_tile(tile_tab, t, te, E);
+    for (int32_t pb = x.p0; pb < x.p1; pb += GPW * U) {
+      int32_t e[U], r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int32_t p = pb + u * GPW + grp;
+        e[u] = p < x.p1 ? __ldcs(perm + p) : -1;
+        r[u] = p < x.p1 ? row_of_position(rowptr, x.lo, x.hi, p) : 0;
+      }
+      for (int32_t k = sub; k < words; k += LPR) {
+        W v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (e[u] >= 0) v[u] = __ldg(g + (int64_t)r[u] * words + k);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (e[u] >= 0) __stcs(gx + (int64_t)e[u] * words + k, v[u]);
+      }
+    }
+  }
+}
+
+// mean: gx[perm[p]] = g[row(p)] / count(row(p)), element-wise in the accumulation type like gather_rows_mean_kernel
+template <typename T, int LPR>
+__global__ void __launch_bounds__(256) expand_rows_mean_kernel(const T* __restrict__ g, const int32_t* __restrict__ rowptr,
+                                                               const int32_t* __restrict__ perm, const int2* __restrict__ tile_tab,
+                                                               T* __restrict__ gx, int64_t E, int32_t K, int32_t te, int64_t n_tiles) {
+  using acc_t = typename Elem<T>::acc_t;
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane & (LPR - 1), grp = lane / LPR;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps) {
+    const ExpandTile x = expand_tile(tile_tab, t, te, E);
+    for (int32_t p = x.p0 + grp; p < x.p1; p += GPW) {
+      const int64_t e = __ldcs(perm + p);
+      const int64_t r = row_of_position(rowptr, x.lo, x.hi, p);
+      const acc_t cnt = (acc_t)(__ldg(rowptr + r + 1) - __ldg(rowptr + r));
+      for (int32_t k = sub; k < K; k += LPR) gx[e * K + k] = Elem<T>::from_acc(Elem<T>::to_acc(g[r * K + k]) / cnt);
+    }
+  }
+}
+
+static int lanes_for(int64_t n) {
+  int lpr = 1;
+  while (lpr < 32 && lpr < n) lpr <<= 1;
+  return lpr;
+}
+
+#define GGL_BY_LPR(lpr, CALL)        \
+  switch (lpr) {                     \
+    case 1: { CALL(1); break; }      \
+    case 2: { CALL(2); break; }      \
+    case 4: { CALL(4); break; }      \
+    case 8: { CALL(8); break; }      \
+    case 16: { CALL(16); break; }    \
+    default: { CALL(32); break; }    \
+  }
+
+template <typename W>
+static void launch_expand_rows(const void* g, const int32_t* rowptr, const int32_t* perm, const int2* tab, void* gx, int64_t E,
+                               int64_t words, int64_t n_tiles, cudaStream_t stream) {
+  const int grid = grid_for(n_tiles * 32);
+  const int32_t te = tile_edges();
+#define GGL_EXPAND(L) expand_rows_kernel<W, L><<<grid, 256, 0, stream>>>((const W*)g, rowptr, perm, tab, (W*)gx, E, (int32_t)words, te, n_tiles)
+  GGL_BY_LPR(lanes_for(words), GGL_EXPAND)
+#undef GGL_EXPAND
+}
+
+template <typename T>
+static void launch_expand_mean(const void* g, const int32_t* rowptr, const int32_t* perm, const int2* tab, void* gx, int64_t E,
+                               int64_t K, int64_t n_tiles, cudaStream_t stream) {
+  const int grid = grid_for(n_tiles * 32);
+  const int32_t te = tile_edges();
+#define GGL_EXPAND(L) expand_rows_mean_kernel<T, L><<<grid, 256, 0, stream>>>((const T*)g, rowptr, perm, tab, (T*)gx, E, (int32_t)K, te, n_tiles)
+  GGL_BY_LPR(lanes_for(K), GGL_EXPAND)
+#undef GGL_EXPAND
 }
 
 template <typename W>
@@ -222,6 +347,43 @@ extern "C" int gglb200_segment_gather_bwd(int reduce, const void* g, const int64
     default: return set_error(GGL_EUNSUPPORTED, "segment_gather_bwd: MEAN backward needs a floating dtype (got %d)", dtype);
   }
   GGL_LAUNCHED("gather_rows_mean");
+  return GGL_OK;
+}
+
+extern "C" int gglb200_segment_expand_bwd(int reduce, const void* g, const int32_t* rowptr, const int32_t* perm,
+                                          const int32_t* plan, void* gx, int64_t E, int64_t n_rows, int64_t K, int dtype,
+                                          void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(reduce == GGL_SUM || reduce == GGL_MEAN, GGL_EINVAL, "segment_expand_bwd: reduce must be SUM or MEAN");
+  GGL_REQUIRE(E >= 0 && K >= 0 && n_rows >= 0, GGL_EINVAL, "segment_expand_bwd: negative size");
+  GGL_REQUIRE(E < INT32_MAX && n_rows < INT32_MAX, GGL_ERANGE, "segment_expand_bwd: n_rows/E exceed int32");
+  const int eb = elem_bytes(dtype);
+  GGL_REQUIRE(eb > 0, GGL_EUNSUPPORTED, "segment_expand_bwd: unknown dtype %d", dtype);
+  if (E == 0 || K == 0) return GGL_OK;
+  GGL_REQUIRE(g && rowptr && perm && plan && gx, GGL_EINVAL, "segment_expand_bwd: NULL pointer");
+  GGL_REQUIRE(n_rows > 0, GGL_EINVAL, "segment_expand_bwd: E > 0 needs n_rows > 0");
+  GGL_REQUIRE(K < INT32_MAX / 8, GGL_ERANGE, "segment_expand_bwd: K too large");
+  const int64_t n_tiles = plan_n_tiles(E);
+  const int2* tab = (const int2*)(plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E)));
+  if (reduce == GGL_SUM) {
+    const int64_t rb = K * eb;
+    const uintptr_t al = (uintptr_t)g | (uintptr_t)gx;
+    if (rb % 16 == 0 && al % 16 == 0) launch_expand_rows<uint4>(g, rowptr, perm, tab, gx, E, rb / 16, n_tiles, stream);
+    else if (rb % 8 == 0 && al % 8 == 0) launch_expand_rows<uint2>(g, rowptr, perm, tab, gx, E, rb / 8, n_tiles, stream);
+    else if (rb % 4 == 0 && al % 4 == 0) launch_expand_rows<uint32_t>(g, rowptr, perm, tab, gx, E, rb / 4, n_tiles, stream);
+    else if (rb % 2 == 0 && al % 2 == 0) launch_expand_rows<uint16_t>(g, rowptr, perm, tab, gx, E, rb / 2, n_tiles, stream);
+    else launch_expand_rows<uint8_t>(g, rowptr, perm, tab, gx, E, rb, n_tiles, stream);
+    GGL_LAUNCHED("expand_rows");
+    return GGL_OK;
+  }
+  switch (dtype) {
+    case GGL_F32: launch_expand_mean<float>(g, rowptr, perm, tab, gx, E, K, n_tiles, stream); break;
+    case GGL_F64: launch_expand_mean<double>(g, rowptr, perm, tab, gx, E, K, n_tiles, stream); break;
+    case GGL_BF16: launch_expand_mean<__nv_bfloat16>(g, rowptr, perm, tab, gx, E, K, n_tiles, stream); break;
+    case GGL_F16: launch_expand_mean<__half>(g, rowptr, perm, tab, gx, E, K, n_tiles, stream); break;
+    default: return set_error(GGL_EUNSUPPORTED, "segment_expand_bwd: MEAN backward needs a floating dtype (got %d)", dtype);
+  }
+  GGL_LAUNCHED("expand_rows_mean");
   return GGL_OK;
 }
 

@@ -18,6 +18,7 @@ Differences, all deliberate (DESIGN.md "Boundary"):
   * gspmm / bspmm additionally accept bf16 / f16 x (fp32 accumulate); the reference is fp32-only.
 """
 import ctypes
+import os
 
 import torch
 
@@ -81,6 +82,10 @@ def _check_segment_args(x, index, N):
         raise ValueError('num_segments must be >= 0')
 
 
+# SUM / MEAN backward: scatter form through the forward CSR (default) or the plain row gather (GGLB200_SEG_BWD=gather)
+_SEG_BWD_EXPAND = os.environ.get('GGLB200_SEG_BWD', 'expand') != 'gather'
+
+
 class _SegmentReduce(torch.autograd.Function):
     """SegmentSum / SegmentMean / SegmentMax (torch_ext/src/segment_{sum,mean,max}.cpp)."""
 
@@ -120,6 +125,11 @@ class _SegmentReduce(torch.autograd.Function):
             if ctx.reduce == _lib.GGL_MAX:
                 _lib.check(lib.gglb200_segment_max_bwd(_ptr(g), _ptr(ctx.arg), _ptr(ctx.csr.rowptr), _ptr(gx), E, ctx.N, K,
                                                        _dtype_code(g), _stream(dev)), 'segment_max_bwd')
+            elif _SEG_BWD_EXPAND:
+                c = ctx.csr
+                _lib.check(lib.gglb200_segment_expand_bwd(ctx.reduce, _ptr(g), _ptr(c.rowptr), _ptr(c.perm), _ptr(c.plan),
+                                                          _ptr(gx), E, ctx.N, K, _dtype_code(g), _stream(dev)),
+                           'segment_expand_bwd')
             else:
                 _lib.check(lib.gglb200_segment_gather_bwd(ctx.reduce, _ptr(g), _ptr(ctx.index), _ptr(ctx.csr.rowptr),
                                                           _ptr(gx), E, K, _dtype_code(g), _stream(dev)),

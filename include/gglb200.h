@@ -180,6 +180,12 @@ GGL_API int gglb200_segment_gather_bwd(int reduce, const void* g, const int64_t*
                                void* gx, int64_t E, int64_t K, int dtype, void* stream);
 GGL_API int gglb200_segment_max_bwd(const void* g, const int64_t* arg, const int32_t* rowptr,
                             void* gx, int64_t E, int64_t n_rows, int64_t K, int dtype, void* stream);
+/* The same SUM / MEAN backward in scatter form through the segment CSR of the forward pass
+ * (rowptr, perm, plan from gglb200_csr_build(key = ids, other = NULL)):  gx[perm[p], k] = g[row(p), k] (/ cnt[row(p)]).
+ * Reads every gradient row once instead of once per message; identical results to the gather form. */
+GGL_API int gglb200_segment_expand_bwd(int reduce, const void* g, const int32_t* rowptr, const int32_t* perm,
+                               const int32_t* plan, void* gx, int64_t E, int64_t n_rows, int64_t K, int dtype,
+                               void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Backward of spmm_mean / spmm_max on the TRANSPOSED CSR (rows = source nodes).

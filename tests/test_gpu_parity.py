@@ -204,6 +204,32 @@ def test_segment_ops_vs_oracle(mp, E, N, K, hub):
         assert np.array_equal(m.grad.cpu().numpy(), gref), (op, 'bwd')
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float64, torch.int8])
+@pytest.mark.parametrize('E,N,K,hub', [(70000, 3000, 32, 5000), (5000, 7000, 3, 0), (33333, 100, 100, 0), (1000, 10, 1, 900),
+                                        (40000, 2000, 260, 0)])
+def test_segment_backward_scatter_and_gather_forms_agree(mp, dtype, E, N, K, hub):
+    """gglb200_segment_expand_bwd (scatter through the CSR) == gglb200_segment_gather_bwd (row gather), bit for bit."""
+    from gammagl_b200 import _lib
+    from gammagl_b200.csr import _ptr, _stream, segment_csr_of
+    lib = _lib.load()
+    ids = make_graph(N, E, seed=E + K, hub=hub)[1].to(DEV)
+    csr = segment_csr_of(ids, N)
+    g = (torch.randn(N, K, generator=torch.Generator().manual_seed(2)) * 8).to(dtype).to(DEV)
+    code = mp._dtype_code(g)
+    for reduce in (_lib.GGL_SUM, _lib.GGL_MEAN):
+        if reduce == _lib.GGL_MEAN and not dtype.is_floating_point:
+            continue
+        a = torch.full((E, K), 77, dtype=dtype, device=DEV)
+        b = torch.full((E, K), 55, dtype=dtype, device=DEV)
+        _lib.check(lib.gglb200_segment_gather_bwd(reduce, _ptr(g), _ptr(ids), _ptr(csr.rowptr), _ptr(a), E, K, code,
+                                                  _stream(g.device)), 'gather')
+        _lib.check(lib.gglb200_segment_expand_bwd(reduce, _ptr(g), _ptr(csr.rowptr), _ptr(csr.perm), _ptr(csr.plan), _ptr(b),
+                                                  E, N, K, code, _stream(g.device)), 'expand')
+        assert torch.equal(a, b), reduce
+        if reduce == _lib.GGL_SUM:
+            assert torch.equal(a, g[ids])
+
+
 def test_segment_max_arg_indices_bit_exact(mp):
     """arg-max edge ids (first edge wins on ties; sentinel N for empty segments) must equal the oracle's exactly."""
     from gammagl_b200 import _lib
