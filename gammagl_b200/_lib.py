@@ -28,6 +28,9 @@ SIGNATURES = {
     'gglb200_ind2ptr': (_int, [_vp, _i64, _i64, _vp, _vp]),
     'gglb200_ptr2ind': (_int, [_vp, _i64, _i64, _vp, _vp]),
     'gglb200_permute_rows': (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    'gglb200_sort_edges_workspace_bytes': (_sz, [_i64, _i64, _i64]),
+    'gglb200_sort_edges': (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gglb200_unique_edges': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'gglb200_spmm_workspace_bytes': (_sz, [_i64, _i64, _int]),
     'gglb200_spmm_workspace_bytes_for_chunks': (_sz, [_i64, _i64, _int]),
     'gglb200_spmm_csr': (_int, [_int, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int,

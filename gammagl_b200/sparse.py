@@ -7,12 +7,13 @@
                           (row, rowptr, col, value, colptr, csr2csc) and `t()`, plus `matmul` = the SpMM north_star asks
                           to be added on these types.
 
-Sorting is the stable GPU radix sort of gglb200_csr_build (the reference argsorts `row * ncols + col` on the host with
-numpy, storage.py:124-140); int64 views are materialised lazily from the int32 arrays the kernels use.
+SparseGraph orders its elements by `row * ncols + col` like SparseStorage (storage.py:124-140, a host numpy argsort there),
+with the GPU two-key radix sort of gglb200_sort_edges; equal (row, col) pairs keep their input order.  CSRAdj sorts by
+the first index only, as sparse_adj.py:47-67 does.  int64 views are materialised lazily from the int32 arrays the kernels use.
 """
 import torch
 
-from . import _lib, mpops
+from . import _lib, mpops, utils
 from .csr import Graph, _ptr, _stream, build_csr, require_cuda
 
 
@@ -102,14 +103,21 @@ class SparseGraph(object):
     def nnz(self):
         return int(self._row.numel())
 
+    @staticmethod
+    def _sorted_csr(major, minor, n_major, n_minor):
+        sm, sn, perm, _, _ = utils.sort_pairs(major, minor, n_major, n_minor)   # by (major, minor), stable
+        c = build_csr(sm, sn, n_major)           # input already in order: the stable row sort keeps it (its perm is the identity)
+        c.perm = perm                            # sorted position -> input element
+        return c
+
     def _rows(self):
         if self._by_row is None:
-            self._by_row = build_csr(self._row, self._col, self._sizes[0])
+            self._by_row = self._sorted_csr(self._row, self._col, self._sizes[0], self._sizes[1])
         return self._by_row
 
     def _cols(self):
         if self._by_col is None:
-            self._by_col = build_csr(self._col, self._row, self._sizes[1])
+            self._by_col = self._sorted_csr(self._col, self._row, self._sizes[1], self._sizes[0])
         return self._by_col
 
     def coo(self):

@@ -111,6 +111,26 @@ GGL_API int    gglb200_csr_build(const int64_t* key, const int64_t* other, int64
 GGL_API int gglb200_ind2ptr(const int64_t* ind, int64_t E, int64_t M, int64_t* ptr, void* stream);
 GGL_API int gglb200_ptr2ind(const int64_t* ptr, int64_t M, int64_t E, int64_t* ind, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Two-key edge sort + duplicate detection (replaces the host argsort of `major * n + minor` in
+ * gammagl/utils/sort_edge_index.py:31-45, gammagl/utils/coalesce.py:41-78 and
+ * gammagl/sparse/storage.py:124-140,200-217).
+ *   major/minor   int64 [E], ids in [0, n_major) / [0, n_minor)
+ *   sorted_major / sorted_minor  int64 [E] out (either may be NULL): the pairs in ascending (major, minor) order;
+ *                 equal pairs keep their input order (stable)
+ *   perm          int32 [E] out: sorted position -> input position
+ *   group         int64 [E] out or NULL: rank of the distinct pair held by each sorted position (0-based,
+ *                 non-decreasing) -- the segment ids coalesce() sums duplicate attributes over (coalesce.py:73-76)
+ *   n_unique      device int64 scalar out or NULL: number of distinct pairs
+ * gglb200_unique_edges keeps the first pair of every group: uniq[group[p]] = sorted[p]  (coalesce.py:69).
+ * ------------------------------------------------------------------------------------------- */
+GGL_API size_t gglb200_sort_edges_workspace_bytes(int64_t E, int64_t n_major, int64_t n_minor);
+GGL_API int gglb200_sort_edges(const int64_t* major, const int64_t* minor, int64_t E, int64_t n_major, int64_t n_minor,
+                       int64_t* sorted_major, int64_t* sorted_minor, int32_t* perm, int64_t* group,
+                       int64_t* n_unique, void* workspace, size_t workspace_bytes, void* stream);
+GGL_API int gglb200_unique_edges(const int64_t* sorted_major, const int64_t* sorted_minor, const int64_t* group, int64_t E,
+                         int64_t* uniq_major, int64_t* uniq_minor, void* stream);
+
 /* out[i] = in[perm[i]] for i < n; `width` consecutive elements of `elem_bytes` (4 or 8 ... any
  * multiple of 4) per index.  Used to bring edge weights into CSR order once per (graph, weight). */
 GGL_API int gglb200_permute_rows(const void* in, const int32_t* perm, void* out, int64_t n, int64_t row_bytes,

@@ -169,3 +169,30 @@ def ptr2ind(ptr, E):
     ind = np.zeros(E, dtype=np.int64)
     lib().ptr2ind_i64(_p(ptr), _i64(ptr.shape[0] - 1), _i64(E), _p(ind))
     return ind
+
+
+def sort_edge_index(edge_index, num_nodes, sort_by_row=True):
+    """gammagl/utils/sort_edge_index.py:33-38: order by edge_index[1-sbr] * N + edge_index[sbr].
+    Stable argsort (the reference's torch.argsort leaves the order of equal keys open).  Returns (sorted, perm)."""
+    ei = np.ascontiguousarray(edge_index, dtype=np.int64)
+    s = int(bool(sort_by_row))
+    idx = ei[1 - s] * np.int64(num_nodes) + ei[s]
+    perm = np.argsort(idx, kind='stable')
+    return ei[:, perm], perm
+
+
+def coalesce(edge_index, edge_attr, num_nodes, sort_by_row=True):
+    """gammagl/utils/coalesce.py:41-78: sort, keep first occurrences (mask = idx[1:] > idx[:-1]), merge duplicate
+    attributes with segment_sum over idx = arange - cumsum(1 - mask) (:73-76).  Returns (edge_index, attr | None)."""
+    ei, perm = sort_edge_index(edge_index, num_nodes, sort_by_row)
+    s = int(bool(sort_by_row))
+    key = np.concatenate([[-1], ei[1 - s] * np.int64(num_nodes) + ei[s]])
+    mask = key[1:] > key[:-1]
+    attr = None if edge_attr is None else np.ascontiguousarray(edge_attr)[perm]
+    if mask.all():
+        return ei, attr
+    out = ei[:, mask]
+    if attr is None:
+        return out, None
+    idx = np.arange(ei.shape[1]) - (1 - mask).cumsum()
+    return out, segment('sum', attr, idx, out.shape[1])

@@ -409,10 +409,13 @@ def test_sparse_structures_vs_oracle(mp):
     sg = S.SparseGraph.from_edge_index(cu(index), cu(w), (N, N))
     assert rel_err(sg.matmul(cu(h)).cpu().numpy(), ref) < 1e-5
     rp, ci, val = sg.csr()
-    assert np.array_equal(rp.cpu().numpy(), O.ind2ptr(srt, N)) and np.array_equal(ci.cpu().numpy(), col.numpy()[order])
-    assert np.array_equal(val.cpu().numpy(), w.numpy()[order])
+    rc_order = O.sort_edge_index(index.numpy(), N, True)[1]                 # storage.py:124-140: by row * ncols + col
+    assert np.array_equal(rp.cpu().numpy(), O.ind2ptr(srt, N)) and np.array_equal(ci.cpu().numpy(), col.numpy()[rc_order])
+    assert np.array_equal(val.cpu().numpy(), w.numpy()[rc_order])
+    r2, c2, v2 = sg.coo()
+    assert np.array_equal(r2.cpu().numpy(), row.numpy()[rc_order]) and np.array_equal(c2.cpu().numpy(), col.numpy()[rc_order])
     cp, ri, _ = sg.csc()
-    corder = np.argsort(col.numpy(), kind='stable')
+    corder = O.sort_edge_index(index.numpy(), N, False)[1]                  # storage.py:200-217: by col * nrows + row
     assert np.array_equal(ri.cpu().numpy(), row.numpy()[corder])
     # csr2csc maps CSR element order to CSC element order
     assert np.array_equal(val.cpu().numpy()[sg.csr2csc().cpu().numpy()], w.numpy()[corder])

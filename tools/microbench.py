@@ -99,7 +99,16 @@ def main(cfg):
     go = torch.randn(N, Ks, generator=g, device=dev)
     m2 = msg.clone().requires_grad_(True)
     o = mpops.unsorted_segment_sum(m2, dst, N)
-    report('unsorted_segment_sum bwd (row gather)', timeit(lambda: o.backward(go, retain_graph=True)), E, seg_b, cfg=cfg)
+    report('unsorted_segment_sum bwd through autograd (includes the [E,K] grad accumulation of torch)', timeit(lambda: o.backward(go, retain_graph=True)), E, seg_b, cfg=cfg)
+    from gammagl_b200.csr import segment_csr_of
+    sc = segment_csr_of(dst, N)
+    gxb = torch.empty(E, Ks, device=dev)
+    report('segment_sum bwd kernel: row gather (gglb200_segment_gather_bwd)', timeit(lambda: _lib.check(lib.gglb200_segment_gather_bwd(
+        _lib.GGL_SUM, _ptr(go), _ptr(dst), _ptr(sc.rowptr), _ptr(gxb), E, Ks, _lib.GGL_F32, _stream(dev)))), E, seg_b, cfg=cfg)
+    report('segment_sum bwd kernel: scatter through the CSR (gglb200_segment_expand_bwd)', timeit(lambda: _lib.check(lib.gglb200_segment_expand_bwd(
+        _lib.GGL_SUM, _ptr(go), _ptr(sc.rowptr), _ptr(sc.perm), _ptr(sc.plan), _ptr(gxb), E, N, Ks, _lib.GGL_F32, _stream(dev)))), E, seg_b, cfg=cfg)
+    report('segment_mean bwd kernel: scatter through the CSR', timeit(lambda: _lib.check(lib.gglb200_segment_expand_bwd(
+        _lib.GGL_MEAN, _ptr(go), _ptr(sc.rowptr), _ptr(sc.perm), _ptr(sc.plan), _ptr(gxb), E, N, Ks, _lib.GGL_F32, _stream(dev)))), E, seg_b, cfg=cfg)
     ones = torch.ones(E, device=dev)
     report('degree: unsorted_segment_sum(ones[E]) K=1', timeit(lambda: mpops.unsorted_segment_sum(ones, dst, N)), E, E * 12 + N * 4, cfg=cfg)
 
