@@ -1,4 +1,4 @@
-"""Host-side mirror of the callers of the path: MessagePassing and the four drop-in target layers.
+"""Host-side mirror of the callers of the path: MessagePassing, the four drop-in target layers and the multi-hop / pooling callers.
 
 `tensorlayerx` (the reference's nn substrate) is not available offline, so these are plain `torch.nn.Module`s that
 restate, line for line in meaning, the `forward` of
@@ -8,6 +8,8 @@ restate, line for line in meaning, the `forward` of
     SAGEConv         /root/reference/gammagl/layers/conv/sage_conv.py:56-108  (mean / gcn / pool)
     GATConv          /root/reference/gammagl/layers/conv/gat_conv.py:98-122   (+ utils/softmax.py:29-35)
     GINConv          /root/reference/gammagl/layers/conv/gin_conv.py:49-63
+    SGConv, APPNPConv  /root/reference/gammagl/layers/conv/sgc_conv.py:35-51, appnp_conv.py:9-37 (multi-hop: K propagates on
+                     one cached CSR), global_{sum,mean,max,min}_pool  /root/reference/gammagl/layers/pool/glob.py:7-135
 
 with the same constructor arguments, argument names and weight layout (`Linear` weight stored [in, out] as in
 tensorlayerx, tests/layers/conv/test_gcn_conv.py:14-17).  `fused=True` (default) routes propagate() through the
@@ -113,9 +115,12 @@ def add_self_loops(edge_index, num_nodes=None):
 
 
 class GCNConv(MessagePassing):
-    def __init__(self, in_channels, out_channels, norm='both', add_bias=True, fused=True, fold_norm=True):
+    def __init__(self, in_channels, out_channels, norm='both', add_bias=True, fused=True, fold_norm=True, aggregate_first=False):
         super().__init__(fused)
         self.fold_norm = fold_norm
+        # A(XW) == (AX)W; aggregating first moves in_channels instead of out_channels floats per edge.
+        # Off by default (the reference always transforms first, gcn_conv.py:79; the other order rounds differently).
+        self.aggregate_first = aggregate_first and in_channels < out_channels
         if norm not in ['left', 'right', 'none', 'both']:
             raise ValueError('Invalid norm value. Must be either "none", "both", "right" or "left".'
                              ' But got "{}".'.format(norm))
@@ -124,10 +129,15 @@ class GCNConv(MessagePassing):
         self.bias = torch.nn.Parameter(torch.zeros(1, out_channels)) if add_bias else None
 
     def forward(self, x, edge_index, edge_weight=None, num_nodes=None):
-        x = self.linear(x)                                                  # gcn_conv.py:79
+        if self.aggregate_first:
+            out = self.linear(self._aggregate(x, edge_index, edge_weight))
+        else:
+            out = self._aggregate(self.linear(x), edge_index, edge_weight)  # gcn_conv.py:79
+        return out + self.bias if self.add_bias else out                    # gcn_conv.py:104-106
+
+    def _aggregate(self, x, edge_index, edge_weight=None):
         if self.fused and self.fold_norm and edge_weight is None:
-            out = mpops.gcn_propagate(edge_index, x, self._norm)           # same math, no per-edge weight stream
-            return out + self.bias if self.add_bias else out
+            return mpops.gcn_propagate(edge_index, x, self._norm)          # same math, no per-edge weight stream
         src, dst = edge_index[0], edge_index[1]
         if edge_weight is None:
             edge_weight = torch.ones((edge_index.shape[1],), device=x.device)
@@ -142,10 +152,7 @@ class GCNConv(MessagePassing):
             deg = degree(dst, num_nodes=num_nodes, dtype=torch.float32)
             norm = deg.pow(-0.5) if self._norm == 'both' else 1.0 / deg
             weights = weights.reshape(-1) * norm[dst]
-        out = self.propagate(x, edge_index, edge_weight=weights, num_nodes=num_nodes)
-        if self.add_bias:
-            out = out + self.bias
-        return out
+        return self.propagate(x, edge_index, edge_weight=weights, num_nodes=num_nodes)
 
 
 class SAGEConv(MessagePassing):
@@ -250,3 +257,69 @@ class GINConv(MessagePassing):
         if x[1] is not None:
             out = out + (1 + self.eps) * x[1]
         return self.nn(out)
+
+
+class SGConv(MessagePassing):
+    """sgc_conv.py:35-51: x = linear(x); iter_K times propagate(sum) on the same edge_index (one cached CSR serves all hops)."""
+
+    def __init__(self, in_channels, out_channels, iter_K=2, fused=True):
+        super().__init__(fused)
+        self.in_channels, self.out_channels, self.iter_K = in_channels, out_channels, iter_K
+        self.linear = Linear(in_channels, out_channels, bias=False)
+
+    def forward(self, x, edge_index, edge_weight=None, num_nodes=None):
+        x = self.linear(x)                                                  # sgc_conv.py:46
+        for _ in range(self.iter_K):                                        # sgc_conv.py:47-48
+            x = self.propagate(x, edge_index, edge_weight=edge_weight, num_nodes=num_nodes)
+        return x
+
+
+class APPNPConv(MessagePassing):
+    """appnp_conv.py:9-37: personalised PageRank propagation x <- (1 - alpha) * A x + alpha * h0, iter_K times."""
+
+    def __init__(self, in_channels, out_channels, iter_K, alpha, drop_rate, fused=True):
+        super().__init__(fused)
+        self.in_channels, self.out_channels, self.iter_K, self.alpha, self.drop_rate = in_channels, out_channels, iter_K, alpha, drop_rate
+        self.linear_w = Linear(in_channels, out_channels, bias=False)
+        self.dropout = torch.nn.Dropout(drop_rate)
+        self.dropout_e = torch.nn.Dropout(0.9)                              # appnp_conv.py:23 (edge-weight dropout, training only)
+
+    def forward(self, x, edge_index, edge_weight=None, num_nodes=None):
+        x = self.linear_w(x)
+        h0 = x
+        x = self.dropout(x)
+        for _ in range(self.iter_K):                                        # appnp_conv.py:30-36
+            if edge_weight is not None:
+                edge_weight = self.dropout_e(edge_weight)
+            x = self.propagate(x, edge_index, edge_weight=edge_weight, num_nodes=num_nodes)
+            x = x * (1 - self.alpha) + self.alpha * h0
+        return x
+
+
+# ---- global pools (layers/pool/glob.py:7-135): one segment reduction over the batch vector ----------------------------
+def _pool_size(batch, size):
+    return int(batch.max().item()) + 1 if size is None else int(size)
+
+
+def global_sum_pool(x, batch, size=None):
+    if batch is None:
+        return x.sum(dim=0, keepdim=True)
+    return mpops.unsorted_segment_sum(x, batch, _pool_size(batch, size))
+
+
+def global_mean_pool(x, batch, size=None):
+    if batch is None:
+        return x.mean(dim=0, keepdim=True)
+    return mpops.unsorted_segment_mean(x, batch, _pool_size(batch, size))
+
+
+def global_max_pool(x, batch, size=None):
+    if batch is None:
+        return x.max(dim=0, keepdim=True)[0]
+    return mpops.unsorted_segment_max(x, batch, _pool_size(batch, size))
+
+
+def global_min_pool(x, batch, size=None):
+    if batch is None:
+        return x.min(dim=0, keepdim=True)[0]
+    return -mpops.unsorted_segment_max(-x, batch, _pool_size(batch, size))

@@ -249,3 +249,70 @@ def test_gat_aggregate_fused_vs_composed(H, C, hub):
     # and against the unfused GPU ops
     a2 = mpops.segment_softmax(torch.nn.functional.leaky_relu(ss.to(DEV)[ei[0].to(DEV)] + sd.to(DEV)[ei[1].to(DEV)], 0.2), ei[1].to(DEV), N)
     assert rel(out, mpops.bspmm(ei.to(DEV), a2, x.to(DEV))) < 2e-5
+
+
+def test_multi_hop_layers_and_aggregate_first():
+    """SGConv (sgc_conv.py:45-49), APPNPConv (appnp_conv.py:27-37) and GCNConv(aggregate_first) against dense fp64 algebra."""
+    from gammagl_b200.layers import APPNPConv, GCNConv, SGConv
+    N, E, F, H = 400, 6000, 12, 28
+    ei = graph(N, E, 5)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(N, F, generator=g)
+    w = torch.rand(ei.shape[1], generator=g)
+    A = dense_adj(ei, w, N)
+    sg = SGConv(F, H, iter_K=3).to(DEV)
+    xs = x.to(DEV).requires_grad_(True)
+    out, grads, go = run(sg, xs, ei.to(DEV), w.to(DEV))
+    W = sg.linear.weights.detach().double().cpu().requires_grad_(True)
+    xd = x.double().requires_grad_(True)
+    ref = A @ (A @ (A @ (xd @ W)))
+    ref.backward(go.double().cpu())
+    assert rel(out, ref) < 1e-5 and rel(xs.grad, xd.grad) < 1e-5 and rel(grads[0], W.grad) < 1e-5
+    # same layer through the reference's message + aggregate decomposition
+    un = copy.deepcopy(sg)
+    un.fused = False
+    assert rel(un(x.to(DEV), ei.to(DEV), w.to(DEV)), ref) < 1e-5
+
+    ap = APPNPConv(F, H, iter_K=4, alpha=0.15, drop_rate=0.5).to(DEV).eval()
+    out = ap(x.to(DEV), ei.to(DEV), w.to(DEV))
+    Wa = ap.linear_w.weights.detach().double().cpu()
+    h0 = x.double() @ Wa
+    r = h0
+    for _ in range(4):
+        r = (A @ r) * (1 - 0.15) + 0.15 * h0
+    assert rel(out, r) < 1e-5
+
+    for norm in ('both', 'none'):
+        a = GCNConv(F, H, norm=norm, aggregate_first=True).to(DEV)
+        b = copy.deepcopy(a)
+        b.aggregate_first = False
+        assert a.aggregate_first
+        xa = x.to(DEV).requires_grad_(True)
+        xb = x.to(DEV).requires_grad_(True)
+        oa, ga, _ = run(a, xa, ei.to(DEV))
+        ob, gb, _ = run(b, xb, ei.to(DEV))
+        assert rel(oa, ob) < 1e-5 and rel(xa.grad, xb.grad) < 1e-5
+        for p, q in zip(ga, gb):
+            assert rel(p, q) < 1e-5
+        # explicit edge weights take the unfolded path in both orders
+        assert rel(a(x.to(DEV), ei.to(DEV), w.to(DEV)), b(x.to(DEV), ei.to(DEV), w.to(DEV))) < 1e-5
+
+
+def test_global_pools():
+    """layers/pool/glob.py:7-135 on the segment kernels: batch vector -> per-graph sum / mean / max / min."""
+    from gammagl_b200.layers import global_max_pool, global_mean_pool, global_min_pool, global_sum_pool
+    g = torch.Generator().manual_seed(8)
+    B, N, F = 37, 5000, 19
+    batch = torch.sort(torch.randint(0, B, (N,), generator=g))[0]
+    x = torch.randn(N, F, generator=g)
+    xd, bd = x.to(DEV), batch.to(DEV)
+    ref = {k: torch.zeros(B, F, dtype=torch.float64) for k in ('sum',)}
+    ref['sum'].index_add_(0, batch, x.double())
+    cnt = torch.bincount(batch, minlength=B).double().clamp_min(1)[:, None]
+    assert rel(global_sum_pool(xd, bd), ref['sum']) < 1e-5
+    assert rel(global_mean_pool(xd, bd, B), ref['sum'] / cnt) < 1e-5
+    mx = torch.stack([x[batch == i].max(0)[0] for i in range(B)])
+    mn = torch.stack([x[batch == i].min(0)[0] for i in range(B)])
+    assert torch.equal(global_max_pool(xd, bd).cpu(), mx) and torch.equal(global_min_pool(xd, bd).cpu(), mn)
+    assert global_sum_pool(xd, None).shape == (1, F) and global_mean_pool(xd, None).shape == (1, F)
+    assert torch.equal(global_max_pool(xd, None).cpu(), x.max(0, keepdim=True)[0])
