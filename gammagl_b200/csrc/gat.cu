@@ -3,6 +3,8 @@
 //   bspmm_bwd_w     grad of c_bspmm_sum wrt the per-head edge weight (SDDMM),
 //                   /root/reference/gammagl/mpops/torch_ext/cpu/bspmm_sum_cpu.cpp:95-107
 //   edge_softmax    segment_softmax over incoming edges, /root/reference/gammagl/utils/softmax.py:29-35
+#include <cstdlib>
+
 #include "spmm_impl.cuh"
 
 namespace ggl {
@@ -192,6 +194,38 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   }
 }
 
+// alpha = exp(logit - m[ids]) / (s[ids] + 1e-16), four heads per thread (the second half of the fused forward)
+__global__ void __launch_bounds__(256) softmax_norm4_kernel(const float4* __restrict__ logit, const float* __restrict__ m,
+                                                            const float* __restrict__ s, const int64_t* __restrict__ ids,
+                                                            float4* __restrict__ alpha, int64_t total4, int32_t H4) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; t < total4; t += stride) {
+    const int64_t e = t / H4;
+    const int64_t off = (__ldg(ids + e) * H4 + (t - e * H4)) * 4;
+    const float4 mm = __ldg(reinterpret_cast<const float4*>(m + off));
+    const float4 ss = __ldg(reinterpret_cast<const float4*>(s + off));
+    const float4 v = __ldcs(logit + t);
+    float4 o;
+    o.x = __fdiv_rn(expf(v.x - mm.x), __fadd_rn(ss.x, 1e-16f));
+    o.y = __fdiv_rn(expf(v.y - mm.y), __fadd_rn(ss.y, 1e-16f));
+    o.z = __fdiv_rn(expf(v.z - mm.z), __fadd_rn(ss.z, 1e-16f));
+    o.w = __fdiv_rn(expf(v.w - mm.w), __fadd_rn(ss.w, 1e-16f));
+    __stcs(alpha + t, o);
+  }
+}
+
+int softmax_stats(const int32_t* rowptr, const int32_t* perm, const int32_t* plan, const float* logit, float* stat_m, float* stat_s,
+                  int64_t n_rows, int64_t E, int32_t H, void* part_ws, size_t part_bytes, cudaStream_t stream);  // gat_fused.cu
+
+static bool softmax_fused_enabled() {  // env GGLB200_SOFTMAX=composed keeps the four-kernel composition
+  static const bool v = [] {
+    const char* e = getenv("GGLB200_SOFTMAX");
+    return !(e && e[0] == 'c');
+  }();
+  return v;
+}
+
 static int ew_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
   const int64_t cap = (int64_t)kSMs * 16;
@@ -285,6 +319,14 @@ extern "C" int gglb200_edge_softmax_fwd(const int32_t* rowptr, const int32_t* pe
   float *m, *s; void* rest; size_t rest_bytes;
   int st = softmax_args("edge_softmax_fwd", rowptr, perm, plan, ids, n_rows, E, H, workspace, workspace_bytes, &m, &s, &rest, &rest_bytes);
   if (st) return st;
+  if (softmax_fused_enabled() && H % 4 == 0 && H <= 128 && (((uintptr_t)logit | (uintptr_t)alpha) % 16 == 0)) {
+    // two passes: online (max, denominator) per segment over the bulk-copy ring, then one element-wise normalisation
+    st = softmax_stats(rowptr, perm, plan, logit, m, s, n_rows, E, H, rest, rest_bytes, stream);
+    if (st) return st;
+    softmax_norm4_kernel<<<ew_grid(E * H / 4), 256, 0, stream>>>((const float4*)logit, m, s, ids, (float4*)alpha, E * (H / 4), H / 4);
+    GGL_LAUNCHED("softmax_norm4");
+    return GGL_OK;
+  }
   st = segment_reduce_f32(GGL_MAX, rowptr, perm, plan, logit, m, n_rows, E, H, rest, rest_bytes, stream);
   if (st) return st;
   softmax_exp_kernel<<<ew_grid(E * H), 256, 0, stream>>>(logit, m, ids, alpha, E * H, H);

@@ -454,6 +454,108 @@ static int gat_launch(Kern kern, int lpr, const GatStream& a, size_t rowbytes, c
   return GGL_OK;
 }
 
+// ---- stand-alone edge softmax: per-(segment, head) max and denominator in ONE streaming pass ------------------------------
+// utils/softmax.py:29-33 runs unsorted_segment_max, exp and unsorted_segment_sum as three passes over [E,H]; here the
+// logit rows (H floats) of each segment stream through the same bulk-copy ring (col = perm of the segment CSR) and an
+// online softmax per lane keeps (m, s) for 4 heads.  Chunk partials are (m, s) pairs combined by the finalize kernel.
+struct SoftmaxStatsState {
+  int32_t kcol, H; bool active;
+  float* stat_m; float* stat_s; float* part;  // partials: [chunk][2H] = m | s
+  float4 m, s;
+  __device__ __forceinline__ void reset() { m = make_float4(kNegBig, kNegBig, kNegBig, kNegBig); s = make_float4(0, 0, 0, 0); }
+  __device__ __forceinline__ void row_begin(int32_t) { reset(); }
+  __device__ __forceinline__ static void upd(float& m_, float& s_, float v) {
+    const float mn = fmaxf(m_, v);
+    s_ = fmaf(s_, __expf(m_ - mn), __expf(v - mn));
+    m_ = mn;
+  }
+  __device__ __forceinline__ void edge(uint32_t row_addr) {
+    if (!active) return;
+    const float4 v = lds4(row_addr + (uint32_t)kcol * 4);
+    upd(m.x, s.x, v.x); upd(m.y, s.y, v.y); upd(m.z, s.z, v.z); upd(m.w, s.w, v.w);
+  }
+  __device__ __forceinline__ void row_end(int32_t row, int32_t deg) {
+    if (!active) return;
+    const bool any = deg > 0;
+    *reinterpret_cast<float4*>(stat_m + (int64_t)row * H + kcol) = any ? m : make_float4(0, 0, 0, 0);
+    *reinterpret_cast<float4*>(stat_s + (int64_t)row * H + kcol) = any ? s : make_float4(1.f, 1.f, 1.f, 1.f);
+    reset();
+  }
+  __device__ __forceinline__ void chunk_end(int64_t chunk, int32_t) {
+    if (!active) return;
+    float* pc = part + chunk * (2 * (int64_t)H);
+    *reinterpret_cast<float4*>(pc + kcol) = m;
+    *reinterpret_cast<float4*>(pc + H + kcol) = s;
+  }
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(32) softmax_stats_kernel(const GatStream a, int32_t H, float* __restrict__ stat_m,
+                                                           float* __restrict__ stat_s, float* __restrict__ part, int32_t pitch) {
+  extern __shared__ __align__(16) unsigned char ring_smem[];
+  const int lane = threadIdx.x & 31, sub = lane & (LPR - 1);
+  SoftmaxStatsState st;
+  st.kcol = sub * 4; st.H = H; st.active = st.kcol < H;
+  st.stat_m = stat_m; st.stat_s = stat_s; st.part = part;
+  st.reset();
+  ring_stream<LPR>(a, st, ring_smem, pitch);
+}
+
+__global__ void __launch_bounds__(128) softmax_stats_finalize_kernel(const int32_t* __restrict__ plan, const float* __restrict__ part,
+                                                                     float* __restrict__ stat_m, float* __restrict__ stat_s,
+                                                                     int32_t H, int32_t ws_chunks) {
+  const int32_t max_chunks = plan[2];
+  const int32_t n_long = min(plan[1], plan[3]);
+  const int32_t* long_tab = plan + plan_long_off(max_chunks);
+  for (int32_t l = blockIdx.x; l < n_long; l += gridDim.x) {
+    const int32_t row = long_tab[3 * l], c0 = long_tab[3 * l + 1], nch = long_tab[3 * l + 2];
+    if (c0 + nch > ws_chunks) continue;
+    for (int32_t h = threadIdx.x; h < H; h += blockDim.x) {
+      float M = kNegBig;
+      for (int32_t j = 0; j < nch; ++j) M = fmaxf(M, part[(int64_t)(c0 + j) * 2 * H + h]);
+      float S = 0.f;
+      for (int32_t j = 0; j < nch; ++j) {
+        const float* pc = part + (int64_t)(c0 + j) * 2 * H;
+        S = fmaf(pc[H + h], __expf(pc[h] - M), S);
+      }
+      stat_m[(int64_t)row * H + h] = M;
+      stat_s[(int64_t)row * H + h] = S;
+    }
+  }
+}
+
+// stat_m / stat_s [n_rows, H] of logit[E, H] over the segment CSR (rowptr, perm, plan).  H % 4 == 0, H <= 128, logit 16-byte aligned.
+int softmax_stats(const int32_t* rowptr, const int32_t* perm, const int32_t* plan, const float* logit, float* stat_m, float* stat_s,
+                  int64_t n_rows, int64_t E, int32_t H, void* part_ws, size_t part_bytes, cudaStream_t stream) {
+  GatStream a;
+  a.rowptr = rowptr; a.col = perm; a.plan = plan;
+  a.tile_tab = plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E));
+  a.n_tiles = plan_n_tiles(E);
+  a.n_rows = (int32_t)n_rows;
+  a.stages = 2;
+  a.src = logit; a.src_stride = H; a.rowb = (uint32_t)H * 4;
+  a.ws_chunks = 0;
+  a.has_long = part_ws != nullptr && E > GGLB200_LONG_ROW;
+  if (a.has_long) {
+    int64_t fit = (int64_t)(part_bytes / ((size_t)H * 8));
+    if (fit > plan_max_chunks(E)) fit = plan_max_chunks(E);
+    if (fit < 1) a.has_long = false; else a.ws_chunks = (int32_t)fit;
+  }
+  float* part = (float*)part_ws;
+  const size_t rowbytes = (size_t)H * 4;
+  int st;
+  if (H <= 32) st = gat_launch(softmax_stats_kernel<8>, 8, a, rowbytes, stream, H, stat_m, stat_s, part);
+  else if (H <= 64) st = gat_launch(softmax_stats_kernel<16>, 16, a, rowbytes, stream, H, stat_m, stat_s, part);
+  else st = gat_launch(softmax_stats_kernel<32>, 32, a, rowbytes, stream, H, stat_m, stat_s, part);
+  if (st) return st;
+  GGL_LAUNCHED("softmax_stats");
+  if (a.has_long) {
+    softmax_stats_finalize_kernel<<<kSMs * 2, 128, 0, stream>>>(plan, part, stat_m, stat_s, H, a.ws_chunks);
+    GGL_LAUNCHED("softmax_stats_finalize");
+  }
+  return GGL_OK;
+}
+
 }  // namespace ggl
 
 using namespace ggl;
