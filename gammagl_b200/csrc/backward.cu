@@ -182,6 +182,79 @@ __global__ void __launch_bounds__(256) expand_rows_mean_kernel(const T* __restri
   }
 }
 
+// fp32 rows that are whole float4 words: the mean forms of the two kernels above at full vector width
+template <int LPR>
+__global__ void __launch_bounds__(256) gather_rows_mean4_kernel(const float4* __restrict__ g, const int64_t* __restrict__ ids,
+                                                                const int32_t* __restrict__ rowptr, float4* __restrict__ gx,
+                                                                int64_t E, int32_t words) {
+  constexpr int GPW = 32 / LPR;
+  constexpr int U = 4;
+  const int lane = threadIdx.x & 31, sub = lane & (LPR - 1), grp = lane / LPR;
+  const int64_t span = (int64_t)gridDim.x * (blockDim.x >> 5) * (GPW * U);
+  for (int64_t e0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (GPW * U); e0 < E; e0 += span) {
+    int64_t r[U];
+    float c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = e0 + u * GPW + grp;
+      r[u] = e < E ? __ldcs(ids + e) : (int64_t)-1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = r[u] >= 0 ? (float)(__ldg(rowptr + r[u] + 1) - __ldg(rowptr + r[u])) : 1.f;
+    for (int32_t k = sub; k < words; k += LPR) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (r[u] >= 0) v[u] = __ldg(g + r[u] * words + k);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (r[u] >= 0) {
+          float4 o;
+          o.x = __fdiv_rn(v[u].x, c[u]); o.y = __fdiv_rn(v[u].y, c[u]); o.z = __fdiv_rn(v[u].z, c[u]); o.w = __fdiv_rn(v[u].w, c[u]);
+          __stcs(gx + (e0 + u * GPW + grp) * words + k, o);
+        }
+    }
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) expand_rows_mean4_kernel(const float4* __restrict__ g, const int32_t* __restrict__ rowptr,
+                                                                const int32_t* __restrict__ perm, const int2* __restrict__ tile_tab,
+                                                                float4* __restrict__ gx, int64_t E, int32_t words, int32_t te,
+                                                                int64_t n_tiles) {
+  constexpr int GPW = 32 / LPR;
+  constexpr int U = 4;
+  const int lane = threadIdx.x & 31, sub = lane & (LPR - 1), grp = lane / LPR;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += warps) {
+    const ExpandTile x = expand_tile(tile_tab, t, te, E);
+    for (int32_t pb = x.p0; pb < x.p1; pb += GPW * U) {
+      int32_t e[U], r[U];
+      float c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int32_t p = pb + u * GPW + grp;
+        e[u] = p < x.p1 ? __ldcs(perm + p) : -1;
+        r[u] = p < x.p1 ? row_of_position(rowptr, x.lo, x.hi, p) : 0;
+        c[u] = (float)(__ldg(rowptr + r[u] + 1) - __ldg(rowptr + r[u]));
+      }
+      for (int32_t k = sub; k < words; k += LPR) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (e[u] >= 0) v[u] = __ldg(g + (int64_t)r[u] * words + k);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (e[u] >= 0) {
+            float4 o;
+            o.x = __fdiv_rn(v[u].x, c[u]); o.y = __fdiv_rn(v[u].y, c[u]); o.z = __fdiv_rn(v[u].z, c[u]); o.w = __fdiv_rn(v[u].w, c[u]);
+            __stcs(gx + (int64_t)e[u] * words + k, o);
+          }
+      }
+    }
+  }
+}
+
 static int lanes_for(int64_t n) {
   int lpr = 1;
   while (lpr < 32 && lpr < n) lpr <<= 1;
@@ -339,6 +412,17 @@ extern "C" int gglb200_segment_gather_bwd(int reduce, const void* g, const int64
     return GGL_OK;
   }
   GGL_REQUIRE(rowptr, GGL_EINVAL, "segment_gather_bwd: MEAN needs rowptr");
+  if (dtype == GGL_F32 && K % 4 == 0 && (((uintptr_t)g | (uintptr_t)gx) % 16 == 0)) {
+    const int64_t words = K / 4;
+    const int lpr = lanes_for(words);
+    const int64_t warps = (E * lpr + 127) / 128;
+    const int g4 = grid_for(warps * 32);
+#define GGL_GM4(L) gather_rows_mean4_kernel<L><<<g4, 256, 0, stream>>>((const float4*)g, ids, rowptr, (float4*)gx, E, (int32_t)words)
+    GGL_BY_LPR(lpr, GGL_GM4)
+#undef GGL_GM4
+    GGL_LAUNCHED("gather_rows_mean4");
+    return GGL_OK;
+  }
   switch (dtype) {
     case GGL_F32: gather_rows_mean_kernel<float><<<grid, 256, 0, stream>>>((const float*)g, ids, rowptr, (float*)gx, E, (int32_t)K); break;
     case GGL_F64: gather_rows_mean_kernel<double><<<grid, 256, 0, stream>>>((const double*)g, ids, rowptr, (double*)gx, E, (int32_t)K); break;
@@ -374,6 +458,16 @@ extern "C" int gglb200_segment_expand_bwd(int reduce, const void* g, const int32
     else if (rb % 2 == 0 && al % 2 == 0) launch_expand_rows<uint16_t>(g, rowptr, perm, tab, gx, E, rb / 2, n_tiles, stream);
     else launch_expand_rows<uint8_t>(g, rowptr, perm, tab, gx, E, rb, n_tiles, stream);
     GGL_LAUNCHED("expand_rows");
+    return GGL_OK;
+  }
+  if (dtype == GGL_F32 && K % 4 == 0 && (((uintptr_t)g | (uintptr_t)gx) % 16 == 0)) {
+    const int64_t words = K / 4;
+    const int g4 = grid_for(n_tiles * 32);
+    const int32_t te = tile_edges();
+#define GGL_EM4(L) expand_rows_mean4_kernel<L><<<g4, 256, 0, stream>>>((const float4*)g, rowptr, perm, tab, (float4*)gx, E, (int32_t)words, te, n_tiles)
+    GGL_BY_LPR(lanes_for(words), GGL_EM4)
+#undef GGL_EM4
+    GGL_LAUNCHED("expand_rows_mean4");
     return GGL_OK;
   }
   switch (dtype) {

@@ -107,6 +107,8 @@ def main(cfg):
         _lib.GGL_SUM, _ptr(go), _ptr(dst), _ptr(sc.rowptr), _ptr(gxb), E, Ks, _lib.GGL_F32, _stream(dev)))), E, seg_b, cfg=cfg)
     report('segment_sum bwd kernel: scatter through the CSR (gglb200_segment_expand_bwd)', timeit(lambda: _lib.check(lib.gglb200_segment_expand_bwd(
         _lib.GGL_SUM, _ptr(go), _ptr(sc.rowptr), _ptr(sc.perm), _ptr(sc.plan), _ptr(gxb), E, N, Ks, _lib.GGL_F32, _stream(dev)))), E, seg_b, cfg=cfg)
+    report('segment_mean bwd kernel: row gather', timeit(lambda: _lib.check(lib.gglb200_segment_gather_bwd(
+        _lib.GGL_MEAN, _ptr(go), _ptr(dst), _ptr(sc.rowptr), _ptr(gxb), E, Ks, _lib.GGL_F32, _stream(dev)))), E, seg_b, cfg=cfg)
     report('segment_mean bwd kernel: scatter through the CSR', timeit(lambda: _lib.check(lib.gglb200_segment_expand_bwd(
         _lib.GGL_MEAN, _ptr(go), _ptr(sc.rowptr), _ptr(sc.perm), _ptr(sc.plan), _ptr(gxb), E, N, Ks, _lib.GGL_F32, _stream(dev)))), E, seg_b, cfg=cfg)
     ones = torch.ones(E, device=dev)
