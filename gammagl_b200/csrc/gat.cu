@@ -218,6 +218,23 @@ __global__ void __launch_bounds__(256) softmax_norm4_kernel(const float4* __rest
 int softmax_stats(const int32_t* rowptr, const int32_t* perm, const int32_t* plan, const float* logit, float* stat_m, float* stat_s,
                   int64_t n_rows, int64_t E, int32_t H, void* part_ws, size_t part_bytes, cudaStream_t stream);  // gat_fused.cu
 
+int softmax_dot(const int32_t* rowptr, const int32_t* perm, const int32_t* plan, const float* alpha, const float* galpha, float* dot,
+                int64_t n_rows, int64_t E, int32_t H, void* part_ws, size_t part_bytes, cudaStream_t stream);  // gat_fused.cu
+
+// glogit = alpha * (galpha - dot[ids]), four heads per thread
+__global__ void __launch_bounds__(256) softmax_bwd4_kernel(const float4* __restrict__ alpha, const float4* __restrict__ galpha,
+                                                           const float* __restrict__ dot, const int64_t* __restrict__ ids,
+                                                           float4* __restrict__ gl, int64_t total4, int32_t H4) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; t < total4; t += stride) {
+    const int64_t e = t / H4;
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dot + (__ldg(ids + e) * H4 + (t - e * H4)) * 4));
+    const float4 a = __ldcs(alpha + t), g = __ldcs(galpha + t);
+    __stcs(gl + t, make_float4(a.x * (g.x - d.x), a.y * (g.y - d.y), a.z * (g.z - d.z), a.w * (g.w - d.w)));
+  }
+}
+
 static bool softmax_fused_enabled() {  // env GGLB200_SOFTMAX=composed keeps the four-kernel composition
   static const bool v = [] {
     const char* e = getenv("GGLB200_SOFTMAX");
@@ -347,6 +364,15 @@ extern "C" int gglb200_edge_softmax_bwd(const int32_t* rowptr, const int32_t* pe
   float *dot, *unused; void* rest; size_t rest_bytes;
   int st = softmax_args("edge_softmax_bwd", rowptr, perm, plan, ids, n_rows, E, H, workspace, workspace_bytes, &dot, &unused, &rest, &rest_bytes);
   if (st) return st;
+  if (softmax_fused_enabled() && H % 4 == 0 && H <= 128 && (((uintptr_t)alpha | (uintptr_t)galpha | (uintptr_t)glogit) % 16 == 0)) {
+    // two passes: per-segment dot over the ring (both rows gathered per edge), then one element-wise pass
+    st = softmax_dot(rowptr, perm, plan, alpha, galpha, dot, n_rows, E, H, rest, rest_bytes, stream);
+    if (st) return st;
+    softmax_bwd4_kernel<<<ew_grid(E * H / 4), 256, 0, stream>>>((const float4*)alpha, (const float4*)galpha, dot, ids, (float4*)glogit,
+                                                                 E * (H / 4), H / 4);
+    GGL_LAUNCHED("softmax_bwd4");
+    return GGL_OK;
+  }
   softmax_prod_kernel<<<ew_grid(E * H), 256, 0, stream>>>(alpha, galpha, glogit, E * H);
   GGL_LAUNCHED("softmax_prod");
   st = segment_reduce_f32(GGL_SUM, rowptr, perm, plan, glogit, dot, n_rows, E, H, rest, rest_bytes, stream);

@@ -33,6 +33,9 @@ struct GatStream {
   uint32_t rowb;
   int32_t n_rows;
   int32_t stages;        // ring depth (2 or 3)
+  const float* src2;     // optional second gathered matrix (same row index), copied behind the first inside a ring row
+  int64_t src2_stride;
+  uint32_t rowb2;        // 0 when unused
 };
 
 // Streams the edges of one tile (or one long-row chunk) through the shared-memory ring and drives a State:
@@ -107,8 +110,11 @@ __device__ __forceinline__ void ring_stream(const GatStream& a, State& st, unsig
       const int32_t nv = min(R, n - pos0);
       const int32_t c = __shfl_sync(gmask, colsrc, gbase + ((pos0 + sub) & (LPR - 1)));
       __syncwarp(gmask);
-      if (sub == 0) mbar_arrive_expect_tx(bar, (uint32_t)nv * a.rowb);
-      if (sub < nv) bulk_copy_g2s(dst + (uint32_t)sub * pitch, a.src + (int64_t)c * a.src_stride, a.rowb, bar);
+      if (sub == 0) mbar_arrive_expect_tx(bar, (uint32_t)nv * (a.rowb + a.rowb2));
+      if (sub < nv) {
+        bulk_copy_g2s(dst + (uint32_t)sub * pitch, a.src + (int64_t)c * a.src_stride, a.rowb, bar);
+        if (a.rowb2) bulk_copy_g2s(dst + (uint32_t)sub * pitch + a.rowb, a.src2 + (int64_t)c * a.src2_stride, a.rowb2, bar);
+      }
     }
   };
   for (int s = 0; s < LAG; ++s) issue(s);
@@ -423,6 +429,7 @@ static int gat_setup(const char* who, const int32_t* rowptr, const int32_t* col,
   if (l < lh) l = lh;
   *lpr = l;
   a->rowptr = rowptr; a->col = col; a->plan = plan;
+  a->src2 = nullptr; a->src2_stride = 0; a->rowb2 = 0;
   a->tile_tab = plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E));
   a->n_tiles = plan_n_tiles(E);
   a->n_rows = (int32_t)n_rows;
@@ -444,7 +451,7 @@ static int gat_setup(const char* who, const int32_t* rowptr, const int32_t* col,
 template <typename Kern, typename... Args>
 static int gat_launch(Kern kern, int lpr, const GatStream& a, size_t rowbytes, cudaStream_t stream, Args... args) {
   const int gpw = 32 / lpr;
-  const int R = 8, STAGES = a.stages;
+  const int R = lpr >= 8 ? 8 : lpr, STAGES = a.stages;  // RingCfg<LPR>::R
   const int32_t pitch = (int32_t)rowbytes;
   const size_t smem = (size_t)gpw * STAGES * R * pitch + (size_t)gpw * STAGES * 8;
   GGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -534,6 +541,7 @@ int softmax_stats(const int32_t* rowptr, const int32_t* perm, const int32_t* pla
   a.n_rows = (int32_t)n_rows;
   a.stages = 2;
   a.src = logit; a.src_stride = H; a.rowb = (uint32_t)H * 4;
+  a.src2 = nullptr; a.src2_stride = 0; a.rowb2 = 0;
   a.ws_chunks = 0;
   a.has_long = part_ws != nullptr && E > GGLB200_LONG_ROW;
   if (a.has_long) {
@@ -544,7 +552,10 @@ int softmax_stats(const int32_t* rowptr, const int32_t* perm, const int32_t* pla
   float* part = (float*)part_ws;
   const size_t rowbytes = (size_t)H * 4;
   int st;
-  if (H <= 32) st = gat_launch(softmax_stats_kernel<8>, 8, a, rowbytes, stream, H, stat_m, stat_s, part);
+  // lanes per segment row = float4 words per logit row (at least 2): H = 8 runs 16 segments per warp side by side
+  if (H <= 8) st = gat_launch(softmax_stats_kernel<2>, 2, a, rowbytes, stream, H, stat_m, stat_s, part);
+  else if (H <= 16) st = gat_launch(softmax_stats_kernel<4>, 4, a, rowbytes, stream, H, stat_m, stat_s, part);
+  else if (H <= 32) st = gat_launch(softmax_stats_kernel<8>, 8, a, rowbytes, stream, H, stat_m, stat_s, part);
   else if (H <= 64) st = gat_launch(softmax_stats_kernel<16>, 16, a, rowbytes, stream, H, stat_m, stat_s, part);
   else st = gat_launch(softmax_stats_kernel<32>, 32, a, rowbytes, stream, H, stat_m, stat_s, part);
   if (st) return st;
@@ -552,6 +563,76 @@ int softmax_stats(const int32_t* rowptr, const int32_t* perm, const int32_t* pla
   if (a.has_long) {
     softmax_stats_finalize_kernel<<<kSMs * 2, 128, 0, stream>>>(plan, part, stat_m, stat_s, H, a.ws_chunks);
     GGL_LAUNCHED("softmax_stats_finalize");
+  }
+  return GGL_OK;
+}
+
+// ---- edge softmax backward: dot[r, h] = sum over the segment of alpha * galpha, both rows gathered per edge -------------------
+struct SoftmaxDotState {
+  int32_t kcol, H; bool active;
+  float* dot; float* part;  // partials: [chunk][H]
+  float4 acc;
+  __device__ __forceinline__ void row_begin(int32_t) { acc = make_float4(0, 0, 0, 0); }
+  __device__ __forceinline__ void edge(uint32_t row_addr) {
+    if (!active) return;
+    const float4 a = lds4(row_addr + (uint32_t)kcol * 4);
+    const float4 g = lds4(row_addr + (uint32_t)(H + kcol) * 4);
+    acc.x = fmaf(a.x, g.x, acc.x); acc.y = fmaf(a.y, g.y, acc.y); acc.z = fmaf(a.z, g.z, acc.z); acc.w = fmaf(a.w, g.w, acc.w);
+  }
+  __device__ __forceinline__ void row_end(int32_t row, int32_t) {
+    if (!active) return;
+    *reinterpret_cast<float4*>(dot + (int64_t)row * H + kcol) = acc;
+    acc = make_float4(0, 0, 0, 0);
+  }
+  __device__ __forceinline__ void chunk_end(int64_t chunk, int32_t) {
+    if (!active) return;
+    *reinterpret_cast<float4*>(part + chunk * (int64_t)H + kcol) = acc;
+  }
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(32) softmax_dot_kernel(const GatStream a, int32_t H, float* __restrict__ dot,
+                                                         float* __restrict__ part, int32_t pitch) {
+  extern __shared__ __align__(16) unsigned char ring_smem[];
+  const int lane = threadIdx.x & 31, sub = lane & (LPR - 1);
+  SoftmaxDotState st;
+  st.kcol = sub * 4; st.H = H; st.active = st.kcol < H;
+  st.dot = dot; st.part = part;
+  st.acc = make_float4(0, 0, 0, 0);
+  ring_stream<LPR>(a, st, ring_smem, pitch);
+}
+
+// dot[n_rows, H] = segment sums of alpha * galpha ([E, H] each) over the segment CSR.  H % 4 == 0, H <= 128, 16-byte aligned.
+int softmax_dot(const int32_t* rowptr, const int32_t* perm, const int32_t* plan, const float* alpha, const float* galpha, float* dot,
+                int64_t n_rows, int64_t E, int32_t H, void* part_ws, size_t part_bytes, cudaStream_t stream) {
+  GatStream a;
+  a.rowptr = rowptr; a.col = perm; a.plan = plan;
+  a.tile_tab = plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E));
+  a.n_tiles = plan_n_tiles(E);
+  a.n_rows = (int32_t)n_rows;
+  a.stages = 2;
+  a.src = alpha; a.src_stride = H; a.rowb = (uint32_t)H * 4;
+  a.src2 = galpha; a.src2_stride = H; a.rowb2 = (uint32_t)H * 4;
+  a.ws_chunks = 0;
+  a.has_long = part_ws != nullptr && E > GGLB200_LONG_ROW;
+  if (a.has_long) {
+    int64_t fit = (int64_t)(part_bytes / ((size_t)H * 4));
+    if (fit > plan_max_chunks(E)) fit = plan_max_chunks(E);
+    if (fit < 1) a.has_long = false; else a.ws_chunks = (int32_t)fit;
+  }
+  float* part = (float*)part_ws;
+  const size_t rowbytes = (size_t)H * 8;
+  int st;
+  if (H <= 8) st = gat_launch(softmax_dot_kernel<2>, 2, a, rowbytes, stream, H, dot, part);
+  else if (H <= 16) st = gat_launch(softmax_dot_kernel<4>, 4, a, rowbytes, stream, H, dot, part);
+  else if (H <= 32) st = gat_launch(softmax_dot_kernel<8>, 8, a, rowbytes, stream, H, dot, part);
+  else if (H <= 64) st = gat_launch(softmax_dot_kernel<16>, 16, a, rowbytes, stream, H, dot, part);
+  else st = gat_launch(softmax_dot_kernel<32>, 32, a, rowbytes, stream, H, dot, part);
+  if (st) return st;
+  GGL_LAUNCHED("softmax_dot");
+  if (a.has_long) {
+    gat_sum_finalize_kernel<<<kSMs * 2, 256, 0, stream>>>(plan, part, H, H, dot, H, H, nullptr, 0, a.ws_chunks);
+    GGL_LAUNCHED("gat_sum_finalize");
   }
   return GGL_OK;
 }

@@ -23,6 +23,7 @@ import math
 import torch
 
 from . import mpops
+from .csr import segment_csr_of
 
 
 class Linear(torch.nn.Module):
@@ -91,10 +92,12 @@ class MessagePassing(torch.nn.Module):
 
 
 def degree(index, num_nodes=None, dtype=torch.float32):
-    """utils/degree.py:10-40: unsorted_segment_sum of ones."""
+    """utils/degree.py:10-40: unsorted_segment_sum of ones == the row lengths of the segment CSR over `index` (exact
+    integers; the CSR is the one the aggregation over the same index uses, built once and cached)."""
     N = int(index.max().item()) + 1 if num_nodes is None else num_nodes
-    one = torch.ones((index.shape[0],), dtype=dtype, device=index.device)
-    return mpops.unsorted_segment_sum(one, index, N)
+    if not index.is_cuda:
+        raise RuntimeError('degree: index is on %s: gammagl_b200 is a CUDA-only backend (no CPU fallback)' % index.device)
+    return segment_csr_of(index, N).degrees().to(dtype)
 
 
 def calc_gcn_norm(edge_index, num_nodes, edge_weight=None):
