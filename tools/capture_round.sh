@@ -23,7 +23,7 @@ for g in rmat uniform; do
 done
 # per-kernel durations of the GAT / softmax / segment-backward / ingest kernels (duration only: one pass per kernel)
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"softmax|gather_rows|expand_rows|sddmm|gat_|pack_pairs|narrow_keys|rowptr_kernel|finalize" \
-    -c 400 --csv --log-file $O/launches_${R}_c4_ops.csv python tools/microbench.py c4 > $O/ncu_gat.log 2>&1
+    -c 300 --csv --log-file $O/launches_${R}_c4_ops.csv python tools/microbench.py c4 > $O/ncu_gat.log 2>&1
 ncu --set full --clock-control none -k regex:softmax_stats -c 1 -o $O/prof_gat \
     python tools/microbench.py c4 >> $O/ncu_gat.log 2>&1
 ncu -i $O/prof_gat.ncu-rep --page raw --csv > $O/ncu_${R}_gat_kernels_raw.csv 2>/dev/null

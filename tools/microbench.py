@@ -50,6 +50,9 @@ def main(cfg):
     s = 4
     spmm_b = E * (K * s + 8) + N * (K * s + 4)
     report('csr_build(dst)', timeit(lambda: build_csr(ei[1], ei[0], N), reps=5, warm=2), E, E * 16 * 4, cfg=cfg)
+    from gammagl_b200 import utils as gutils
+    report('sort_edge_index (two-key radix sort, int64 in/out)', timeit(lambda: gutils.sort_edge_index(ei, num_nodes=N), reps=5, warm=2), E, E * (16 + 16 + 5 * 24), cfg=cfg)
+    report('coalesce (sort + duplicate groups + unique)', timeit(lambda: gutils.coalesce(ei, num_nodes=N), reps=5, warm=2), E, E * (16 + 16 + 5 * 24 + 24), cfg=cfg)
     fwd = gr.fwd
     bwd = gr.bwd
     for red, code in (('sum', _lib.GGL_SUM), ('mean', _lib.GGL_MEAN), ('max', _lib.GGL_MAX)):
