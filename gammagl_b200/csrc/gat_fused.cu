@@ -167,6 +167,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : slope * v; }
 
 constexpr float kNegBig = -1e30f;
+constexpr int kFB = 8;  // chunk partials fetched together by the finalize kernels (loads in flight on a hub row's chunk list)
 
 struct GatDims {
   int32_t H, C, K, LH;   // LH = C/4 lanes per head
@@ -251,14 +252,32 @@ __global__ void __launch_bounds__(256) gat_fwd_finalize_kernel(const int32_t* __
     if (c0 + nch > ws_chunks) continue;
     for (int32_t k = threadIdx.x; k < d.K; k += blockDim.x) {
       const int32_t h = k / d.C;
+      // partials of kFB chunks are fetched together (independent loads), then combined in ascending chunk order
       float M = kNegBig;
-      for (int32_t j = 0; j < nch; ++j) M = fmaxf(M, part[(int64_t)(c0 + j) * W + d.K + h]);
+      for (int32_t j0 = 0; j0 < nch; j0 += kFB) {
+        float mv[kFB];
+#pragma unroll
+        for (int u = 0; u < kFB; ++u) mv[u] = j0 + u < nch ? part[(int64_t)(c0 + j0 + u) * W + d.K + h] : kNegBig;
+#pragma unroll
+        for (int u = 0; u < kFB; ++u) M = fmaxf(M, mv[u]);
+      }
       float S = 0.f, A = 0.f;
-      for (int32_t j = 0; j < nch; ++j) {
-        const float* pc = part + (int64_t)(c0 + j) * W;
-        const float f = __expf(pc[d.K + h] - M);
-        S = fmaf(pc[d.K + d.H + h], f, S);
-        A = fmaf(pc[k], f, A);
+      for (int32_t j0 = 0; j0 < nch; j0 += kFB) {
+        float mv[kFB], sv[kFB], av[kFB];
+#pragma unroll
+        for (int u = 0; u < kFB; ++u) {
+          const bool ok = j0 + u < nch;
+          const float* pc = part + (int64_t)(c0 + (ok ? j0 + u : 0)) * W;
+          mv[u] = ok ? pc[d.K + h] : kNegBig; sv[u] = ok ? pc[d.K + d.H + h] : 0.f; av[u] = ok ? pc[k] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kFB; ++u) {
+          if (j0 + u < nch) {
+            const float f = __expf(mv[u] - M);
+            S = fmaf(sv[u], f, S);
+            A = fmaf(av[u], f, A);
+          }
+        }
       }
       out[(int64_t)row * d.K + k] = A / S;
       if (k % d.C == 0) { stat_m[(int64_t)row * d.H + h] = M; stat_s[(int64_t)row * d.H + h] = S; }
@@ -407,7 +426,14 @@ __global__ void __launch_bounds__(256) gat_sum_finalize_kernel(const int32_t* __
     if (c0 + nch > ws_chunks) continue;
     for (int32_t k = threadIdx.x; k < W; k += blockDim.x) {
       float S = 0.f;
-      for (int32_t j = 0; j < nch; ++j) S += part[(int64_t)(c0 + j) * Wp + k];
+      for (int32_t j0 = 0; j0 < nch; j0 += kFB) {
+        float v[kFB];
+#pragma unroll
+        for (int u = 0; u < kFB; ++u) v[u] = j0 + u < nch ? part[(int64_t)(c0 + j0 + u) * Wp + k] : 0.f;
+#pragma unroll
+        for (int u = 0; u < kFB; ++u)
+          if (j0 + u < nch) S += v[u];
+      }
       if (k < wa) out_a[(int64_t)row * sa + k] = S;
       else out_b[(int64_t)row * sb + (k - wa)] = S;
     }
@@ -519,11 +545,25 @@ __global__ void __launch_bounds__(128) softmax_stats_finalize_kernel(const int32
     if (c0 + nch > ws_chunks) continue;
     for (int32_t h = threadIdx.x; h < H; h += blockDim.x) {
       float M = kNegBig;
-      for (int32_t j = 0; j < nch; ++j) M = fmaxf(M, part[(int64_t)(c0 + j) * 2 * H + h]);
+      for (int32_t j0 = 0; j0 < nch; j0 += kFB) {
+        float mv[kFB];
+#pragma unroll
+        for (int u = 0; u < kFB; ++u) mv[u] = j0 + u < nch ? part[(int64_t)(c0 + j0 + u) * 2 * H + h] : kNegBig;
+#pragma unroll
+        for (int u = 0; u < kFB; ++u) M = fmaxf(M, mv[u]);
+      }
       float S = 0.f;
-      for (int32_t j = 0; j < nch; ++j) {
-        const float* pc = part + (int64_t)(c0 + j) * 2 * H;
-        S = fmaf(pc[H + h], __expf(pc[h] - M), S);
+      for (int32_t j0 = 0; j0 < nch; j0 += kFB) {
+        float mv[kFB], sv[kFB];
+#pragma unroll
+        for (int u = 0; u < kFB; ++u) {
+          const bool ok = j0 + u < nch;
+          const float* pc = part + (int64_t)(c0 + (ok ? j0 + u : 0)) * 2 * H;
+          mv[u] = ok ? pc[h] : kNegBig; sv[u] = ok ? pc[H + h] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kFB; ++u)
+          if (j0 + u < nch) S = fmaf(sv[u], __expf(mv[u] - M), S);
       }
       stat_m[(int64_t)row * H + h] = M;
       stat_s[(int64_t)row * H + h] = S;

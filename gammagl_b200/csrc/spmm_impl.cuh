@@ -636,15 +636,30 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) spmm_finalize_kernel(cons
     acc_t acc[VEC];
     int32_t argv[VEC];
     reset_acc<T, VEC, ISMAX>(acc, argv);
-    for (int32_t j = 0; j < nch; ++j) {
-      const acc_t* pv = reinterpret_cast<const acc_t*>(p.part_val) + (int64_t)(c0 + j) * p.K + kcol;
+    // A hub row has hundreds of chunks: fetch the partials of FB chunks at once (independent loads in flight), then
+    // combine them in ascending chunk order -- the same order and rounding as a plain sequential loop.
+    constexpr int FB = 8;
+    for (int32_t j0 = 0; j0 < nch; j0 += FB) {
+      acc_t v[FB][VEC];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        acc_t v = pv[i];
-        if constexpr (ISMAX) {
-          if (acc[i] < v) { acc[i] = v; argv[i] = p.part_arg[(int64_t)(c0 + j) * p.K + kcol + i]; }
-        } else {
-          acc[i] = add_rn(acc[i], v);
+      for (int u = 0; u < FB; ++u) {
+        if (j0 + u < nch) {
+          const acc_t* pv = reinterpret_cast<const acc_t*>(p.part_val) + (int64_t)(c0 + j0 + u) * p.K + kcol;
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) v[u][i] = pv[i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < FB; ++u) {
+        if (j0 + u < nch) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            if constexpr (ISMAX) {
+              if (acc[i] < v[u][i]) { acc[i] = v[u][i]; argv[i] = p.part_arg[(int64_t)(c0 + j0 + u) * p.K + kcol + i]; }
+            } else {
+              acc[i] = add_rn(acc[i], v[u][i]);
+            }
+          }
         }
       }
     }

@@ -128,15 +128,22 @@ class _SegmentReduce(torch.autograd.Function):
             if ctx.reduce == _lib.GGL_MAX:
                 _lib.check(lib.gglb200_segment_max_bwd(_ptr(g), _ptr(ctx.arg), _ptr(ctx.csr.rowptr), _ptr(gx), E, ctx.N, K,
                                                        _dtype_code(g), _stream(dev)), 'segment_max_bwd')
-            elif _SEG_BWD == 'expand' or (_SEG_BWD == 'auto' and g.numel() * g.element_size() > _SEG_BWD_L2_BYTES):
-                c = ctx.csr
-                _lib.check(lib.gglb200_segment_expand_bwd(ctx.reduce, _ptr(g), _ptr(c.rowptr), _ptr(c.perm), _ptr(c.plan),
-                                                          _ptr(gx), E, ctx.N, K, _dtype_code(g), _stream(dev)),
-                           'segment_expand_bwd')
             else:
-                _lib.check(lib.gglb200_segment_gather_bwd(ctx.reduce, _ptr(g), _ptr(ctx.index), _ptr(ctx.csr.rowptr),
-                                                          _ptr(gx), E, K, _dtype_code(g), _stream(dev)),
-                           'segment_gather_bwd')
+                reduce, c = ctx.reduce, ctx.csr
+                if reduce == _lib.GGL_MEAN and g.dtype == torch.float32:
+                    # g[r] / count[r] once per segment row instead of once per message: same operands, same quotient
+                    gs = torch.empty_like(g)
+                    _lib.check(lib.gglb200_scale_rows_by_count(_ptr(g), _ptr(c.rowptr), _ptr(gs), ctx.N, K, _stream(dev)),
+                               'scale_rows_by_count')
+                    g, reduce = gs, _lib.GGL_SUM
+                if _SEG_BWD == 'expand' or (_SEG_BWD == 'auto' and g.numel() * g.element_size() > _SEG_BWD_L2_BYTES):
+                    _lib.check(lib.gglb200_segment_expand_bwd(reduce, _ptr(g), _ptr(c.rowptr), _ptr(c.perm), _ptr(c.plan),
+                                                              _ptr(gx), E, ctx.N, K, _dtype_code(g), _stream(dev)),
+                               'segment_expand_bwd')
+                else:
+                    _lib.check(lib.gglb200_segment_gather_bwd(reduce, _ptr(g), _ptr(ctx.index), _ptr(c.rowptr),
+                                                              _ptr(gx), E, K, _dtype_code(g), _stream(dev)),
+                               'segment_gather_bwd')
         return gx, None, None, None
 
 
