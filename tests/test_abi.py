@@ -68,3 +68,35 @@ def test_cpu_tensors_are_rejected_loudly():
         mpops.unsorted_segment_sum(x, ids, 2)
     with pytest.raises(_lib.GglError):
         mpops.gspmm(torch.tensor([[0, 1], [1, 0]]), None, torch.ones(2, 4))
+
+
+def test_new_entry_points_validate_without_gpu():
+    """gglb200_sort_edges / unique_edges / segment_expand_bwd: size queries and argument errors return before any launch."""
+    lib = _lib.load()
+    assert lib.gglb200_sort_edges_workspace_bytes(1000, 50, 50) >= 2 * 8000 + 2 * 4000
+    assert lib.gglb200_sort_edges_workspace_bytes(0, 0, 0) > 0
+    st = lib.gglb200_sort_edges(None, None, -1, 4, 4, None, None, None, None, None, None, 0, None)
+    assert st == -1 and b'negative' in lib.gglb200_last_error()
+    st = lib.gglb200_sort_edges(None, None, 5, 4, 4, None, None, None, None, None, None, 0, None)
+    assert st == -1 and b'must not be NULL' in lib.gglb200_last_error()
+    st = lib.gglb200_sort_edges(None, None, 1 << 31, 4, 4, None, None, None, None, None, None, 0, None)
+    assert st == -4
+    assert lib.gglb200_unique_edges(None, None, None, 0, None, None, None) == 0          # nothing to do
+    assert lib.gglb200_unique_edges(None, None, None, 3, None, None, None) == -1
+    assert lib.gglb200_segment_expand_bwd(2, None, None, None, None, None, 4, 4, 4, 0, None) == -1   # MAX is not a gather
+    assert lib.gglb200_segment_expand_bwd(0, None, None, None, None, None, 0, 4, 4, 0, None) == 0    # E == 0
+    assert lib.gglb200_segment_expand_bwd(0, None, None, None, None, None, 4, 4, 4, 0, None) == -1   # NULL pointers
+    assert lib.gglb200_segment_expand_bwd(0, None, None, None, None, None, 4, 4, 4, 99, None) == -2  # unknown dtype (GGL_EUNSUPPORTED)
+
+
+def test_utils_reject_cpu_tensors():
+    import pytest
+    import torch
+    from gammagl_b200 import layers, utils
+    ei = torch.tensor([[0, 1], [1, 0]])
+    with pytest.raises(_lib.GglError):
+        utils.sort_edge_index(ei)
+    with pytest.raises(_lib.GglError):
+        utils.coalesce(ei)
+    with pytest.raises(RuntimeError):
+        layers.degree(ei[0], 2)
