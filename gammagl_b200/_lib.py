@@ -35,6 +35,7 @@ SIGNATURES = {
     'gglb200_spmm_workspace_bytes_for_chunks': (_sz, [_i64, _i64, _int]),
     'gglb200_spmm_csr': (_int, [_int, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int,
                                 _vp, _sz, _vp]),
+    'gglb200_spmm_csr_epilogue': (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _int, _i64, _i64, _i64, _i64, _int, _vp, _sz, _vp]),
     'gglb200_spmm_csr_peer': (_int, [_int, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _i64, _int, _vp, _sz, _vp]),
     'gglb200_scale_rows': (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
     'gglb200_degree_power': (_int, [_vp, _vp, _i64, _c.c_float, _vp]),

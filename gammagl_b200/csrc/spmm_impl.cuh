@@ -53,6 +53,8 @@ struct SpmmArgs {
   int64_t* arg;             // MAX only, may be NULL
   int64_t arg_empty;
   const float* out_scale;   // NULL, or [n_rows] fp32: out[r,:] = out_scale[r] * reduce(...) (folded GCN normalisation)
+  const float* bias;        // NULL, or [K] fp32 added after out_scale (GCNConv's bias, gcn_conv.py:104-106); SUM, floating out
+  int32_t relu;             // != 0: out = max(out, 0) after the bias (the activation the models apply next)
   int64_t n_rows, E, K;
   int64_t n_src;            // rows of x (bounds the superset copies of unaligned rows)
   void* part_val;           // workspace: [ws_chunks, K] acc_t
@@ -81,6 +83,12 @@ __device__ __forceinline__ void accumulate(typename Elem<T>::acc_t (&acc)[VEC], 
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     acc_t xv = Elem<T>::to_acc(v.v[i]);
+    if constexpr (WMODE != 0 && Elem<T>::is_float && sizeof(T) == 2 && !ISMAX) {
+      // 16-bit storage has no bit-exact reference (the reference is fp32-only here; north_star tolerance 1e-2): one fused
+      // multiply-add per element instead of two separately rounded operations -- these rows are issue-bound, not byte-bound
+      acc[i] = fmaf((acc_t)wv, xv, acc[i]);
+      continue;
+    }
     if constexpr (WMODE != 0 && Elem<T>::is_float) xv = mul_rn((acc_t)wv, xv);
     if constexpr (ISMAX) {
       if (acc[i] < xv) { acc[i] = xv; argv[i] = c; }
@@ -168,6 +176,14 @@ __device__ __forceinline__ void finish_row(typename Elem<T>::acc_t (&acc)[VEC], 
       const float sc = __ldg(p.out_scale + row);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[i] = mul_rn(acc[i], sc);
+    }
+    if (p.bias) {  // separately rounded add, like `out + bias` after the aggregation in the reference
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = add_rn(acc[i], (acc_t)__ldg(p.bias + kcol + i));
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = acc[i] < (acc_t)0 ? (acc_t)0 : acc[i];   // NaN stays NaN like torch.relu
     }
   }
   if (p.reduce == GGL_MEAN) {

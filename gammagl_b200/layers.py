@@ -19,11 +19,15 @@ decomposition on the B200 segment operators (materialised [E,K] messages).  Both
 The dense X.W products stay torch.matmul (cuBLAS): tensor cores live there, outside the aggregation metric.
 """
 import math
+import os
 
 import torch
 
 from . import mpops
 from .csr import segment_csr_of
+
+
+_EPILOGUE = os.environ.get('GGLB200_EPILOGUE', '1') != '0'   # 0: bias / activation as separate torch ops (same results)
 
 
 class Linear(torch.nn.Module):
@@ -118,9 +122,15 @@ def add_self_loops(edge_index, num_nodes=None):
 
 
 class GCNConv(MessagePassing):
-    def __init__(self, in_channels, out_channels, norm='both', add_bias=True, fused=True, fold_norm=True, aggregate_first=False):
+    def __init__(self, in_channels, out_channels, norm='both', add_bias=True, fused=True, fold_norm=True, aggregate_first=False,
+                 fused_activation=None):
         super().__init__(fused)
         self.fold_norm = fold_norm
+        if fused_activation not in (None, 'relu'):
+            raise ValueError("fused_activation must be None or 'relu'")
+        # the ReLU the models apply right after the layer (models/gcn.py), fused with the bias into the
+        # aggregation kernel's row write on the folded path; applied as a separate op on the other paths.  Default: none.
+        self.fused_activation = fused_activation
         # A(XW) == (AX)W; aggregating first moves in_channels instead of out_channels floats per edge.
         # Off by default (the reference always transforms first, gcn_conv.py:79; the other order rounds differently).
         self.aggregate_first = aggregate_first and in_channels < out_channels
@@ -132,11 +142,16 @@ class GCNConv(MessagePassing):
         self.bias = torch.nn.Parameter(torch.zeros(1, out_channels)) if add_bias else None
 
     def forward(self, x, edge_index, edge_weight=None, num_nodes=None):
+        relu = self.fused_activation == 'relu'
+        if _EPILOGUE and self.fused and self.fold_norm and edge_weight is None and not self.aggregate_first:
+            # bias and activation ride in the aggregation kernel's epilogue (bit-identical to the separate passes)
+            return mpops.gcn_propagate(edge_index, self.linear(x), self._norm, bias=self.bias if self.add_bias else None, relu=relu)
         if self.aggregate_first:
             out = self.linear(self._aggregate(x, edge_index, edge_weight))
         else:
             out = self._aggregate(self.linear(x), edge_index, edge_weight)  # gcn_conv.py:79
-        return out + self.bias if self.add_bias else out                    # gcn_conv.py:104-106
+        out = out + self.bias if self.add_bias else out                     # gcn_conv.py:104-106
+        return torch.relu(out) if relu else out
 
     def _aggregate(self, x, edge_index, edge_weight=None):
         if self.fused and self.fold_norm and edge_weight is None:

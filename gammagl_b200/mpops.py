@@ -43,7 +43,8 @@ def _dtype_code(t):
         raise _lib.GglError('unsupported dtype %s' % t.dtype)
 
 
-def spmm_csr(csr, col, x2d, reduce, w=None, wperm=None, heads=1, want_arg=False, arg_empty=0, n_rows=None, out_scale=None):
+def spmm_csr(csr, col, x2d, reduce, w=None, wperm=None, heads=1, want_arg=False, arg_empty=0, n_rows=None, out_scale=None,
+             bias=None, relu=False):
     """Launch the aggregation kernel family on a Csr.  x2d: [n_src, K] contiguous.  Returns (out, arg)."""
     lib = _lib.load()
     n_rows = csr.n_rows if n_rows is None else n_rows
@@ -57,10 +58,16 @@ def spmm_csr(csr, col, x2d, reduce, w=None, wperm=None, heads=1, want_arg=False,
         if PROFILE is not None:
             ev0 = torch.cuda.Event(enable_timing=True)
             ev0.record()
-        _lib.check(lib.gglb200_spmm_csr(reduce, _ptr(csr.rowptr), _ptr(col), _ptr(csr.plan),
-                                        _ptr(w), _ptr(wperm), heads, _ptr(x2d), _ptr(out), _ptr(arg), arg_empty, _ptr(out_scale),
-                                        n_rows, x2d.shape[0], csr.E, K, _dtype_code(x2d), _ptr(ws), ws_bytes, _stream(dev)),
-                   'spmm_csr')
+        if bias is not None or relu:       # layer epilogue fused into the row write (GGL_SUM only)
+            _lib.check(lib.gglb200_spmm_csr_epilogue(_ptr(csr.rowptr), _ptr(col), _ptr(csr.plan), _ptr(w), _ptr(wperm), heads,
+                                                     _ptr(x2d), _ptr(out), _ptr(out_scale), _ptr(bias), int(bool(relu)), n_rows,
+                                                     x2d.shape[0], csr.E, K, _dtype_code(x2d), _ptr(ws), ws_bytes, _stream(dev)),
+                       'spmm_csr_epilogue')
+        else:
+            _lib.check(lib.gglb200_spmm_csr(reduce, _ptr(csr.rowptr), _ptr(col), _ptr(csr.plan),
+                                            _ptr(w), _ptr(wperm), heads, _ptr(x2d), _ptr(out), _ptr(arg), arg_empty, _ptr(out_scale),
+                                            n_rows, x2d.shape[0], csr.E, K, _dtype_code(x2d), _ptr(ws), ws_bytes, _stream(dev)),
+                       'spmm_csr')
         if PROFILE is not None:
             ev1 = torch.cuda.Event(enable_timing=True)
             ev1.record()
@@ -324,12 +331,18 @@ class _GcnPropagate(torch.autograd.Function):
     of one per edge), so this path is checked at 1e-5 relative, not bit-exactly."""
 
     @staticmethod
-    def forward(ctx, x, edge_index, norm):
+    def forward(ctx, x, edge_index, norm, bias=None, relu=False):
         lib = _lib.load()
         require_cuda(x, 'x')
         require_cuda(edge_index, 'edge_index')
         if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
             raise _lib.GglError('gcn_propagate needs a floating x')
+        bias_flat = None
+        if bias is not None:
+            require_cuda(bias, 'bias')
+            bias_flat = bias.detach().reshape(-1).to(torch.float32).contiguous()
+            if bias_flat.numel() != x[0].numel():
+                raise ValueError('bias must have %d elements, got %d' % (x[0].numel(), bias_flat.numel()))
         x = x.contiguous()
         N = x.shape[0]
         g = graph_of(edge_index, N)
@@ -348,8 +361,12 @@ class _GcnPropagate(torch.autograd.Function):
             if ns is not None:
                 xs = torch.empty_like(x2d)
                 _lib.check(lib.gglb200_scale_rows(_ptr(x2d), _ptr(ns), _ptr(xs), N, K, _dtype_code(x2d), _stream(dev)), 'scale_rows')
-            out, _ = spmm_csr(g.fwd, g.fwd.col, xs, _lib.GGL_SUM, out_scale=nd)
+            out, _ = spmm_csr(g.fwd, g.fwd.col, xs, _lib.GGL_SUM, out_scale=nd, bias=bias_flat, relu=relu)
         ctx.graph, ctx.ns, ctx.nd, ctx.shape = g, ns, nd, tuple(x.shape)
+        ctx.relu, ctx.bias_shape = bool(relu), None if bias is None else tuple(bias.shape)
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        if relu:
+            ctx.save_for_backward(out)
         return out.view(x.shape)
 
     @staticmethod
@@ -357,6 +374,12 @@ class _GcnPropagate(torch.autograd.Function):
         lib = _lib.load()
         g = ctx.graph
         grad = grad_out.contiguous().view(g.N, -1)
+        if ctx.relu:
+            (out,) = ctx.saved_tensors
+            grad = grad * (out > 0).to(grad.dtype)
+        gbias = None
+        if ctx.bias_shape is not None:
+            gbias = grad.sum(dim=0, dtype=torch.float32).to(ctx.bias_dtype).reshape(ctx.bias_shape)
         K = grad.shape[1]
         dev = grad.device
         with torch.cuda.device(dev):
@@ -365,14 +388,15 @@ class _GcnPropagate(torch.autograd.Function):
                 gs = torch.empty_like(grad)
                 _lib.check(lib.gglb200_scale_rows(_ptr(grad), _ptr(ctx.nd), _ptr(gs), g.N, K, _dtype_code(grad), _stream(dev)), 'scale_rows')
             gx, _ = spmm_csr(g.bwd, g.bwd.col, gs, _lib.GGL_SUM, out_scale=ctx.ns)
-        return gx.view(ctx.shape), None, None
+        return gx.view(ctx.shape), None, None, gbias, None
 
 
-def gcn_propagate(edge_index, x, norm='both'):
-    """GCNConv's normalised propagate with unit edge weights (gcn_conv.py:78-104 after the Linear), weight-stream free."""
+def gcn_propagate(edge_index, x, norm='both', bias=None, relu=False):
+    """GCNConv's normalised propagate with unit edge weights (gcn_conv.py:78-104 after the Linear), weight-stream free.
+    `bias` ([K] or [1, K]) and `relu` fuse `out + bias` (gcn_conv.py:104-106) and the model's ReLU into the row write."""
     if norm not in ('both', 'left', 'right', 'none'):
         raise ValueError('Invalid norm value. Must be either "none", "both", "right" or "left".')
-    return _GcnPropagate.apply(x, edge_index, norm)
+    return _GcnPropagate.apply(x, edge_index, norm, bias, relu)
 
 
 def gspmm(index, weight=None, x=None, reduce='sum'):

@@ -183,6 +183,14 @@ GGL_API int    gglb200_spmm_csr(int reduce,
  * Remote rows are fetched by the same bulk async copies straight from the owner's HBM over NVLink, so the
  * transfer overlaps the reduction tile by tile -- no pack / all-to-all / halo buffer.  Requires K*sizeof(dtype) % 16
  * == 0, GGL_SUM or GGL_MEAN.  The caller orders the kernel after every rank has finished writing its shard. */
+/* gglb200_spmm_csr(GGL_SUM, ...) with the layer epilogue fused into the row write:
+ *   out[r, k] = act( out_scale[r] * sum(...) + bias[k] ),  act = max(., 0) when relu != 0.
+ * out_scale [n_rows] and bias [K] are fp32 and may be NULL; each step is rounded separately, so the result is
+ * bit-identical to running `out + bias` (gcn_conv.py:104-106) and the model's ReLU as separate passes. */
+GGL_API int gglb200_spmm_csr_epilogue(const int32_t* rowptr, const int32_t* col, const int32_t* plan, const float* w,
+                              const int32_t* wperm, int32_t heads, const void* x, void* out, const float* out_scale,
+                              const float* bias, int relu, int64_t n_rows, int64_t n_src, int64_t E, int64_t K,
+                              int dtype, void* workspace, size_t workspace_bytes, void* stream);
 GGL_API int gglb200_spmm_csr_peer(int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
                           const float* w, const int32_t* wperm, int32_t heads, const void* const* x_table,
                           int32_t owner_shift, void* out, const float* out_scale, int64_t n_rows, int64_t E,

@@ -316,3 +316,63 @@ def test_global_pools():
     assert torch.equal(global_max_pool(xd, bd).cpu(), mx) and torch.equal(global_min_pool(xd, bd).cpu(), mn)
     assert global_sum_pool(xd, None).shape == (1, F) and global_mean_pool(xd, None).shape == (1, F)
     assert torch.equal(global_max_pool(xd, None).cpu(), x.max(0, keepdim=True)[0])
+
+
+@pytest.mark.parametrize('norm', ['both', 'none'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_bias_relu_epilogue_is_bit_identical_to_separate_passes(norm, dtype):
+    """gglb200_spmm_csr_epilogue: act(out_scale * sum + bias) in the row write == the separate `+ bias` and ReLU passes."""
+    from gammagl_b200 import mpops
+    N, E, K = 3000, 70000, 100
+    ei = graph(N, E, 11)
+    ei[1, :2500] = 5                                                          # one split row: the finalize kernel applies the epilogue too
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(N, K, generator=g).to(dtype)
+    bias = torch.randn(1, K, generator=g)
+    go = torch.randn(N, K, generator=g).to(dtype)
+    xa = x.to(DEV).requires_grad_(True)
+    ba = bias.to(DEV).requires_grad_(True)
+    fused = mpops.gcn_propagate(ei.to(DEV), xa, norm, bias=ba, relu=True)
+    fused.backward(go.to(DEV))
+    xb = x.to(DEV).requires_grad_(True)
+    bb = bias.to(DEV).requires_grad_(True)
+    plain = mpops.gcn_propagate(ei.to(DEV), xb, norm)
+    sep = torch.relu((plain.float() + bb).to(dtype)) if dtype != torch.float32 else torch.relu(plain + bb)
+    sep.backward(go.to(DEV))
+    if dtype == torch.float32:
+        assert torch.equal(fused, sep)
+        assert torch.equal(xa.grad, xb.grad)
+    else:   # 16-bit: the fused path rounds to bf16 once (after bias and ReLU), the separate passes twice
+        assert rel(fused, sep) < 1e-2 and rel(xa.grad, xb.grad) < 2e-2
+    assert rel(ba.grad, bb.grad) < (1e-5 if dtype == torch.float32 else 2e-2)
+    # bias only / relu only
+    assert torch.equal(mpops.gcn_propagate(ei.to(DEV), x.to(DEV), norm, relu=True), torch.relu(mpops.gcn_propagate(ei.to(DEV), x.to(DEV), norm)))
+    if dtype == torch.float32:
+        assert torch.equal(mpops.gcn_propagate(ei.to(DEV), x.to(DEV), norm, bias=bias.to(DEV)), mpops.gcn_propagate(ei.to(DEV), x.to(DEV), norm) + bias.to(DEV))
+
+
+def test_gcn_conv_fused_activation():
+    from gammagl_b200.layers import GCNConv
+    N, E, F, H = 500, 8000, 24, 40
+    ei = graph(N, E, 13)
+    x = torch.randn(N, F, generator=torch.Generator().manual_seed(14))
+    a = GCNConv(F, H, fused_activation='relu').to(DEV)
+    torch.nn.init.normal_(a.bias)
+    b = copy.deepcopy(a)
+    b.fused_activation = None
+    c = copy.deepcopy(a)
+    c.fused = False                                                           # reference decomposition + separate bias / relu
+    xa, xb, xc = (x.to(DEV).requires_grad_(True) for _ in range(3))
+    oa, ga, go = run(a, xa, ei.to(DEV))
+    ob = torch.relu(b(xb, ei.to(DEV)))
+    b.zero_grad()
+    ob.backward(go)
+    gb = [p.grad.clone() for p in b.parameters()]
+    oc, gc, _ = run(c, xc, ei.to(DEV))
+    assert torch.equal(oa, ob) and rel(oa, oc) < 1e-5
+    assert rel(xa.grad, xb.grad) < 1e-6 and rel(xa.grad, xc.grad) < 1e-5
+    for p, q, r in zip(ga, gb, gc):
+        assert rel(p, q) < 1e-5 and rel(p, r) < 1e-5
+    # explicit edge weights take the unfolded path: same semantics with the activation as a separate op
+    w = torch.rand(ei.shape[1], generator=torch.Generator().manual_seed(15)).to(DEV)
+    assert torch.equal(a(x.to(DEV), ei.to(DEV), w), torch.relu(b(x.to(DEV), ei.to(DEV), w)))
