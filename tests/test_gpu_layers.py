@@ -342,9 +342,16 @@ def test_bias_relu_epilogue_is_bit_identical_to_separate_passes(norm, dtype):
     if dtype == torch.float32:
         assert torch.equal(fused, sep)
         assert torch.equal(xa.grad, xb.grad)
-    else:   # 16-bit: the fused path rounds to bf16 once (after bias and ReLU), the separate passes twice
-        assert rel(fused, sep) < 1e-2 and rel(xa.grad, xb.grad) < 2e-2
-    assert rel(ba.grad, bb.grad) < (1e-5 if dtype == torch.float32 else 2e-2)
+        assert rel(ba.grad, bb.grad) < 1e-5
+    else:
+        # 16-bit: the fused path rounds to bf16 once (after bias and ReLU), the separate passes twice, so outputs agree to
+        # bf16 precision and a few ReLU masks near zero differ.  The backward is checked against the fused output's own mask.
+        assert rel(fused, sep) < 2e-2
+        mask = (fused > 0).to(dtype)
+        xm = x.to(DEV).requires_grad_(True)
+        mpops.gcn_propagate(ei.to(DEV), xm, norm).backward(go.to(DEV) * mask)
+        assert torch.equal(xa.grad, xm.grad)
+        assert rel(ba.grad, (go.to(DEV) * mask).float().sum(0, keepdim=True)) < 2e-2
     # bias only / relu only
     assert torch.equal(mpops.gcn_propagate(ei.to(DEV), x.to(DEV), norm, relu=True), torch.relu(mpops.gcn_propagate(ei.to(DEV), x.to(DEV), norm)))
     if dtype == torch.float32:
