@@ -6,19 +6,44 @@ Two plug points, both left by the reference itself:
      `utils/degree.py`, `utils/norm.py`, 39 files) imported them by name.  enable() rebinds those names, in
      `gammagl.mpops`, `gammagl.mpops.torch` and in every already-imported `gammagl.*` module that holds a copy.
   2. `MessagePassing.propagate` takes the fused branch iff the concrete class defines `message_aggregate`
-     (`message_passing.py:144`).  enable(fuse_layers=True) installs one on GCNConv / SAGEConv / GATConv / GINConv --
+     (`message_passing.py:144`).  enable(fuse_layers=True) installs one on GCNConv / SAGEConv / GATConv / GINConv and the multi-hop layers --
      the override the authors left commented out (`gcn_conv.py:110-115`, `gat_conv.py:124-129`).
+  3. (utils=True) `gammagl.utils.sort_edge_index` / `coalesce` copies are wrapped: CUDA tensors go to the GPU two-key sort
+     (`gammagl_b200.utils`), numpy arrays and CPU tensors to the original.
 disable() restores the originals.
 """
+import functools
 import sys
+import types
+
+import torch
 
 from . import mpops
+from . import utils as _utils
 
 _NAMES = ['unsorted_segment_sum', 'unsorted_segment_mean', 'unsorted_segment_max', 'segment_sum', 'segment_mean',
           'segment_max', 'gspmm', 'bspmm', 'c_segment_sum', 'c_segment_mean', 'c_segment_max', 'c_spmm_sum',
           'c_spmm_mean', 'c_spmm_max', 'c_bspmm_sum']
-_FUSED_LAYERS = ['GCNConv', 'SAGEConv', 'GATConv', 'GINConv']
+# Layers whose `message` is the base gather-times-weight (message_passing.py:55-61) and that call propagate() with 1-D (or
+# per-head) edge weights: the fused operator computes exactly their message + aggregate.  The second line are the multi-hop
+# layers (K propagates on one edge_index per forward: sgc_conv.py:47-48, appnp_conv.py:30-36, gcnii_conv.py:75-86,
+# gpr_conv.py:72-73, mixhop_conv.py:95-100, cheb_conv.py:117-121, hid_conv.py:95-96, magcl_conv.py:85-87), where the CSR
+# cached on the first hop serves all the others.
+_FUSED_LAYERS = ['GCNConv', 'SAGEConv', 'GATConv', 'GINConv',
+                 'SGConv', 'APPNPConv', 'GCNIIConv', 'GPRConv', 'MixHopConv', 'ChebConv', 'Hid', 'MAGCLConv']
+_UTILS = ['sort_edge_index', 'coalesce']   # gammagl/utils/sort_edge_index.py, coalesce.py: host argsort -> GPU two-key sort
 _saved = []
+
+
+def _cuda_or_original(new, old):
+    """The reference utilities also serve numpy arrays and CPU tensors: only CUDA tensors are routed to the GPU sort."""
+    @functools.wraps(old)
+    def dispatch(edge_index, *args, **kwargs):
+        if isinstance(edge_index, torch.Tensor) and edge_index.is_cuda:
+            return new(edge_index, *args, **kwargs)
+        return old(edge_index, *args, **kwargs)
+    dispatch._gglb200_original = old
+    return dispatch
 
 
 def _fused_message_aggregate(self, x, edge_index, edge_weight=None, aggr='sum', num_nodes=None):
@@ -32,7 +57,7 @@ def _fused_message_aggregate(self, x, edge_index, edge_weight=None, aggr='sum', 
     return mpops.gspmm(edge_index, edge_weight, x, aggr)
 
 
-def enable(fuse_layers=True, modules=None):
+def enable(fuse_layers=True, modules=None, utils=True):
     """Rebind the aggregation operators of an imported `gammagl` to this backend.  Returns the number of rebinds."""
     mods = modules if modules is not None else {k: v for k, v in sys.modules.items()
                                                 if v is not None and (k == 'gammagl' or k.startswith('gammagl.'))}
@@ -48,10 +73,17 @@ def enable(fuse_layers=True, modules=None):
                     _saved.append((mod, fn, old, True))
                     setattr(mod, fn, new)
                     count += 1
-        if hasattr(mod, 'segment_softmax') and name.endswith('softmax'):
+        if name.endswith('softmax') and getattr(mod, 'segment_softmax', mpops.segment_softmax) is not mpops.segment_softmax:
             _saved.append((mod, 'segment_softmax', getattr(mod, 'segment_softmax'), True))
             setattr(mod, 'segment_softmax', mpops.segment_softmax)
             count += 1
+        if utils:
+            for fn in _UTILS:
+                old = getattr(mod, fn, None)
+                if callable(old) and not isinstance(old, types.ModuleType) and not hasattr(old, '_gglb200_original'):
+                    _saved.append((mod, fn, old, True))
+                    setattr(mod, fn, _cuda_or_original(getattr(_utils, fn), old))
+                    count += 1
         if fuse_layers:
             for cls_name in _FUSED_LAYERS:
                 cls = getattr(mod, cls_name, None)

@@ -27,13 +27,20 @@ def _fake_gammagl():
             return 'message_aggregate' in self.__class__.__dict__
     msg.MessagePassing = MessagePassing
     conv = types.ModuleType('gammagl.layers.conv')
-    for n in plugin._FUSED_LAYERS + ['SGConv']:
+    for n in plugin._FUSED_LAYERS + ['HGTConv']:
         setattr(conv, n, type(n, (MessagePassing,), {}))
     sm = types.ModuleType('gammagl.utils.softmax')
     sm.segment_softmax = orig
     sm.unsorted_segment_max = orig
+    ut = types.ModuleType('gammagl.utils')
+    ut.coalesce = lambda edge_index, *a, **k: ('original', edge_index)       # the function shadows the submodule name
+    ut.sort_edge_index = lambda edge_index, *a, **k: ('original', edge_index)
+    utc = types.ModuleType('gammagl.utils.coalesce')
+    utc.coalesce = ut.coalesce
+    mods_extra = {'gammagl.utils': ut, 'gammagl.utils.coalesce': utc}
     mods = {'gammagl': pkg, 'gammagl.mpops': mp, 'gammagl.mpops.torch': mpt,
             'gammagl.layers.conv.message_passing': msg, 'gammagl.layers.conv': conv, 'gammagl.utils.softmax': sm}
+    mods.update(mods_extra)
     return mods, orig
 
 
@@ -49,8 +56,17 @@ def test_enable_rebinds_every_copy_and_disable_restores():
     conv = mods['gammagl.layers.conv']
     for name in plugin._FUSED_LAYERS:
         assert getattr(conv, name)().propagate() is True      # reference switch (message_passing.py:144) now fuses
-    assert conv.SGConv().propagate() is False                 # other layers are left alone
+    assert conv.HGTConv().propagate() is False                # layers with their own message() are left alone
+    # utilities: CPU tensors / numpy keep the original implementation, CUDA tensors would go to the GPU sort
+    import torch
+    cpu_ei = torch.tensor([[1, 0], [0, 1]])
+    original_coalesce = mods['gammagl.utils.coalesce'].coalesce._gglb200_original
+    assert mods['gammagl.utils'].coalesce(cpu_ei) == ('original', cpu_ei)
+    assert mods['gammagl.utils.coalesce'].coalesce(cpu_ei)[0] == 'original'
+    assert mods['gammagl.utils'].sort_edge_index([[0], [1]])[0] == 'original'
+    assert plugin.enable(modules=mods) == 0                    # idempotent: nothing left to rebind
     plugin.disable()
+    assert mods['gammagl.utils'].coalesce is original_coalesce
     assert mods['gammagl.mpops'].gspmm is orig
     assert mods['gammagl.mpops'].use_ext is False
     assert getattr(conv, 'GCNConv')().propagate() is False
