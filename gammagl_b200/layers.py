@@ -50,9 +50,14 @@ class MessagePassing(torch.nn.Module):
     """message_passing.py:35-167.  propagate() takes the fused branch when the subclass did not override
     `message` (the base message is gather x weight, exactly what gspmm fuses) and `fused` is on."""
 
-    def __init__(self, fused=True):
+    def __init__(self, fused=True, fuse_max=False):
         super().__init__()
         self.fused = fused
+        # aggr='max': the reference layer runs message + unsorted_segment_max, whose backward credits the FIRST winning edge
+        # only (src/segment_max.cpp:48-61); its gspmm-max operator credits every parallel edge of the winning source
+        # (cpu/spmm_max_cpu.cpp:84-96).  Both operators are reproduced exactly, so on multigraphs the fused form would change
+        # the layer's gradients: max is fused only on request (graphs without parallel edges), sum / mean always.
+        self.fuse_max = fuse_max
 
     def message(self, x, edge_index, edge_weight=None):
         msg = x[edge_index[0, :]]                                           # message_passing.py:56
@@ -84,7 +89,7 @@ class MessagePassing(torch.nn.Module):
         edge_weight = kwargs.get('edge_weight')
         base_message = type(self).message is MessagePassing.message
         square = kwargs['num_nodes'] == x.shape[0]                          # gspmm output rows = x rows (no bipartite)
-        if self.fused and base_message and square:
+        if self.fused and base_message and square and (aggr != 'max' or self.fuse_max):
             out = self.message_aggregate(x, edge_index, edge_weight=edge_weight, aggr=aggr)
         else:
             if base_message:

@@ -48,8 +48,10 @@ def _cuda_or_original(new, old):
 
 def _fused_message_aggregate(self, x, edge_index, edge_weight=None, aggr='sum', num_nodes=None):
     """Fused gather x weight -> reduce.  Falls back to the reference's own decomposition (still on the B200 segment
-    operators) for bipartite calls, where gspmm's output row count (= x rows) would be wrong."""
-    if num_nodes is not None and num_nodes != x.shape[0]:
+    operators) for bipartite calls, where gspmm's output row count (= x rows) would be wrong, and for aggr='max'."""
+    if (num_nodes is not None and num_nodes != x.shape[0]) or aggr == 'max':
+        # max: message + unsorted_segment_max credits the first winning edge only, gspmm-max every parallel edge of the winning
+        # source (cpu/spmm_max_cpu.cpp:84-96) -- the layer keeps the reference layer's gradients on multigraphs
         msg = self.message(x, edge_index, edge_weight) if edge_weight is not None else self.message(x, edge_index)
         return self.aggregate(msg, edge_index, num_nodes=num_nodes, aggr=aggr)
     if edge_weight is not None and edge_weight.dim() == 2 and x.dim() == 3:

@@ -83,12 +83,14 @@ def test_sage_conv(aggr):
     if aggr == 'pool':
         # duplicate (src,dst) pairs: the reference's gspmm-max backward credits EVERY parallel edge of the winning
         # source (cpu/spmm_max_cpu.cpp:84-96) while segment_max credits the first edge only -- both are reproduced
-        # exactly, so the fused and unfused layers agree only on a coalesced graph.
+        # exactly, so the gspmm-max form (fuse_max=True) and the layer's default message + segment_max form agree only
+        # on a coalesced graph.
         ei = torch.unique(ei, dim=1)
     if aggr == 'gcn':
         ei[0, 0] = N - 1          # the layer sizes the graph by 1 + max(src) (sage_conv.py:84-86)
     x = torch.randn(N, F, generator=torch.Generator().manual_seed(4))
     fused = SAGEConv(F, H, aggr=aggr).to(DEV)
+    fused.fuse_max = True
     unfused = copy.deepcopy(fused)
     unfused.fused = False
     xf = x.to(DEV).requires_grad_(True)
