@@ -6,6 +6,10 @@ TEST INFRASTRUCTURE ONLY.  Compiles, unmodified and where they lie, the referenc
 into oracle/_ref/_torch_ext.so with torch.utils.cpp_extension (the sources depend on libtorch only).
 Flags follow what the reference's setup.py effectively ships for a CPU build (setup.py:83-88): no
 COMPILE_WITH_OMP (the macro is misspelt there, setup.py:50), no COMPILE_WITH_CUDA, -O2.
+The OpenMP variant is not an alternative: with -fopenmp -DCOMPILE_WITH_OMP the sources do not compile (tried here with
+g++: `'idx' has not been declared` at cpu/segment_max_cpu.cpp:46, `#pragma omp critical` in an invalid position at
+cpu/segment_sum_cpu.cpp:52, segment_mean_cpu.cpp:55,71, segment_max_cpu.cpp:56), so the single-threaded edge loops are the
+only CPU implementation of the path the reference can actually ship, and the one bench.py times.
 
 No reference source is copied into this repo; only the built .so lands in oracle/_ref/ (git-ignored,
 NOT gpurun-ignored, so it travels to the GPU box).  If /root/reference is absent (GPU box) the
