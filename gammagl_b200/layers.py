@@ -78,6 +78,10 @@ class MessagePassing(torch.nn.Module):
     def message_aggregate(self, x, edge_index, edge_weight=None, aggr='sum'):
         if edge_weight is not None and edge_weight.dim() == 2 and x.dim() == 3:
             return mpops.bspmm(edge_index, edge_weight, x, aggr)            # per-head weights (GAT)
+        if mpops.weight_needs_grad(edge_weight) and x.dim() == 2 and aggr == 'sum':
+            # gspmm has no gradient for the weight (src/gspmm.cpp:30,79) but the reference layer's message * weight has:
+            # the one-head bspmm is the same forward kernel plus the SDDMM weight gradient
+            return mpops.bspmm(edge_index, edge_weight.reshape(-1, 1), x.unsqueeze(1), 'sum').squeeze(1)
         return mpops.gspmm(edge_index, edge_weight, x, aggr)                # message_passing.py:99-104
 
     def update(self, x):
@@ -89,7 +93,8 @@ class MessagePassing(torch.nn.Module):
         edge_weight = kwargs.get('edge_weight')
         base_message = type(self).message is MessagePassing.message
         square = kwargs['num_nodes'] == x.shape[0]                          # gspmm output rows = x rows (no bipartite)
-        if self.fused and base_message and square and (aggr != 'max' or self.fuse_max):
+        differentiable_w = mpops.weight_needs_grad(edge_weight) and not (aggr == 'sum' and x.dim() in (2, 3))
+        if self.fused and base_message and square and (aggr != 'max' or self.fuse_max) and not differentiable_w:
             out = self.message_aggregate(x, edge_index, edge_weight=edge_weight, aggr=aggr)
         else:
             if base_message:

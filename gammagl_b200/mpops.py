@@ -399,6 +399,12 @@ def gcn_propagate(edge_index, x, norm='both', bias=None, relu=False):
     return _GcnPropagate.apply(x, edge_index, norm, bias, relu)
 
 
+def weight_needs_grad(weight):
+    """True when autograd must reach an edge weight: gspmm cannot provide that gradient (no grad for weight in the reference
+    operator either, src/gspmm.cpp:30,79), the callers then use bspmm (sum) or the message + aggregate decomposition."""
+    return weight is not None and weight.requires_grad and torch.is_grad_enabled()
+
+
 def gspmm(index, weight=None, x=None, reduce='sum'):
     """Generalized SpMM: out[dst] (+|mean|max)= weight[e] * x[src]  (torch.py:302-351)."""
     if reduce == 'sum':

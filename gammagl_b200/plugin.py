@@ -49,7 +49,12 @@ def _cuda_or_original(new, old):
 def _fused_message_aggregate(self, x, edge_index, edge_weight=None, aggr='sum', num_nodes=None):
     """Fused gather x weight -> reduce.  Falls back to the reference's own decomposition (still on the B200 segment
     operators) for bipartite calls, where gspmm's output row count (= x rows) would be wrong, and for aggr='max'."""
-    if (num_nodes is not None and num_nodes != x.shape[0]) or aggr == 'max':
+    differentiable_w = mpops.weight_needs_grad(edge_weight)
+    if differentiable_w and aggr == 'sum' and x.dim() == 2 and edge_weight.dim() == 1 and (num_nodes is None or num_nodes == x.shape[0]):
+        # the reference layer's message * weight is differentiable in the weight, gspmm is not (src/gspmm.cpp:30,79):
+        # one-head bspmm = the same forward kernel + the SDDMM weight gradient
+        return mpops.bspmm(edge_index, edge_weight.reshape(-1, 1), x.unsqueeze(1), 'sum').squeeze(1)
+    if (num_nodes is not None and num_nodes != x.shape[0]) or aggr == 'max' or (differentiable_w and not (edge_weight.dim() == 2 and x.dim() == 3)):
         # max: message + unsorted_segment_max credits the first winning edge only, gspmm-max every parallel edge of the winning
         # source (cpu/spmm_max_cpu.cpp:84-96) -- the layer keeps the reference layer's gradients on multigraphs
         msg = self.message(x, edge_index, edge_weight) if edge_weight is not None else self.message(x, edge_index)
