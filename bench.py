@@ -339,6 +339,11 @@ def run_b200(args):
                 'algorithmic_bytes_per_launch': alg_bytes, 'avg_launch_ms': kavg, 'launches_timed': len(kern_ms),
                 'peak_source': peak_src,
                 'formula': 'E*(K*s+4+4) + N*(K*s+4) per SpMM pass (SURVEY.md 8d gather model)'}
+    if traffic:
+        # the same launch seen from DRAM: bytes that actually crossed HBM (ncu, per launch) over the live launch time.  frac > 1
+        # above means gathered rows were served by L2; this figure says how close the launch runs to the memory system itself.
+        roofline['dram_achieved'] = traffic / (kavg * 1e-3) / 1e9
+        roofline['dram_frac'] = roofline['dram_achieved'] / peak
 
     # end-to-end through the public operator with HOST buffers (pinned): x and grad_out go up, out and grad_x come back
     e2e = None
