@@ -3,6 +3,8 @@ on the GPU two-key sort of `gglb200_sort_edges` instead of a host argsort.
 
     sort_edge_index   /root/reference/gammagl/utils/sort_edge_index.py:5-45
     coalesce          /root/reference/gammagl/utils/coalesce.py:8-78
+    to_undirected     /root/reference/gammagl/utils/undirected.py:62-109 (concat both directions, coalesce)
+    is_undirected     /root/reference/gammagl/utils/undirected.py:6-59   (row-sorted == transposed column-sorted, incl. attributes)
     maybe_num_nodes   /root/reference/gammagl/utils/num_nodes.py
 
 Same names, argument meaning and return values.  Differences, all deliberate:
@@ -104,3 +106,25 @@ def coalesce(edge_index, edge_attr=None, num_nodes=None, reduce='add', is_sorted
     if edge_attr is None:
         return out
     return out, _map_attr(attr, lambda t: mpops.unsorted_segment_sum(t, group, U))   # coalesce.py:76
+
+
+def to_undirected(edge_index, edge_attr=None, num_nodes=None, reduce='add'):
+    """Add the reverse of every edge and merge duplicates (undirected.py:96-109): coalesce(cat(ei, ei[::-1]))."""
+    require_cuda(edge_index, 'edge_index')
+    if isinstance(edge_attr, int):                             # undirected.py:96-98: to_undirected(edge_index, num_nodes)
+        edge_attr, num_nodes = None, edge_attr
+    row, col = edge_index[0], edge_index[1]
+    both = torch.stack([torch.cat([row, col]), torch.cat([col, row])])
+    attr = _map_attr(edge_attr, lambda t: torch.cat([t, t], dim=0))
+    return coalesce(both, attr, num_nodes, reduce)
+
+
+def is_undirected(edge_index, edge_attr=None, num_nodes=None):
+    """True iff the row-sorted edge list equals the transposed column-sorted one, attributes included (undirected.py:35-59)."""
+    require_cuda(edge_index, 'edge_index')
+    N = maybe_num_nodes(edge_index, num_nodes)
+    attrs = [] if edge_attr is None else ([edge_attr] if isinstance(edge_attr, torch.Tensor) else list(edge_attr))
+    ei1, attr1 = sort_edge_index(edge_index, attrs, N, sort_by_row=True)
+    ei2, attr2 = sort_edge_index(ei1, attr1, N, sort_by_row=False)
+    return (bool((ei1[0] == ei2[1]).all()) and bool((ei1[1] == ei2[0]).all())
+            and all(bool((a == b).all()) for a, b in zip(attr1, attr2)))

@@ -196,3 +196,22 @@ def coalesce(edge_index, edge_attr, num_nodes, sort_by_row=True):
         return out, None
     idx = np.arange(ei.shape[1]) - (1 - mask).cumsum()
     return out, segment('sum', attr, idx, out.shape[1])
+
+
+def to_undirected(edge_index, edge_attr, num_nodes):
+    """gammagl/utils/undirected.py:99-109: both directions concatenated, then coalesce."""
+    ei = np.ascontiguousarray(edge_index, dtype=np.int64)
+    both = np.stack([np.concatenate([ei[0], ei[1]]), np.concatenate([ei[1], ei[0]])])
+    attr = None if edge_attr is None else np.concatenate([edge_attr, edge_attr], axis=0)
+    return coalesce(both, attr, num_nodes, True)
+
+
+def is_undirected(edge_index, edge_attr, num_nodes):
+    """gammagl/utils/undirected.py:35-59."""
+    ei1, p1 = sort_edge_index(edge_index, num_nodes, True)
+    ei2, p2 = sort_edge_index(ei1, num_nodes, False)
+    ok = bool(np.all(ei1[0] == ei2[1]) and np.all(ei1[1] == ei2[0]))
+    if edge_attr is not None:
+        a1 = np.asarray(edge_attr)[p1]
+        ok = ok and bool(np.all(a1 == a1[p2]))
+    return ok

@@ -45,6 +45,9 @@ def _tlx_shim():
     def gather(x, indices, axis=0):
         return torch.index_select(x, axis, torch.as_tensor(indices, dtype=torch.int64))
     tlx.gather = gather
+    tlx.concat = lambda xs, axis=0: torch.cat(list(xs), dim=axis)
+    tlx.stack = lambda xs, axis=0: torch.stack(list(xs), dim=axis)
+    tlx.all = torch.all
     tlx.ops = types.SimpleNamespace(is_tensor=tlx.is_tensor, argsort=lambda x, descending=False: torch.argsort(x, descending=descending),
                                     convert_to_numpy=tlx.convert_to_numpy)
     return tlx
@@ -62,11 +65,12 @@ def load_reference_utils():
     _exec_reference('utils/num_nodes.py', ns)
     _exec_reference('utils/sort_edge_index.py', ns)
     _exec_reference('utils/coalesce.py', ns)
-    return ns['sort_edge_index'], ns['coalesce']
+    _exec_reference('utils/undirected.py', ns)
+    return ns['sort_edge_index'], ns['coalesce'], ns['to_undirected'], ns['is_undirected']
 
 
 def main():
-    sort_edge_index, coalesce = load_reference_utils()
+    sort_edge_index, coalesce, to_undirected, is_undirected = load_reference_utils()
     # ---- KATs -------------------------------------------------------------------------------------
     ei = torch.tensor([[2, 1, 1, 0], [1, 2, 0, 1]])
     attr = torch.tensor([[1], [2], [3], [4]])
@@ -80,7 +84,17 @@ def main():
     assert c1.tolist() == [[0, 1], [1, 0]]                                   # test_coalesce.py:13-14
     c2 = coalesce(cei, cattr)
     assert c2[0].tolist() == [[0, 1], [1, 0]] and c2[1].tolist() == [[-4.0, 4.0], [2.0, 5.0]]              # :18-21
-    np.savez(os.path.join(HERE, 'utils_kat.npz'), sort_ei=ei.numpy(), sort_attr=attr.numpy(), sort_out=out.numpy(),
+    # tests/utils/test_undirected.py:5-36
+    r1, c1 = torch.tensor([0, 1, 0]), torch.tensor([1, 0, 0])
+    assert is_undirected(torch.stack([r1, c1])) and is_undirected(torch.stack([r1, c1]), torch.tensor([0, 0, 1]))
+    assert not is_undirected(torch.stack([r1, c1]), torch.tensor([0, 1, 1]))
+    r2, c2 = torch.tensor([0, 1, 1]), torch.tensor([1, 0, 2])
+    assert not is_undirected(torch.stack([r2, c2]))
+    uattr = torch.tensor([[1, 0], [2, 3], [-5, 4]], dtype=torch.float32)
+    uei, ua = to_undirected(edge_index=torch.stack([r2, c2]), edge_attr=uattr, reduce='add')
+    assert uei.tolist() == [[0, 1, 1, 2], [1, 0, 2, 1]] and ua.tolist() == [[3., 3.], [3., 3.], [-5., 4.], [-5., 4.]]
+    np.savez(os.path.join(HERE, 'utils_kat.npz'), und_ei=torch.stack([r2, c2]).numpy(), und_attr=uattr.numpy(), und_out=uei.numpy(),
+             und_out_attr=ua.numpy(), sort_ei=ei.numpy(), sort_attr=attr.numpy(), sort_out=out.numpy(),
              sort_out_attr=out2[1].numpy(), co_ei=cei.numpy(), co_attr=cattr.numpy(), co_out=c2[0].numpy(),
              co_out_attr=c2[1].numpy())
     # ---- randomized -------------------------------------------------------------------------------
@@ -102,6 +116,9 @@ def main():
                 rec['sort_%s_attr' % tag] = s_at.numpy()
             rec['co_%s_ei' % tag] = c_ei.numpy()
             rec['co_%s_attr' % tag] = c_at.numpy()
+        u_ei, u_at = to_undirected(e.clone(), a.clone(), N)
+        rec['und_ei'], rec['und_attr'] = u_ei.numpy(), u_at.numpy()
+        rec['is_und'] = np.array([is_undirected(e.clone(), None, N), is_undirected(u_ei, None, N), is_undirected(u_ei, u_at, N)])
         np.savez_compressed(os.path.join(HERE, 'utils_rand_%s.npz' % name), **rec)
         print(name, 'E', E, 'unique', rec['co_row_ei'].shape[1])
 

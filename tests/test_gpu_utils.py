@@ -105,3 +105,24 @@ def test_sorted_input_is_unchanged_and_idempotent(U):
     assert torch.equal(U.coalesce(c, num_nodes=1000, is_sorted=True), c)
     key = c[0] * 1000 + c[1]
     assert bool((key[1:] > key[:-1]).all())
+
+
+def test_undirected_kat_and_reference_outputs(U):
+    """to_undirected / is_undirected (utils/undirected.py) against tests/utils/test_undirected.py:5-36 and reference outputs."""
+    z = np.load(os.path.join(GOLDEN, 'utils_kat.npz'))
+    row, col = torch.tensor([0, 1, 0], device=DEV), torch.tensor([1, 0, 0], device=DEV)
+    assert U.is_undirected(torch.stack([row, col]))
+    assert U.is_undirected(torch.stack([row, col]), torch.tensor([0, 0, 1], device=DEV))
+    assert not U.is_undirected(torch.stack([row, col]), torch.tensor([0, 1, 1], device=DEV))
+    assert not U.is_undirected(cu(z['und_ei']))
+    ei, attr = U.to_undirected(cu(z['und_ei']), cu(z['und_attr']))
+    assert ei.cpu().tolist() == [[0, 1, 1, 2], [1, 0, 2, 1]]
+    assert attr.cpu().tolist() == [[3., 3.], [3., 3.], [-5., 4.], [-5., 4.]]
+    assert U.to_undirected(cu(z['und_ei']), 3).cpu().tolist() == [[0, 1, 1, 2], [1, 0, 2, 1]]       # (edge_index, num_nodes) form
+    for path in RAND:
+        r = np.load(path)
+        N = int(r['N'])
+        ei, attr = U.to_undirected(cu(r['ei']), cu(r['attr']), N)
+        assert np.array_equal(ei.cpu().numpy(), r['und_ei']) and np.array_equal(attr.cpu().numpy(), r['und_attr'])
+        got = [U.is_undirected(cu(r['ei']), None, N), U.is_undirected(ei, None, N), U.is_undirected(ei, attr, N)]
+        assert got == r['is_und'].tolist()

@@ -39,3 +39,27 @@ def test_oracle_matches_reference_outputs(path):
         ei, attr = O.coalesce(z['ei'], z['attr'], N, sbr)
         assert np.array_equal(ei, z['co_%s_ei' % tag])
         assert np.array_equal(attr, z['co_%s_attr' % tag])                   # integer-valued floats: exact in any order
+
+
+def test_kat_undirected():
+    """/root/reference/tests/utils/test_undirected.py:5-36."""
+    z = np.load(os.path.join(GOLDEN, 'utils_kat.npz'))
+    row, col = np.array([0, 1, 0]), np.array([1, 0, 0])
+    assert O.is_undirected(np.stack([row, col]), None, 2)
+    assert O.is_undirected(np.stack([row, col]), np.array([0, 0, 1]), 2)
+    assert not O.is_undirected(np.stack([row, col]), np.array([0, 1, 1]), 2)
+    assert not O.is_undirected(z['und_ei'], None, 3)
+    ei, attr = O.to_undirected(z['und_ei'], z['und_attr'], 3)
+    assert ei.tolist() == [[0, 1, 1, 2], [1, 0, 2, 1]]
+    assert attr.tolist() == [[3., 3.], [3., 3.], [-5., 4.], [-5., 4.]]
+    assert np.array_equal(ei, z['und_out']) and np.array_equal(attr, z['und_out_attr'])
+
+
+@pytest.mark.parametrize('path', RAND, ids=[os.path.basename(p)[:-4] for p in RAND])
+def test_undirected_oracle_matches_reference_outputs(path):
+    z = np.load(path)
+    N = int(z['N'])
+    ei, attr = O.to_undirected(z['ei'], z['attr'], N)
+    assert np.array_equal(ei, z['und_ei']) and np.array_equal(attr, z['und_attr'])
+    got = [O.is_undirected(z['ei'], None, N), O.is_undirected(z['und_ei'], None, N), O.is_undirected(z['und_ei'], z['und_attr'], N)]
+    assert got == z['is_und'].tolist()
