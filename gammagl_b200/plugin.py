@@ -64,6 +64,13 @@ def _fused_message_aggregate(self, x, edge_index, edge_weight=None, aggr='sum', 
     return mpops.gspmm(edge_index, edge_weight, x, aggr)
 
 
+# MessagePassing.__init__ registers the method with Inspector.inspect(), which files the signature under func.__name__
+# (utils/inspector.py:27-41) and then looks it up as 'message_aggregate' (message_passing.py:29-33): the installed function
+# must carry that name or constructing any patched layer raises KeyError.
+_fused_message_aggregate.__name__ = 'message_aggregate'
+_fused_message_aggregate.__qualname__ = 'message_aggregate'
+
+
 def enable(fuse_layers=True, modules=None, utils=True):
     """Rebind the aggregation operators of an imported `gammagl` to this backend.  Returns the number of rebinds."""
     mods = modules if modules is not None else {k: v for k, v in sys.modules.items()

@@ -111,6 +111,11 @@ def make_tlx():
     tlx.expand_dims = lambda x, axis: torch.unsqueeze(x, axis)
     tlx.convert_to_tensor = lambda x, dtype=None: torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x, dtype=dtype)
     tlx.convert_to_numpy = lambda x: x.detach().cpu().numpy()
+    tlx.cast = lambda x, dtype=None: x if dtype is None or x.dtype == dtype else x.to(dtype)
+    tlx.zeros_like = lambda x, dtype=None: torch.zeros_like(x, dtype=dtype)
+    tlx.constant = lambda value, dtype=torch.float32, shape=None, device=None: torch.full(tuple(shape), value, dtype=dtype)
+    inits.Constant = lambda value=0.0: (lambda shape, dtype=torch.float32: torch.as_tensor(np.asarray(value), dtype=dtype).reshape(tuple(shape)).clone())
+    nn.ModuleList, nn.ModuleDict = torch.nn.ModuleList, torch.nn.ModuleDict
     for name, mod in (('tensorlayerx', tlx), ('tensorlayerx.nn', nn), ('tensorlayerx.ops', ops), ('tensorlayerx.initializers', inits)):
         sys.modules[name] = mod
     return tlx
@@ -165,6 +170,11 @@ def load_reference_layers():
                    ('SGConv', 'sgc_conv'), ('APPNPConv', 'appnp_conv')):
         out[cls] = getattr(_load('gammagl.layers.conv.' + f, 'layers/conv/%s.py' % f), cls)
     return out
+
+
+def load_extra_layer(cls, f):
+    """Another reference conv layer (after load_reference_layers()), e.g. load_extra_layer('GCNIIConv', 'gcnii_conv')."""
+    return getattr(_load('gammagl.layers.conv.' + f, 'layers/conv/%s.py' % f), cls)
 
 
 def graph(N, E, seed):

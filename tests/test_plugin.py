@@ -56,6 +56,7 @@ def test_enable_rebinds_every_copy_and_disable_restores():
     conv = mods['gammagl.layers.conv']
     for name in plugin._FUSED_LAYERS:
         assert getattr(conv, name)().propagate() is True      # reference switch (message_passing.py:144) now fuses
+        assert getattr(conv, name).message_aggregate.__name__ == 'message_aggregate'   # Inspector files signatures by __name__
     assert conv.HGTConv().propagate() is False                # layers with their own message() are left alone
     # utilities: CPU tensors / numpy keep the original implementation, CUDA tensors would go to the GPU sort
     import torch
