@@ -87,7 +87,8 @@ def enable(fuse_layers=True, modules=None, utils=True):
                     _saved.append((mod, fn, old, True))
                     setattr(mod, fn, new)
                     count += 1
-        if name.endswith('softmax') and getattr(mod, 'segment_softmax', mpops.segment_softmax) is not mpops.segment_softmax:
+        # every copy: utils/softmax.py defines it, utils/__init__ and gat_conv.py (`from gammagl.utils import segment_softmax`) hold one
+        if callable(getattr(mod, 'segment_softmax', None)) and mod.segment_softmax is not mpops.segment_softmax:
             _saved.append((mod, 'segment_softmax', getattr(mod, 'segment_softmax'), True))
             setattr(mod, 'segment_softmax', mpops.segment_softmax)
             count += 1

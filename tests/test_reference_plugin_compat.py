@@ -111,3 +111,33 @@ def test_fused_branch_on_reference_layers_equals_message_plus_aggregate(ref):
     # the four target layers and the multi-hop ones the shim can build (ChebConv and Hid need get_laplacian / cal_g_gradient;
     # their propagate() calls were checked by reading cheb_conv.py:117-121 and hid_conv.py:95-96)
     assert names >= {'GCNConv', 'SAGEConv', 'GATConv', 'GINConv', 'SGConv', 'APPNPConv', 'GCNIIConv', 'GPRConv', 'MixHopConv', 'MAGCLConv'}
+
+
+def test_enable_rebinds_the_real_module_tree(ref):
+    """plugin.enable() on the reference's real modules (loaded by path): every copy of the operators and of segment_softmax is
+    rebound -- also the ones `from gammagl.utils import segment_softmax` left in gat_conv.py -- and disable() restores them."""
+    G, L, plugin, tlx = ref
+    from gammagl_b200 import mpops as b200
+    saved_ops, plugin.mpops = plugin.mpops, b200
+    mods = {k: v for k, v in sys.modules.items() if k == 'gammagl' or k.startswith('gammagl.')}
+    before = {k: getattr(v, 'segment_softmax', None) for k, v in mods.items()}
+    try:
+        n = plugin.enable(modules=mods)
+        assert n > 40
+        assert sys.modules['gammagl.layers.conv.message_passing'].unsorted_segment_sum is b200.unsorted_segment_sum
+        assert sys.modules['gammagl.layers.conv.message_passing'].gspmm is b200.gspmm
+        assert sys.modules['gammagl.mpops.torch'].c_spmm_sum is b200.c_spmm_sum and sys.modules['gammagl.mpops'].use_ext is True
+        for name in ('gammagl.utils.softmax', 'gammagl.utils', 'gammagl.layers.conv.gat_conv'):
+            assert sys.modules[name].segment_softmax is b200.segment_softmax, name
+        assert sys.modules['gammagl.utils.norm'].unsorted_segment_sum is b200.unsorted_segment_sum      # calc_gcn_norm
+        assert sys.modules['gammagl.utils.degree'].unsorted_segment_sum is b200.unsorted_segment_sum    # degree
+        for cls in ('GCNConv', 'SAGEConv', 'GATConv', 'GINConv', 'SGConv', 'APPNPConv', 'GCNIIConv', 'GPRConv', 'MixHopConv', 'MAGCLConv'):
+            assert 'message_aggregate' in L[cls].__dict__, cls
+        L['GCNConv'](4, 4)                                                     # constructing a patched layer must not raise
+    finally:
+        plugin.disable()
+        plugin.mpops = saved_ops
+    for k, v in mods.items():
+        assert getattr(v, 'segment_softmax', None) is before[k], k
+    assert 'message_aggregate' not in L['GCNConv'].__dict__
+    assert sys.modules['gammagl.layers.conv.message_passing'].gspmm is not b200.gspmm
