@@ -62,6 +62,17 @@ def permute_rows(t, perm):
     return out
 
 
+def unique_pairs(sorted_major, sorted_minor, group, n_unique):
+    """First pair of every duplicate group of a sorted pair list (gglb200_unique_edges; coalesce.py:69)."""
+    dev, E = sorted_major.device, sorted_major.numel()
+    um = torch.empty(n_unique, dtype=torch.int64, device=dev)
+    un = torch.empty(n_unique, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().gglb200_unique_edges(_ptr(sorted_major), _ptr(sorted_minor), _ptr(group), E, _ptr(um), _ptr(un),
+                                                    _stream(dev)), 'unique_edges')
+    return um, un
+
+
 def _map_attr(edge_attr, fn):
     if edge_attr is None:
         return None
@@ -87,7 +98,6 @@ def coalesce(edge_index, edge_attr=None, num_nodes=None, reduce='add', is_sorted
     """Sort edge_index and merge duplicate edges, summing their attributes (coalesce.py:41-78).
     `is_sorted` is accepted for signature parity; the stable sort leaves sorted input unchanged."""
     require_cuda(edge_index, 'edge_index')
-    lib = _lib.load()
     N = maybe_num_nodes(edge_index, num_nodes)
     a, b = (0, 1) if sort_by_row else (1, 0)
     sm, sn, perm, group, n_unique = sort_pairs(edge_index[a], edge_index[b], N, N, want_groups=True)
@@ -98,11 +108,7 @@ def coalesce(edge_index, edge_attr=None, num_nodes=None, reduce='add', is_sorted
     if U == E:                                                 # no duplicates (coalesce.py:63-66)
         out[a], out[b] = sm, sn
         return out if edge_attr is None else (out, attr)
-    um = torch.empty(U, dtype=torch.int64, device=dev)
-    un = torch.empty(U, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.gglb200_unique_edges(_ptr(sm), _ptr(sn), _ptr(group), E, _ptr(um), _ptr(un), _stream(dev)), 'unique_edges')
-    out[a], out[b] = um, un
+    out[a], out[b] = unique_pairs(sm, sn, group, U)
     if edge_attr is None:
         return out
     return out, _map_attr(attr, lambda t: mpops.unsorted_segment_sum(t, group, U))   # coalesce.py:76

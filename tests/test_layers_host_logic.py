@@ -1,0 +1,171 @@
+"""CPU test of the HOST logic of gammagl_b200.layers (the mirror of MessagePassing / GCN / SAGE / GAT / GIN / SGC / APPNP):
+the operators of gammagl_b200.mpops are replaced by plain torch CPU stand-ins with the reference operators' semantics
+(gspmm without a weight gradient, segment max = first-wins on distinct values, ...), and every layer case of
+tests/golden/layers_ref.npz -- outputs and input gradients of the reference's OWN layers -- must be reproduced, through the
+fused branch and through message + aggregate.  This is the CPU twin of tests/test_gpu_zz_reference_layers.py: it checks the
+layer algebra, parameter layout, routing (fuse / no fuse for max, differentiable edge weights, bipartite fall-back); the
+kernels behind the operators are covered by -m gpu."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gammagl_b200 import layers as L
+from gammagl_b200 import mpops
+
+Z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'layers_ref.npz'))
+TAGS = ['gcn_both', 'gcn_left', 'gcn_right', 'gcn_none', 'gcn_weighted', 'sage_mean', 'sage_gcn', 'sage_pool',
+        'gat_h8_cat', 'gat_h4_avg', 'gat_h1_cat', 'gin', 'sgc', 'appnp']
+
+
+def _bshape(ids, x):
+    return ids.reshape((-1,) + (1,) * (x.dim() - 1)).expand_as(x)
+
+
+def seg_sum(x, ids, n=None):
+    n = int(ids.max()) + 1 if n is None else int(n)
+    return torch.zeros((n,) + tuple(x.shape[1:]), dtype=x.dtype).index_add(0, ids, x)
+
+
+def seg_mean(x, ids, n=None):
+    n = int(ids.max()) + 1 if n is None else int(n)
+    cnt = torch.bincount(ids, minlength=n).clamp_min(1).to(x.dtype)
+    return seg_sum(x, ids, n) / cnt.reshape((-1,) + (1,) * (x.dim() - 1))
+
+
+def seg_max(x, ids, n=None):
+    n = int(ids.max()) + 1 if n is None else int(n)
+    out = torch.full((n,) + tuple(x.shape[1:]), torch.finfo(x.dtype).min, dtype=x.dtype)
+    return out.scatter_reduce(0, _bshape(ids, x), x, 'amax', include_self=True)
+
+
+def gspmm(index, weight=None, x=None, reduce='sum'):
+    msg = x[index[0]]
+    if weight is not None:
+        msg = msg * weight.detach().reshape((-1,) + (1,) * (x.dim() - 1))     # no gradient for the weight (src/gspmm.cpp:30,79)
+    return {'sum': seg_sum, 'mean': seg_mean, 'max': seg_max}[reduce](msg, index[1], x.shape[0])
+
+
+def bspmm(index, weight=None, x=None, reduce='sum'):
+    return seg_sum(x[index[0]] * weight.unsqueeze(-1), index[1], x.shape[0])
+
+
+def segment_softmax(data, ids, n):
+    mx = seg_max(data, ids, n)
+    ex = torch.exp(data - mx[ids].detach())
+    return ex / (seg_sum(ex, ids, n)[ids] + 1e-16)
+
+
+def gcn_propagate(edge_index, x, norm='both', bias=None, relu=False):
+    N = x.shape[0]
+    src, dst = edge_index
+    w = torch.ones(edge_index.shape[1], dtype=x.dtype)
+    p = -0.5 if norm == 'both' else -1.0
+    if norm in ('both', 'left'):
+        d = torch.bincount(src, minlength=N).to(x.dtype)
+        w = w * torch.where(d > 0, d.pow(p), torch.zeros_like(d))[src]
+    if norm in ('both', 'right'):
+        d = torch.bincount(dst, minlength=N).to(x.dtype)
+        w = w * torch.where(d > 0, d.pow(p), torch.zeros_like(d))[dst]
+    out = seg_sum(x[src] * w[:, None], dst, N)
+    if bias is not None:
+        out = out + bias.reshape(1, -1)
+    return torch.relu(out) if relu else out
+
+
+def gat_aggregate(edge_index, x, s_src, s_dst, negative_slope=0.2):
+    e = torch.nn.functional.leaky_relu(s_src[edge_index[0]] + s_dst[edge_index[1]], negative_slope)
+    return bspmm(edge_index, segment_softmax(e, edge_index[1], x.shape[0]), x)
+
+
+@pytest.fixture()
+def host(monkeypatch):
+    for name, fn in (('unsorted_segment_sum', seg_sum), ('unsorted_segment_mean', seg_mean), ('unsorted_segment_max', seg_max),
+                     ('gspmm', gspmm), ('bspmm', bspmm), ('segment_softmax', segment_softmax), ('gcn_propagate', gcn_propagate),
+                     ('gat_aggregate', gat_aggregate)):
+        monkeypatch.setattr(mpops, name, fn)
+    monkeypatch.setattr(L, 'degree', lambda index, num_nodes=None, dtype=torch.float32:
+                        torch.bincount(index, minlength=int(index.max()) + 1 if num_nodes is None else num_nodes).to(dtype))
+    return L
+
+
+def build(tag):
+    F, H = Z['x'].shape[1], 20
+    w = torch.from_numpy(Z['w'])
+    if tag.startswith('gcn_'):
+        norm = tag[4:]
+        return (L.GCNConv(F, H, norm='both'), (w,)) if norm == 'weighted' else (L.GCNConv(F, H, norm=norm), ())
+    if tag.startswith('sage_'):
+        return L.SAGEConv(F, H, aggr=tag[5:]), ()
+    if tag.startswith('gat_'):
+        return L.GATConv(F, 8, heads=int(tag.split('_')[1][1:]), concat=tag.endswith('cat')), ()
+    if tag == 'gin':
+        return L.GINConv(L.Linear(F, H), eps=0.25), ()
+    if tag == 'sgc':
+        return L.SGConv(F, H, iter_K=3), (w,)
+    return L.APPNPConv(F, H, iter_K=4, alpha=0.15, drop_rate=0.5), (w,)
+
+
+def load(layer, tag):
+    for key in Z.files:
+        if key.startswith(tag + '_p_'):
+            obj, path = layer, key[len(tag) + 3:].split('__')
+            for a in path[:-1]:
+                obj = getattr(obj, a, None)
+            if obj is not None and hasattr(obj, path[-1]):
+                getattr(obj, path[-1]).data = torch.from_numpy(Z[key]).clone()
+    return layer.eval()
+
+
+def rel(a, b):
+    a, b = a.detach().double().numpy(), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize('fused', [True, False], ids=['fused', 'message+aggregate'])
+@pytest.mark.parametrize('tag', TAGS)
+def test_layer_mirror_reproduces_reference_layer(host, tag, fused):
+    layer, extra = build(tag)
+    layer = load(layer, tag)
+    layer.fused = fused
+    ei = torch.from_numpy(Z['ei'])
+    x = torch.from_numpy(Z['x']).requires_grad_(True)
+    out = layer(x, ei, *extra)
+    assert rel(out, Z[tag + '_out']) < 2e-5
+    out.backward(torch.from_numpy(Z[tag + '_gout']))
+    assert rel(x.grad, Z[tag + '_gx']) < 2e-5
+
+
+def test_routing_of_propagate(host):
+    """sum / mean fuse; max keeps message + segment_max unless fuse_max; a weight that needs grad is never dropped."""
+    calls = []
+    real = {k: getattr(mpops, k) for k in ('gspmm', 'bspmm', 'unsorted_segment_max', 'unsorted_segment_sum', 'unsorted_segment_mean')}
+    for k, f in real.items():
+        setattr(mpops, k, (lambda k, f: lambda *a, **kw: (calls.append(k), f(*a, **kw))[1])(k, f))
+    try:
+        mp = L.MessagePassing()
+        ei = torch.tensor([[0, 1, 2, 2, 3], [1, 2, 1, 0, 3]])
+        x = torch.arange(8, dtype=torch.float32).reshape(4, 2)
+        w = torch.rand(5)
+        for aggr, want in (('sum', 'gspmm'), ('mean', 'gspmm'), ('max', 'unsorted_segment_max')):
+            calls.clear()
+            mp.propagate(x, ei, aggr=aggr, edge_weight=w)
+            assert calls == [want], (aggr, calls)
+        mp.fuse_max = True
+        calls.clear(); mp.propagate(x, ei, aggr='max'); assert calls == ['gspmm']
+        mp.fuse_max = False
+        wg = w.clone().requires_grad_(True)
+        calls.clear(); out = mp.propagate(x, ei, edge_weight=wg); assert calls == ['bspmm']
+        out.sum().backward(); assert wg.grad is not None and float(wg.grad.abs().sum()) > 0
+        calls.clear(); mp.propagate(x, ei, edge_weight=wg, aggr='mean'); assert calls == ['unsorted_segment_mean']
+        with torch.no_grad():
+            calls.clear(); mp.propagate(x, ei, edge_weight=wg); assert calls == ['gspmm']
+        calls.clear(); mp.propagate(x, ei, num_nodes=6); assert calls == ['unsorted_segment_sum']      # bipartite: no fusion
+        # reference KAT (tests/layers/conv/test_message_passing.py:12-24)
+        assert mp.propagate(x, ei, aggr='sum').tolist() == [[4.0, 5.0], [4.0, 6.0], [2.0, 3.0], [6.0, 7.0]]
+        assert mp.propagate(x, ei, aggr='mean').tolist() == [[4.0, 5.0], [2.0, 3.0], [2.0, 3.0], [6.0, 7.0]]
+        assert mp.propagate(x, ei, aggr='max').tolist() == [[4.0, 5.0], [4.0, 5.0], [2.0, 3.0], [6.0, 7.0]]
+    finally:
+        for k, f in real.items():
+            setattr(mpops, k, f)
