@@ -141,3 +141,31 @@ def test_enable_rebinds_the_real_module_tree(ref):
         assert getattr(v, 'segment_softmax', None) is before[k], k
     assert 'message_aggregate' not in L['GCNConv'].__dict__
     assert sys.modules['gammagl.layers.conv.message_passing'].gspmm is not b200.gspmm
+
+
+def test_fused_branch_keeps_the_edge_weight_gradient_of_the_reference_layer(ref):
+    """SGConv forwards a user edge weight straight into propagate (sgc_conv.py:45-49); the reference layer's message * weight
+    is differentiable in it.  With the fused branch installed (one-head bspmm for sum) d out / d w must equal the stock one."""
+    G, L, plugin, tlx = ref
+    N, E, F, H = 90, 900, 8, 8
+    ei = G.graph(N, E, 3)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(N, F, generator=g)
+    w0 = torch.rand(ei.shape[1], generator=g)
+    gout = torch.randn(N, H, generator=g)
+
+    def grads():
+        m = L['SGConv'](F, H, iter_K=2)
+        w = w0.clone().requires_grad_(True)
+        xx = x.clone().requires_grad_(True)
+        out = m(xx, ei, w)
+        out.backward(gout)
+        return out.detach().numpy(), xx.grad.numpy(), w.grad.numpy()
+    o0, gx0, gw0 = grads()
+    L['SGConv'].message_aggregate = plugin._fused_message_aggregate
+    try:
+        o1, gx1, gw1 = grads()
+    finally:
+        del L['SGConv'].message_aggregate
+    assert float(np.abs(gw0).sum()) > 0
+    assert rel(o1, o0) < 1e-5 and rel(gx1, gx0) < 1e-5 and rel(gw1, gw0) < 1e-5
