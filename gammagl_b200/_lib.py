@@ -24,12 +24,12 @@ SIGNATURES = {
     'gglb200_set_l2_fetch_granularity': (_int, [_int, _c.POINTER(_int)]),
     'gglb200_csr_build_workspace_bytes': (_sz, [_i64, _i64]),
     'gglb200_csr_plan_ints': (_sz, [_i64]),
-    'gglb200_csr_build': (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gglb200_csr_build': (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gglb200_ind2ptr': (_int, [_vp, _i64, _i64, _vp, _vp]),
     'gglb200_ptr2ind': (_int, [_vp, _i64, _i64, _vp, _vp]),
     'gglb200_permute_rows': (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     'gglb200_sort_edges_workspace_bytes': (_sz, [_i64, _i64, _i64]),
-    'gglb200_sort_edges': (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gglb200_sort_edges': (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gglb200_unique_edges': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'gglb200_spmm_workspace_bytes': (_sz, [_i64, _i64, _int]),
     'gglb200_spmm_workspace_bytes_for_chunks': (_sz, [_i64, _i64, _int]),
@@ -37,6 +37,7 @@ SIGNATURES = {
                                 _vp, _sz, _vp]),
     'gglb200_spmm_csr_epilogue': (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _int, _i64, _i64, _i64, _i64, _int, _vp, _sz, _vp]),
     'gglb200_spmm_csr_peer': (_int, [_int, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _i64, _int, _vp, _sz, _vp]),
+    'gglb200_gather_rows_peer': (_int, [_vp, _i32, _vp, _vp, _i64, _i64, _vp]),
     'gglb200_scale_rows': (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
     'gglb200_degree_power': (_int, [_vp, _vp, _i64, _c.c_float, _vp]),
     'gglb200_segment_gather_bwd': (_int, [_int, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
@@ -78,7 +79,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.gglb200_abi_version() != 1:
+    if lib.gglb200_abi_version() != 2:
         raise GglError('libgglb200.so ABI version mismatch')
     _lib = lib
     return lib

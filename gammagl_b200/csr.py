@@ -8,7 +8,12 @@ col / csr2csc caches), reduced to what the aggregation path needs:
              (rows = source, col = destination) of one edge_index[2,E]
   caches     an LRU keyed on the *identity of the memory* (storage pointer, offset, shape, strides,
              tensor._version) that also holds a strong reference to the keyed tensor, so the address
-             cannot be recycled for different contents while the entry lives.
+             cannot be recycled for different contents while the entry lives.  `_version` is the ONLY
+             invalidation signal: writes through `.data`, DLPack aliases or raw CUDA kernels do not bump it --
+             call clear_caches() after such a write.  Tensors created under torch.inference_mode() have no
+             version counter and are never cached (the CSR is rebuilt per call).
+  streams    a Csr is built on the stream current at build time; use_on_current_stream() makes any other
+             stream wait for that build, and the long-row partials buffer is kept per stream.
 """
 import collections
 import ctypes
@@ -35,25 +40,35 @@ def require_cuda(t, name):
 
 class Csr:
     """rowptr[N+1] i32, col[E] i32 (or None), perm[E] i32, plan (long-row work list), has_long."""
-    __slots__ = ('rowptr', 'col', 'perm', 'plan', 'n_rows', 'E', 'has_long', 'n_chunks', 'device', '_ws')
+    __slots__ = ('rowptr', 'col', 'perm', 'plan', 'n_rows', 'E', 'has_long', 'n_chunks', 'device', '_ws', 'build_event')
 
     def workspace(self, K, reduce):
         """Partials buffer for split rows; empty when the graph has no row longer than LONG_ROW."""
         if not self.has_long:
             return None, 0
         need = _lib.load().gglb200_spmm_workspace_bytes_for_chunks(self.n_chunks, K, reduce)
-        ws = self._ws.get('buf')
+        key = torch.cuda.current_stream(self.device).cuda_stream       # one buffer per stream: concurrent streams never share partials
+        ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._ws['buf'] = ws
+            self._ws[key] = ws
         return ws, ws.numel()
 
     def degrees(self):
         return self.rowptr[1:] - self.rowptr[:-1]
 
+    def use_on_current_stream(self):
+        """Order the current stream after the build of this CSR (no-op cost when it is the build stream)."""
+        ev = getattr(self, 'build_event', None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
-def build_csr(key, other, n_rows):
-    """key/other: int64 [E] CUDA tensors (other may be None) -> Csr.  One host sync (long-row count)."""
+
+def build_csr(key, other, n_rows, n_other=None):
+    """key/other: int64 [E] CUDA tensors (other may be None) -> Csr.  One host sync (long-row count + range errors).
+    n_other: number of rows `other` may address (None: n_rows; < 0: unchecked, `other` carries an encoding).
+    Raises IndexError when a key is outside [0, n_rows) or an `other` id outside [0, n_other) -- the reference's CPU
+    operators raise as well (TORCH_CHECK_INDEX idx < N, cpu/segment_max_cpu.cpp:50); nothing is clamped silently."""
     lib = _lib.load()
     require_cuda(key, 'index')
     if key.dtype != torch.int64:
@@ -74,10 +89,17 @@ def build_csr(key, other, n_rows):
         c.plan = torch.empty(lib.gglb200_csr_plan_ints(E), dtype=torch.int32, device=dev)
         ws_bytes = lib.gglb200_csr_build_workspace_bytes(E, n_rows)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.gglb200_csr_build(_ptr(key), _ptr(other), E, n_rows, _ptr(c.rowptr), _ptr(c.col), _ptr(c.perm),
+        n_other = int(n_rows) if n_other is None else int(n_other)
+        _lib.check(lib.gglb200_csr_build(_ptr(key), _ptr(other), E, n_rows, n_other, _ptr(c.rowptr), _ptr(c.col), _ptr(c.perm),
                                          _ptr(c.plan), _ptr(ws), ws_bytes, _stream(dev)), 'csr_build')
-        c.n_chunks, n_long = (int(v) for v in c.plan[:2].tolist()) if E > _lib.LONG_ROW else (0, 0)
+        head = c.plan[:8].tolist()                                      # the one host sync of the build
+        if head[6] or head[7]:
+            raise IndexError('index out of range: %d row ids outside [0, %d), %d column ids outside [0, %d)'
+                             % (head[6], n_rows, head[7], n_other))
+        c.n_chunks, n_long = head[0], head[1]
         c.has_long = n_long > 0
+        c.build_event = torch.cuda.Event()
+        c.build_event.record(torch.cuda.current_stream(dev))
     return c
 
 
@@ -118,6 +140,9 @@ class _Lru:
                 t.dtype, t.device.index, extra)
 
     def get(self, t, extra, make):
+        if t.is_inference():
+            # inference tensors carry no version counter (t._version raises): build per call, never cache
+            return make()
         k = self.key_of(t, extra)
         hit = self.d.get(k)
         if hit is not None:

@@ -22,11 +22,24 @@ int set_error(int code, const char* fmt, ...) {
 
 int64_t plan_max_chunks_host(int64_t E) { return plan_max_chunks(E); }
 
+int sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 int tile_edges() {
   static int v = [] {
     const char* e = getenv("GGLB200_TILE_EDGES");
     int t = e ? atoi(e) : GGLB200_TILE_EDGES;
-    if (t < 64 || t > 8192 || (t & (t - 1))) t = GGLB200_TILE_EDGES;
+    // a tile must not exceed GGLB200_LONG_ROW: a long row has to be the LAST row its tile owns (it outruns the tile window)
+    if (t < 64 || t > GGLB200_LONG_ROW || (t & (t - 1))) t = GGLB200_TILE_EDGES;
     return t;
   }();
   return v;

@@ -12,7 +12,7 @@ namespace ggl {
 
 static int grid_for(int64_t n, int block = 256) {
   int64_t g = (n + block - 1) / block;
-  int64_t cap = (int64_t)kSMs * 32;
+  int64_t cap = (int64_t)sm_count() * 32;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
@@ -52,7 +52,7 @@ static void launch_gather_rows(const void* g, const int64_t* ids, void* gx, int6
   while (lpr < 32 && lpr < words) lpr <<= 1;
   const int64_t warps = (E * lpr + 127) / 128;  // 4 rows per group per iteration
   int64_t grid = (warps + 7) / 8;
-  const int64_t cap = (int64_t)kSMs * 32;
+  const int64_t cap = (int64_t)sm_count() * 32;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   const W* gp = (const W*)g;

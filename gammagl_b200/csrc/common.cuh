@@ -40,7 +40,7 @@ extern std::atomic<int64_t> g_launches;
       return ::ggl::set_error((int)e__, "%s: %s", #call, cudaGetErrorString(e__));     \
   } while (0)
 
-constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
+int sm_count();  // SMs of the current device (148 on B200: 2 dies x 74), queried once per device; api.cu
 
 // ---- plan layout (int32 array produced by gglb200_csr_build, consumed by the reduce kernels) --------
 //   [0] n_chunks  [1] n_long_rows  [2] max_chunks (capacity)  [3] max_long (capacity)

@@ -5,7 +5,10 @@
 // per-element binary-search kernels of gammagl/ops/sparse/cuda/convert.cu:41-60.
 //
 // Pipeline (all on `stream`, no host sync, caller-owned workspace):
-//   1. narrow:   key32[i] = (int32) key[i] (clamped to [0,N-1]),  id[i] = i
+//   1. narrow:   key32[i] = (int32) key[i],  id[i] = i; keys outside [0,N) are COUNTED in plan[6] (and folded to the
+//                ends of the sort domain so that nothing is ever dereferenced out of range); the caller reads plan[6..7]
+//                at its one host sync and raises -- the reference's CPU operators raise too (TORCH_CHECK_INDEX idx < N,
+//                cpu/segment_max_cpu.cpp:50)
 //   2. sort:     cub::DeviceRadixSort::SortPairs over ceil(log2 N) bits  -- LSD radix = STABLE, so
 //                inside a row edge ids stay ascending (the order of the reference's serial loops)
 //   3. rowptr:   boundary detection on the sorted keys (each thread fills the rowptr entries between
@@ -22,15 +25,18 @@ namespace ggl {
 // plan layout: see common.cuh
 
 __global__ void __launch_bounds__(256) narrow_keys_kernel(const int64_t* __restrict__ key, int32_t* __restrict__ key32,
-                                                          int32_t* __restrict__ id, int64_t E, int32_t n_minus_1) {
+                                                          int32_t* __restrict__ id, int64_t E, int32_t n_minus_1,
+                                                          int32_t* __restrict__ bad_keys) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int32_t bad = 0;
   for (; i < E; i += stride) {
     int64_t k = key[i];
-    k = k < 0 ? 0 : (k > n_minus_1 ? n_minus_1 : k);
+    if (k < 0 || k > n_minus_1) { ++bad; k = k < 0 ? 0 : n_minus_1; }
     key32[i] = (int32_t)k;
     id[i] = (int32_t)i;
   }
+  if (bad) atomicAdd(bad_keys, bad);  // error path only
 }
 
 // rowptr[r] = first sorted position whose key >= r.  Thread i (0..E) owns rows (key[i-1], key[i]].
@@ -46,10 +52,17 @@ __global__ void __launch_bounds__(256) rowptr_kernel(const int32_t* __restrict__
 }
 
 __global__ void __launch_bounds__(256) gather_col_kernel(const int64_t* __restrict__ other, const int32_t* __restrict__ perm,
-                                                         int32_t* __restrict__ col, int64_t E) {
+                                                         int32_t* __restrict__ col, int64_t E, int64_t n_other,
+                                                         int32_t* __restrict__ bad_other) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < E; i += stride) col[i] = (int32_t)other[perm[i]];
+  int32_t bad = 0;
+  for (; i < E; i += stride) {
+    int64_t c = other[perm[i]];
+    if (n_other >= 0 && (c < 0 || c >= n_other)) { ++bad; c = 0; }  // never hand an out-of-range row id to the gather kernels
+    col[i] = (int32_t)c;
+  }
+  if (bad) atomicAdd(bad_other, bad);  // error path only
 }
 
 __global__ void __launch_bounds__(256) plan_kernel(const int32_t* __restrict__ rowptr, int32_t* __restrict__ plan, int64_t N) {
@@ -159,7 +172,7 @@ static size_t cub_temp_bytes(int64_t E, int64_t N) {
 
 static int grid_for(int64_t n, int block = 256) {
   int64_t g = (n + block - 1) / block;
-  int64_t cap = (int64_t)kSMs * 32;
+  int64_t cap = (int64_t)sm_count() * 32;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
@@ -181,7 +194,7 @@ extern "C" size_t gglb200_csr_build_workspace_bytes(int64_t E, int64_t N) {
   return 3 * align256((size_t)E * 4) + align256(cub_temp_bytes(E > 0 ? E : 1, N)) + 256;
 }
 
-extern "C" int gglb200_csr_build(const int64_t* key, const int64_t* other, int64_t E, int64_t N,
+extern "C" int gglb200_csr_build(const int64_t* key, const int64_t* other, int64_t E, int64_t N, int64_t n_other,
                                  int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* plan,
                                  void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -214,7 +227,7 @@ extern "C" int gglb200_csr_build(const int64_t* key, const int64_t* other, int64
   size_t cub_bytes = workspace_bytes - 3 * eb;
 
   // ids start in `perm` (buffer 0) and ping-pong with id_b; whichever side the sort ends on is copied back
-  narrow_keys_kernel<<<grid_for(E), 256, 0, stream>>>(key, key_a, perm, E, (int32_t)(N - 1));
+  narrow_keys_kernel<<<grid_for(E), 256, 0, stream>>>(key, key_a, perm, E, (int32_t)(N - 1), plan + 6);
   GGL_LAUNCHED("narrow_keys");
 
   cub::DoubleBuffer<int32_t> dk(key_a, key_b), dv(perm, id_b);
@@ -226,7 +239,7 @@ extern "C" int gglb200_csr_build(const int64_t* key, const int64_t* other, int64
   rowptr_kernel<<<grid_for(E + 1), 256, 0, stream>>>(dk.Current(), rowptr, E, N);
   GGL_LAUNCHED("rowptr");
   if (col) {
-    gather_col_kernel<<<grid_for(E), 256, 0, stream>>>(other, perm, col, E);
+    gather_col_kernel<<<grid_for(E), 256, 0, stream>>>(other, perm, col, E, n_other, plan + 7);
     GGL_LAUNCHED("gather_col");
   }
   plan_kernel<<<grid_for(N), 256, 0, stream>>>(rowptr, plan, N);

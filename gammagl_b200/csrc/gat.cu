@@ -245,7 +245,7 @@ static bool softmax_fused_enabled() {  // env GGLB200_SOFTMAX=composed keeps the
 
 static int ew_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
-  const int64_t cap = (int64_t)kSMs * 16;
+  const int64_t cap = (int64_t)sm_count() * 16;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 

@@ -601,7 +601,7 @@ int softmax_stats(const int32_t* rowptr, const int32_t* perm, const int32_t* pla
   if (st) return st;
   GGL_LAUNCHED("softmax_stats");
   if (a.has_long) {
-    softmax_stats_finalize_kernel<<<kSMs * 2, 128, 0, stream>>>(plan, part, stat_m, stat_s, H, a.ws_chunks);
+    softmax_stats_finalize_kernel<<<sm_count() * 2, 128, 0, stream>>>(plan, part, stat_m, stat_s, H, a.ws_chunks);
     GGL_LAUNCHED("softmax_stats_finalize");
   }
   return GGL_OK;
@@ -671,7 +671,7 @@ int softmax_dot(const int32_t* rowptr, const int32_t* perm, const int32_t* plan,
   if (st) return st;
   GGL_LAUNCHED("softmax_dot");
   if (a.has_long) {
-    gat_sum_finalize_kernel<<<kSMs * 2, 256, 0, stream>>>(plan, part, H, H, dot, H, H, nullptr, 0, a.ws_chunks);
+    gat_sum_finalize_kernel<<<sm_count() * 2, 256, 0, stream>>>(plan, part, H, H, dot, H, H, nullptr, 0, a.ws_chunks);
     GGL_LAUNCHED("gat_sum_finalize");
   }
   return GGL_OK;
@@ -717,7 +717,7 @@ extern "C" int gglb200_gat_fwd(const int32_t* rowptr, const int32_t* col, const 
   GGL_GAT_DISPATCH(gat_fwd_kernel, d, s_dst, out, stat_m, stat_s, part);
   GGL_LAUNCHED("gat_fwd");
   if (a.has_long) {
-    gat_fwd_finalize_kernel<<<kSMs * 2, 256, 0, stream>>>(plan, part, out, stat_m, stat_s, d, a.ws_chunks);
+    gat_fwd_finalize_kernel<<<sm_count() * 2, 256, 0, stream>>>(plan, part, out, stat_m, stat_s, d, a.ws_chunks);
     GGL_LAUNCHED("gat_fwd_finalize");
   }
   return GGL_OK;
@@ -743,7 +743,7 @@ extern "C" int gglb200_gat_bwd_src(const int32_t* rowptr_t, const int32_t* col_t
   GGL_GAT_DISPATCH(gat_bwd_src_kernel, d, xcat, xcat_stride, gx, gs_src, part);
   GGL_LAUNCHED("gat_bwd_src");
   if (a.has_long) {
-    gat_sum_finalize_kernel<<<kSMs * 2, 256, 0, stream>>>(plan_t, part, d.K + H, d.W, gx, d.K, d.K, gs_src, H, a.ws_chunks);
+    gat_sum_finalize_kernel<<<sm_count() * 2, 256, 0, stream>>>(plan_t, part, d.K + H, d.W, gx, d.K, d.K, gs_src, H, a.ws_chunks);
     GGL_LAUNCHED("gat_sum_finalize");
   }
   return GGL_OK;
@@ -769,7 +769,7 @@ extern "C" int gglb200_gat_bwd_dst(const int32_t* rowptr, const int32_t* col, co
   GGL_GAT_DISPATCH(gat_bwd_dst_kernel, d, gcat, gcat_stride, gs_dst, part);
   GGL_LAUNCHED("gat_bwd_dst");
   if (a.has_long) {
-    gat_sum_finalize_kernel<<<kSMs * 2, 256, 0, stream>>>(plan, part, H, d.W, gs_dst, H, H, nullptr, 0, a.ws_chunks);
+    gat_sum_finalize_kernel<<<sm_count() * 2, 256, 0, stream>>>(plan, part, H, d.W, gs_dst, H, H, nullptr, 0, a.ws_chunks);
     GGL_LAUNCHED("gat_sum_finalize");
   }
   return GGL_OK;

@@ -26,7 +26,7 @@ static int bits_for(int64_t n) {  // smallest b >= 1 with 2^b >= n
 
 static int grid_for(int64_t n, int block = 256) {
   int64_t g = (n + block - 1) / block;
-  const int64_t cap = (int64_t)kSMs * 32;
+  const int64_t cap = (int64_t)sm_count() * 32;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
@@ -36,16 +36,20 @@ static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 __global__ void __launch_bounds__(256) pack_pairs_kernel(const int64_t* __restrict__ major, const int64_t* __restrict__ minor,
                                                          uint64_t* __restrict__ key, int32_t* __restrict__ id, int64_t E,
-                                                         int64_t major_max, int64_t minor_max, int minor_bits) {
+                                                         int64_t major_max, int64_t minor_max, int minor_bits,
+                                                         int64_t* __restrict__ n_bad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
   for (; i < E; i += stride) {
     int64_t a = __ldcs(major + i), b = __ldcs(minor + i);
-    a = a < 0 ? 0 : (a > major_max ? major_max : a);  // ids outside [0, n) are a caller error; clamped to stay in the key width
-    b = b < 0 ? 0 : (b > minor_max ? minor_max : b);
+    // ids outside [0, n) are a caller error: counted in *n_bad (the caller raises) and folded to stay in the key width
+    if (a < 0 || a > major_max) { ++bad; a = a < 0 ? 0 : major_max; }
+    if (b < 0 || b > minor_max) { ++bad; b = b < 0 ? 0 : minor_max; }
     key[i] = ((uint64_t)a << minor_bits) | (uint64_t)b;
     id[i] = (int32_t)i;
   }
+  if (bad && n_bad) atomicAdd(reinterpret_cast<unsigned long long*>(n_bad), bad);  // error path only
 }
 
 __global__ void __launch_bounds__(256) unpack_pairs_kernel(const uint64_t* __restrict__ key, int64_t* __restrict__ major,
@@ -116,10 +120,11 @@ extern "C" size_t gglb200_sort_edges_workspace_bytes(int64_t E, int64_t n_major,
 
 extern "C" int gglb200_sort_edges(const int64_t* major, const int64_t* minor, int64_t E, int64_t n_major, int64_t n_minor,
                                   int64_t* sorted_major, int64_t* sorted_minor, int32_t* perm, int64_t* group,
-                                  int64_t* n_unique, void* workspace, size_t workspace_bytes, void* stream_) {
+                                  int64_t* n_unique, int64_t* n_bad, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GGL_REQUIRE(E >= 0 && n_major >= 0 && n_minor >= 0, GGL_EINVAL, "sort_edges: negative size");
   GGL_REQUIRE(E < INT32_MAX && n_major < INT32_MAX && n_minor < INT32_MAX, GGL_ERANGE, "sort_edges: E / n exceed int32");
+  if (n_bad) GGL_CUDA(cudaMemsetAsync(n_bad, 0, sizeof(int64_t), stream));
   if (E == 0) {
     if (n_unique) GGL_CUDA(cudaMemsetAsync(n_unique, 0, sizeof(int64_t), stream));
     return GGL_OK;
@@ -139,7 +144,7 @@ extern "C" int gglb200_sort_edges(const int64_t* major, const int64_t* minor, in
   void* cub_ws = ws + 2 * kb + 2 * ib;
   size_t cub_bytes = workspace_bytes - (2 * kb + 2 * ib);
 
-  pack_pairs_kernel<<<grid_for(E), 256, 0, stream>>>(major, minor, key_a, perm, E, n_major - 1, n_minor - 1, minor_bits);
+  pack_pairs_kernel<<<grid_for(E), 256, 0, stream>>>(major, minor, key_a, perm, E, n_major - 1, n_minor - 1, minor_bits, n_bad);
   GGL_LAUNCHED("pack_pairs");
   cub::DoubleBuffer<uint64_t> dk(key_a, key_b);
   cub::DoubleBuffer<int32_t> dv(perm, id_b);

@@ -712,7 +712,7 @@ int launch_ring(const SpmmArgs& p, int tiles) {
   spmm_ring_kernel<T, VEC, LPR, WMODE, ISMAX><<<dim3((unsigned)blocks, tiles), 32, smem, p.stream>>>(q, pitch, x_end_al, stages);
   GGL_LAUNCHED("spmm_ring");
   if (p.has_long) {
-    spmm_finalize_kernel<T, VEC, LPR, ISMAX><<<dim3(kSMs, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(q);
+    spmm_finalize_kernel<T, VEC, LPR, ISMAX><<<dim3(sm_count(), tiles), kWarpsPerBlock * 32, 0, p.stream>>>(q);
     GGL_LAUNCHED("spmm_finalize");
   }
   return GGL_OK;
@@ -745,9 +745,9 @@ int launch_config(const SpmmArgs& p) {
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, spmm_chunks_kernel<T, VEC, LPR, WMODE, ISMAX>, kWarpsPerBlock * 32, 0) != cudaSuccess || o < 1) o = 2;
       occ_chunks = o;
     }
-    spmm_chunks_kernel<T, VEC, LPR, WMODE, ISMAX><<<dim3(kSMs * occ_chunks, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(p);
+    spmm_chunks_kernel<T, VEC, LPR, WMODE, ISMAX><<<dim3(sm_count() * occ_chunks, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(p);
     GGL_LAUNCHED("spmm_chunks");
-    spmm_finalize_kernel<T, VEC, LPR, ISMAX><<<dim3(kSMs, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(p);
+    spmm_finalize_kernel<T, VEC, LPR, ISMAX><<<dim3(sm_count(), tiles), kWarpsPerBlock * 32, 0, p.stream>>>(p);
     GGL_LAUNCHED("spmm_finalize");
   }
   return GGL_OK;

@@ -52,6 +52,7 @@ def spmm_csr(csr, col, x2d, reduce, w=None, wperm=None, heads=1, want_arg=False,
     dev = x2d.device
     with torch.cuda.device(dev):
         _lib.tune_device(dev.index)
+        csr.use_on_current_stream()        # a CSR built on another stream: order this stream after its build
         out = torch.empty((n_rows, K), dtype=x2d.dtype, device=dev)
         arg = torch.empty((n_rows, K), dtype=torch.int64, device=dev) if want_arg else None
         ws, ws_bytes = csr.workspace(K, reduce)

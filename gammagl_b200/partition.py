@@ -109,8 +109,8 @@ class HaloPlan:
     def csr(self):
         if self._csr is None:
             from .csr import build_csr
-            fwd = build_csr(self.edge_index_ext[1], self.edge_index_ext[0], self.n_local)
-            bwd = build_csr(self.edge_index_ext[0], self.edge_index_ext[1], self.n_src)
+            fwd = build_csr(self.edge_index_ext[1], self.edge_index_ext[0], self.n_local, n_other=self.n_src)
+            bwd = build_csr(self.edge_index_ext[0], self.edge_index_ext[1], self.n_src, n_other=self.n_local)
             self._csr = (fwd, bwd)
         return self._csr
 
@@ -184,9 +184,17 @@ class PeerGraph:
 
     Forward uses the in-edges of the owned nodes (rows = local dst, col = encoded global src); backward uses their
     out-edges (rows = local src, col = encoded global dst), obtained once at plan time by an all-to-all of the
-    edge list -- so the backward pass is a pull as well and needs no scatter / reduction across GPUs."""
+    edge list -- so the backward pass is a pull as well and needs no scatter / reduction across GPUs.
 
-    def __init__(self, edge_index_local, N, group=None):
+    Halo cache (`cache_rows`): a remote row that at least two local edges reference is pulled ONCE per pass into a
+    cache region behind the rank's own shard (gglb200_gather_rows_peer: remote reads, no pack on the owner, no
+    collective) and the aggregation kernel finds it in local HBM -- `col` of those edges is rewritten to
+    owner = self, row = B + slot.  Rows referenced once keep their direct peer address.  NVLink bytes per pass drop
+    from (remote edges) x row to (distinct remote rows) x row; the per-row edge order, hence the result bits, do not
+    change.  cache_rows: None = every remote row referenced >= 2 times (env GGLB200_PEER_CACHE_ROWS caps it; 0 = off)."""
+
+    def __init__(self, edge_index_local, N, group=None, cache_rows=None):
+        import os
         from .csr import build_csr
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -199,8 +207,17 @@ class PeerGraph:
         self.n_local = self.hi - self.lo
         src, dst = edge_index_local[0], edge_index_local[1]
         dev = src.device
+        self.device = dev
         self.E = int(src.numel())
-        self.fwd = build_csr(dst - self.lo, _encode(src, self.B), self.n_local)
+        if self.E and (int(src.min()) < 0 or int(src.max()) >= self.N):
+            raise IndexError('PeerGraph: source ids outside [0, %d)' % self.N)
+        if cache_rows is None:
+            env = os.environ.get('GGLB200_PEER_CACHE_ROWS')
+            cache_rows = int(env) if env is not None else (1 << OWNER_SHIFT) - self.B - 1
+        cache_rows = max(0, min(int(cache_rows), (1 << OWNER_SHIFT) - self.B - 1))
+        col_f, self.cache_fwd, self.stats_fwd = self._with_cache(_encode(src, self.B), cache_rows)
+        self.fwd = build_csr(dst - self.lo, col_f, self.n_local, n_other=-1)   # col = owner << 27 | row (validated above)
+        del col_f
         # out-edges of the owned nodes: bucket the local edge list by the owner of its source and exchange
         owner = torch.div(src, self.B, rounding_mode='floor')
         order = torch.argsort(owner, stable=True)
@@ -210,22 +227,69 @@ class PeerGraph:
         send_counts = [int(c) for c in counts.tolist()]
         recv_counts = [int(c) for c in cnt_out.tolist()]
         pairs = torch.stack([src[order], dst[order]], dim=1).contiguous()          # [E, 2]
+        del owner, order
         got = pairs.new_empty((sum(recv_counts), 2))
         _all_to_all(got, pairs, recv_counts, send_counts, self.group)
+        del pairs
         self.E_out = int(got.shape[0])
-        self.bwd = build_csr(got[:, 0] - self.lo, _encode(got[:, 1], self.B), self.n_local)
-        self.device = dev
+        col_b, self.cache_bwd, self.stats_bwd = self._with_cache(_encode(got[:, 1], self.B), cache_rows)
+        self.bwd = build_csr(got[:, 0] - self.lo, col_b, self.n_local, n_other=-1)
+        del col_b, got
+        # symmetric buffers hold [B shard rows | cache rows]; every rank allocates the same (maximal) cache capacity
+        cap = torch.tensor([self.cache_fwd.numel(), self.cache_bwd.numel()], dtype=torch.int64, device=dev)
+        if self.world > 1:
+            if dist.get_backend(self.group) == 'nccl':
+                dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
+            else:
+                c = cap.cpu()
+                dist.all_reduce(c, op=dist.ReduceOp.MAX, group=self.group)
+                cap = c
+        self.cache_cap = {'x': int(cap[0]), 'g': int(cap[1])}
         self._bufs = {}
 
+    def _with_cache(self, enc, cache_rows):
+        """enc: encoded (owner << shift | row) source ids of the local edges.  Returns (col, cache_ids int32 sorted, stats):
+        col = enc with every cached remote id replaced by (rank << shift | B + slot)."""
+        remote = (enc >> OWNER_SHIFT) != self.rank
+        n_remote = int(remote.sum())
+        stats = {'edges': int(enc.numel()), 'remote_edges': n_remote, 'cached_rows': 0, 'cached_edges': 0,
+                 'direct_remote_edges': n_remote}
+        empty = torch.empty(0, dtype=torch.int32, device=enc.device)
+        if cache_rows <= 0 or n_remote == 0:
+            return enc, empty, stats
+        uniq, cnt = torch.unique(enc[remote], return_counts=True)                # sorted ascending = by (owner, row)
+        keep = cnt >= 2
+        if int(keep.sum()) > cache_rows:                                          # over capacity: keep the hottest rows
+            thr = torch.topk(cnt, cache_rows).values[-1]
+            keep = cnt > thr
+            room = cache_rows - int(keep.sum())
+            if room > 0:
+                ties = torch.nonzero(cnt == thr).view(-1)[:room]
+                keep[ties] = True
+        cached = uniq[keep]
+        if cached.numel() == 0:
+            return enc, empty, stats
+        pos = torch.searchsorted(cached, enc).clamp_(max=cached.numel() - 1)
+        hit = remote & (cached[pos] == enc)
+        col = torch.where(hit, (self.rank << OWNER_SHIFT) | (self.B + pos), enc)
+        stats.update(cached_rows=int(cached.numel()), cached_edges=int(hit.sum()),
+                     direct_remote_edges=n_remote - int(hit.sum()))
+        return col, cached.to(torch.int32).contiguous(), stats
+
     def _symm(self, tag, K, dtype):
-        """Symmetric [B, K] buffer + handle (allocated once per (tag, K, dtype); collective call)."""
+        """Symmetric [B + cache capacity, K] buffer + handle (allocated once per (tag, K, dtype); collective call)."""
         import torch.distributed._symmetric_memory as symm
         key = (tag, K, dtype)
         if key not in self._bufs:
-            t = symm.empty((self.B, K), dtype=dtype, device=self.device)
+            t = symm.empty((self.B + self.cache_cap[tag], K), dtype=dtype, device=self.device)
             hdl = symm.rendezvous(t, self.group)
             self._bufs[key] = (t, hdl)
         return self._bufs[key]
+
+    def nvlink_bytes_per_pass(self, K, elem_size, tag='x'):
+        """Bytes this rank pulls over NVLink in one pass: one row per cached row + one per uncached remote edge."""
+        st = self.stats_fwd if tag == 'x' else self.stats_bwd
+        return (st['cached_rows'] + st['direct_remote_edges']) * K * elem_size
 
     def _pull(self, csr, tag, x_local, in_scale, out_scale):
         from . import _lib, mpops
@@ -233,6 +297,7 @@ class PeerGraph:
         lib = _lib.load()
         K = x_local.shape[1]
         buf, hdl = self._symm(tag, K, x_local.dtype)
+        cache_ids = self.cache_fwd if tag == 'x' else self.cache_bwd
         dev = x_local.device
         with torch.cuda.device(dev):
             _lib.tune_device(dev.index)
@@ -248,8 +313,12 @@ class PeerGraph:
             if mpops.PROFILE is not None:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev0.record()
+            table = ctypes_ptr(hdl.buffer_ptrs_dev)
+            if cache_ids.numel():                        # deduplicated halo: one NVLink read per cached row
+                _lib.check(lib.gglb200_gather_rows_peer(table, OWNER_SHIFT, _ptr(cache_ids), _ptr(buf[self.B:]), cache_ids.numel(),
+                                                        K * x_local.element_size(), _stream(dev)), 'gather_rows_peer')
             _lib.check(lib.gglb200_spmm_csr_peer(_lib.GGL_SUM, _ptr(csr.rowptr), _ptr(csr.col), _ptr(csr.plan), None, None, 1,
-                                                 ctypes_ptr(hdl.buffer_ptrs_dev), OWNER_SHIFT, _ptr(out), _ptr(out_scale),
+                                                 table, OWNER_SHIFT, _ptr(out), _ptr(out_scale),
                                                  self.n_local, csr.E, K, mpops._dtype_code(x_local), _ptr(ws), nb, _stream(dev)),
                        'spmm_csr_peer')
             if mpops.PROFILE is not None:

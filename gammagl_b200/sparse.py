@@ -106,7 +106,7 @@ class SparseGraph(object):
     @staticmethod
     def _sorted_csr(major, minor, n_major, n_minor):
         sm, sn, perm, _, _ = utils.sort_pairs(major, minor, n_major, n_minor)   # by (major, minor), stable
-        c = build_csr(sm, sn, n_major)           # input already in order: the stable row sort keeps it (its perm is the identity)
+        c = build_csr(sm, sn, n_major, n_other=n_minor)   # input already in order: the stable row sort keeps it (its perm is the identity)
         c.perm = perm                            # sorted position -> input element
         return c
 

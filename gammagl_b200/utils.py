@@ -41,10 +41,14 @@ def sort_pairs(major, minor, n_major, n_minor, want_sorted=True, want_groups=Fal
         perm = torch.empty(E, dtype=torch.int32, device=dev)
         group = torch.empty(E, dtype=torch.int64, device=dev) if want_groups else None
         n_unique = torch.zeros(1, dtype=torch.int64, device=dev) if want_groups else None
+        n_bad = torch.empty(1, dtype=torch.int64, device=dev)
         ws_bytes = lib.gglb200_sort_edges_workspace_bytes(E, n_major, n_minor)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(lib.gglb200_sort_edges(_ptr(major), _ptr(minor), E, int(n_major), int(n_minor), _ptr(sm), _ptr(sn), _ptr(perm),
-                                          _ptr(group), _ptr(n_unique), _ptr(ws), ws_bytes, _stream(dev)), 'sort_edges')
+                                          _ptr(group), _ptr(n_unique), _ptr(n_bad), _ptr(ws), ws_bytes, _stream(dev)), 'sort_edges')
+        bad = int(n_bad.item())                                # host sync: range errors are raised, never returned as data
+        if bad:
+            raise IndexError('sort_pairs: %d ids outside [0, %d) x [0, %d)' % (bad, int(n_major), int(n_minor)))
     return sm, sn, perm, group, n_unique
 
 

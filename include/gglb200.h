@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GGLB200_ABI_VERSION 1
+#define GGLB200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GGL_API __attribute__((visibility("default")))
@@ -97,12 +97,15 @@ GGL_API int gglb200_set_l2_fetch_granularity(int bytes, int* previous);
  *   col   [E] int32 out       other[perm[i]]           (may be NULL)
  *   perm  [E] int32 out       original edge id of the i-th sorted edge (stable: ascending inside a row)
  *   plan  [gglb200_csr_plan_ints(E)] int32 out   long-row work list consumed by the reduce kernels
- *   Keys outside [0,N) are a caller error (the reference leaves them unchecked as well,
- *   cpu/segment_sum_cpu.cpp:47-56); they are clamped into the sort domain and never dereferenced.
+ *   n_other  number of rows `col` may address (x.shape[0]); < 0 = unchecked (col carries an encoding, e.g. peer ids)
+ *   Range errors are never silent: keys outside [0,N) are COUNTED in plan[6], `other` ids outside [0,n_other) in
+ *   plan[7] (and folded to a valid id so that no kernel dereferences them).  The caller reads plan[0..7] after the
+ *   build -- the one host sync it needs anyway for plan[0] -- and raises when either count is non-zero, like the
+ *   reference's CPU operators do (TORCH_CHECK_INDEX idx < N, cpu/segment_max_cpu.cpp:50).
  * ------------------------------------------------------------------------------------------- */
 GGL_API size_t gglb200_csr_build_workspace_bytes(int64_t E, int64_t N);
 GGL_API size_t gglb200_csr_plan_ints(int64_t E);
-GGL_API int    gglb200_csr_build(const int64_t* key, const int64_t* other, int64_t E, int64_t N,
+GGL_API int    gglb200_csr_build(const int64_t* key, const int64_t* other, int64_t E, int64_t N, int64_t n_other,
                          int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* plan,
                          void* workspace, size_t workspace_bytes, void* stream);
 
@@ -122,12 +125,14 @@ GGL_API int gglb200_ptr2ind(const int64_t* ptr, int64_t M, int64_t E, int64_t* i
  *   group         int64 [E] out or NULL: rank of the distinct pair held by each sorted position (0-based,
  *                 non-decreasing) -- the segment ids coalesce() sums duplicate attributes over (coalesce.py:73-76)
  *   n_unique      device int64 scalar out or NULL: number of distinct pairs
+ *   n_bad         device int64 scalar out or NULL: number of ids outside [0, n_major) / [0, n_minor) -- a caller error
+ *                 the host side raises on (such ids are folded into the key width, never returned silently)
  * gglb200_unique_edges keeps the first pair of every group: uniq[group[p]] = sorted[p]  (coalesce.py:69).
  * ------------------------------------------------------------------------------------------- */
 GGL_API size_t gglb200_sort_edges_workspace_bytes(int64_t E, int64_t n_major, int64_t n_minor);
 GGL_API int gglb200_sort_edges(const int64_t* major, const int64_t* minor, int64_t E, int64_t n_major, int64_t n_minor,
                        int64_t* sorted_major, int64_t* sorted_minor, int32_t* perm, int64_t* group,
-                       int64_t* n_unique, void* workspace, size_t workspace_bytes, void* stream);
+                       int64_t* n_unique, int64_t* n_bad, void* workspace, size_t workspace_bytes, void* stream);
 GGL_API int gglb200_unique_edges(const int64_t* sorted_major, const int64_t* sorted_minor, const int64_t* group, int64_t E,
                          int64_t* uniq_major, int64_t* uniq_minor, void* stream);
 
@@ -195,6 +200,13 @@ GGL_API int gglb200_spmm_csr_peer(int reduce, const int32_t* rowptr, const int32
                           const float* w, const int32_t* wperm, int32_t heads, const void* const* x_table,
                           int32_t owner_shift, void* out, const float* out_scale, int64_t n_rows, int64_t E,
                           int64_t K, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Halo-cache fill of the 1-D node partition: dst[i, :] = x_table[ids[i] >> owner_shift][(ids[i] & mask), :] for i < n
+ * (row_bytes per row, a multiple of 16).  Rows that several local edges reference are pulled over NVLink ONCE per pass
+ * into a cache region behind the rank's own shard (remote reads: no pack on the owner, no all-to-all); `col` of those
+ * edges then addresses owner = self, row = B + slot, and gglb200_spmm_csr_peer finds them in local HBM. */
+GGL_API int gglb200_gather_rows_peer(const void* const* x_table, int32_t owner_shift, const int32_t* ids, void* dst,
+                             int64_t n, int64_t row_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Backward helpers of the segment ops (src/segment_sum.cpp:43-54, src/segment_mean.cpp:44-63,

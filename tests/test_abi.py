@@ -33,7 +33,7 @@ def test_exports_nothing_else():
 
 def test_version_and_sizes():
     lib = _lib.load()
-    assert lib.gglb200_abi_version() == 1
+    assert lib.gglb200_abi_version() == 2
     assert lib.gglb200_csr_plan_ints(0) >= 4
     assert lib.gglb200_csr_build_workspace_bytes(1000, 10) >= 3 * 4000
     assert lib.gglb200_spmm_workspace_bytes(100, 16, 0) == 0          # no row can be long
@@ -44,9 +44,9 @@ def test_argument_validation_without_gpu():
     lib = _lib.load()
     st = lib.gglb200_spmm_csr(7, None, None, None, None, None, 1, None, None, None, 0, None, 4, 4, 4, 4, 0, None, 0, None)
     assert st == -1 and b'unknown reduce' in lib.gglb200_last_error()
-    st = lib.gglb200_csr_build(None, None, -1, 4, None, None, None, None, None, 0, None)
+    st = lib.gglb200_csr_build(None, None, -1, 4, 4, None, None, None, None, None, 0, None)
     assert st == -1
-    st = lib.gglb200_csr_build(None, None, 1 << 31, 4, None, None, None, None, None, 0, None)
+    st = lib.gglb200_csr_build(None, None, 1 << 31, 4, 4, None, None, None, None, None, 0, None)
     assert st == -4
     st = lib.gglb200_spmm_csr(0, None, None, None, None, None, 1, None, None, None, 0, None, 4, 4, 4, 4, 99, None, 0, None)
     assert st == -1  # NULL rowptr is caught before the dtype switch
@@ -75,11 +75,11 @@ def test_new_entry_points_validate_without_gpu():
     lib = _lib.load()
     assert lib.gglb200_sort_edges_workspace_bytes(1000, 50, 50) >= 2 * 8000 + 2 * 4000
     assert lib.gglb200_sort_edges_workspace_bytes(0, 0, 0) > 0
-    st = lib.gglb200_sort_edges(None, None, -1, 4, 4, None, None, None, None, None, None, 0, None)
+    st = lib.gglb200_sort_edges(None, None, -1, 4, 4, None, None, None, None, None, None, None, 0, None)
     assert st == -1 and b'negative' in lib.gglb200_last_error()
-    st = lib.gglb200_sort_edges(None, None, 5, 4, 4, None, None, None, None, None, None, 0, None)
+    st = lib.gglb200_sort_edges(None, None, 5, 4, 4, None, None, None, None, None, None, None, 0, None)
     assert st == -1 and b'must not be NULL' in lib.gglb200_last_error()
-    st = lib.gglb200_sort_edges(None, None, 1 << 31, 4, 4, None, None, None, None, None, None, 0, None)
+    st = lib.gglb200_sort_edges(None, None, 1 << 31, 4, 4, None, None, None, None, None, None, None, 0, None)
     assert st == -4
     assert lib.gglb200_unique_edges(None, None, None, 0, None, None, None) == 0          # nothing to do
     assert lib.gglb200_unique_edges(None, None, None, 3, None, None, None) == -1

@@ -1,0 +1,104 @@
+"""GPU tests of the error and caching behaviour around the kernels (round-1 advisor findings):
+  * ids outside their range raise IndexError (the reference's CPU operators raise as well: TORCH_CHECK_INDEX idx < N,
+    /root/reference/gammagl/mpops/torch_ext/cpu/segment_max_cpu.cpp:50) -- nothing is clamped silently;
+  * index tensors created under torch.inference_mode() work (no version counter: never cached);
+  * two CUDA streams aggregating over the same cached graph do not share the long-row partials buffer;
+  * GGLB200_TILE_EDGES above GGLB200_LONG_ROW is refused (a long row must be the last row of its tile)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def mp():
+    from gammagl_b200 import _lib, mpops
+    _lib.load()
+    return mpops
+
+
+def test_out_of_range_ids_raise(mp):
+    from gammagl_b200 import utils
+    from gammagl_b200.csr import clear_caches
+    g = torch.Generator().manual_seed(0)
+    N, E, K = 50, 400, 8
+    x = torch.randn(E, K, generator=g).to(DEV)
+    ids = torch.randint(0, N, (E,), generator=g).to(DEV)
+    bad = ids.clone()
+    bad[17] = N                                    # one past the end
+    with pytest.raises(IndexError):
+        mp.unsorted_segment_sum(x, bad, N)
+    neg = ids.clone()
+    neg[3] = -1
+    with pytest.raises(IndexError):
+        mp.unsorted_segment_max(x, neg, N)
+    ei = torch.randint(0, N, (2, E), generator=g).to(DEV)
+    xs = torch.randn(N, K, generator=g).to(DEV)
+    w = torch.rand(E, generator=g).to(DEV)
+    e2 = ei.clone()
+    e2[0, 5] = N + 3                               # bad SOURCE id: would be an out-of-bounds gather
+    with pytest.raises(IndexError):
+        mp.gspmm(e2, w, xs, 'sum')
+    e3 = ei.clone()
+    e3[1, 5] = N                                   # bad destination id
+    with pytest.raises(IndexError):
+        mp.gspmm(e3, w, xs, 'sum')
+    with pytest.raises(IndexError):
+        utils.sort_edge_index(e2, num_nodes=N)
+    with pytest.raises(IndexError):
+        utils.coalesce(e3, num_nodes=N)
+    clear_caches()
+    out = mp.gspmm(ei, w, xs, 'sum')               # the library is still usable after the errors
+    ref, _ = O.spmm_fwd('sum', ei.cpu().numpy(), w.cpu().numpy(), xs.cpu().numpy())
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_inference_mode_index_tensors(mp):
+    g = torch.Generator().manual_seed(1)
+    N, E, K = 300, 5000, 16
+    ei_c = torch.randint(0, N, (2, E), generator=g)
+    x_c = torch.randn(N, K, generator=g)
+    w_c = torch.rand(E, generator=g)
+    ref, _ = O.spmm_fwd('sum', ei_c.numpy(), w_c.numpy(), x_c.numpy())
+    with torch.inference_mode():
+        ei = ei_c.to(DEV)                          # an inference tensor: ei._version raises
+        assert ei.is_inference()
+        out = mp.gspmm(ei, w_c.to(DEV), x_c.to(DEV), 'sum')
+        seg = mp.unsorted_segment_sum(x_c.to(DEV)[ei[0]], ei[1], N)
+        deg = mp.unsorted_segment_sum(torch.ones(E, device=DEV), ei[1], N)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    r2 = O.segment('sum', x_c.numpy()[ei_c[0].numpy()], ei_c[1].numpy(), N)
+    assert np.array_equal(seg.cpu().numpy(), r2)
+    assert np.array_equal(deg.cpu().numpy(), np.bincount(ei_c[1].numpy(), minlength=N).astype(np.float32))
+
+
+def test_two_streams_share_a_cached_graph(mp):
+    """Both streams reduce a graph with a split row (> 1024 edges): each must use its own partials buffer."""
+    g = torch.Generator().manual_seed(2)
+    N, E, K = 200, 30000, 64
+    ei = torch.randint(0, N, (2, E), generator=g)
+    ei[1, :6000] = 7
+    xa, xb = torch.randn(N, K, generator=g), torch.randn(N, K, generator=g)
+    w = torch.rand(E, generator=g)
+    eid, wd, xad, xbd = ei.to(DEV), w.to(DEV), xa.to(DEV), xb.to(DEV)
+    mp.gspmm(eid, wd, xad, 'sum')                  # builds + caches the CSR on the default stream
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(20):
+        with torch.cuda.stream(s1):
+            oa = mp.gspmm(eid, wd, xad, 'sum')
+        with torch.cuda.stream(s2):
+            ob = mp.gspmm(eid, wd, xbd, 'sum')
+        outs.append((oa, ob))
+    torch.cuda.synchronize()
+    ra, _ = O.spmm_fwd('sum', ei.numpy(), w.numpy(), xa.numpy())
+    rb, _ = O.spmm_fwd('sum', ei.numpy(), w.numpy(), xb.numpy())
+    for oa, ob in outs:
+        assert np.max(np.abs(oa.cpu().numpy() - ra)) <= 1e-5 * np.max(np.abs(ra))
+        assert np.max(np.abs(ob.cpu().numpy() - rb)) <= 1e-5 * np.max(np.abs(rb))
+        assert torch.equal(oa, outs[0][0]) and torch.equal(ob, outs[0][1])     # deterministic, no cross-talk

@@ -96,3 +96,37 @@ def test_owned_ranges_cover_all_nodes():
             spans = [P.owned_range(N, world, r) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == N
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_peer_halo_cache_remap_is_consistent():
+    """PeerGraph._with_cache (host logic, no GPU): remote ids referenced >= 2 times move to the cache region of the own
+    shard (owner = self, row = B + slot); decoding the rewritten col through the cache id list gives back the original ids."""
+    from gammagl_b200 import partition as P
+    g = torch.Generator().manual_seed(3)
+    world, rank, B = 4, 1, 1000
+    src = torch.randint(0, world * B, (20000,), generator=g)
+    src[:3000] = torch.randint(0, 5, (3000,), generator=g)             # hub rows owned by rank 0
+    enc = P._encode(src, B)
+    pg = object.__new__(P.PeerGraph)
+    pg.rank, pg.B = rank, B
+    for cap in (0, 7, 10 ** 6):
+        col, cache_ids, st = pg._with_cache(enc, cap)
+        assert st['edges'] == enc.numel() and st['cached_rows'] == cache_ids.numel() <= cap
+        owner, row = col >> P.OWNER_SHIFT, col & ((1 << P.OWNER_SHIFT) - 1)
+        in_cache = (owner == rank) & (row >= B)
+        assert int(in_cache.sum()) == st['cached_edges']
+        assert st['direct_remote_edges'] == st['remote_edges'] - st['cached_edges']
+        decoded = col.clone()
+        if cache_ids.numel():
+            assert bool((cache_ids[1:] > cache_ids[:-1]).all())        # sorted by (owner, row), distinct
+            decoded[in_cache] = cache_ids.to(torch.int64)[row[in_cache] - B]
+        assert torch.equal(decoded, enc)
+        if cap >= 10 ** 6:                                             # unlimited: exactly the remote ids seen at least twice
+            remote = (enc >> P.OWNER_SHIFT) != rank
+            u, c = torch.unique(enc[remote], return_counts=True)
+            assert torch.equal(cache_ids.to(torch.int64), u[c >= 2])
+        if cap == 7 and cache_ids.numel():                             # capped: the hottest rows are kept
+            remote = (enc >> P.OWNER_SHIFT) != rank
+            u, c = torch.unique(enc[remote], return_counts=True)
+            kept = torch.isin(u, cache_ids.to(torch.int64))
+            assert int(c[kept].min()) >= int(c[~kept].max())
