@@ -11,6 +11,11 @@ Two plug points, both left by the reference itself:
   3. (utils=True) `gammagl.utils.sort_edge_index` / `coalesce` copies are wrapped: CUDA tensors go to the GPU two-key sort
      (`gammagl_b200.utils`), numpy arrays and CPU tensors to the original.
 disable() restores the originals.
+
+Layers constructed BEFORE enable(): MessagePassing.__init__ files the signature of `message_aggregate` in the instance's
+Inspector (message_passing.py:29-33), and the base signature has no `num_nodes`, so such an instance would hand
+num_nodes=None to the fused method (wrong row count for bipartite (src, dst) calls).  enable() therefore re-inspects every
+live instance of the patched classes (and disable() restores them); models may be built before or after enable().
 """
 import functools
 import sys
@@ -30,7 +35,7 @@ _NAMES = ['unsorted_segment_sum', 'unsorted_segment_mean', 'unsorted_segment_max
 # gpr_conv.py:72-73, mixhop_conv.py:95-100, cheb_conv.py:117-121, hid_conv.py:95-96, magcl_conv.py:85-87), where the CSR
 # cached on the first hop serves all the others.
 _FUSED_LAYERS = ['GCNConv', 'SAGEConv', 'GATConv', 'GINConv',
-                 'SGConv', 'APPNPConv', 'GCNIIConv', 'GPRConv', 'MixHopConv', 'ChebConv', 'Hid', 'MAGCLConv']
+                 'SGConv', 'APPNPConv', 'GCNIIConv', 'GPRConv', 'MixHopConv', 'ChebConv', 'Hid_conv', 'MAGCLConv']
 _UTILS = ['sort_edge_index', 'coalesce']   # gammagl/utils/sort_edge_index.py, coalesce.py: host argsort -> GPU two-key sort
 _saved = []
 
@@ -105,8 +110,31 @@ def enable(fuse_layers=True, modules=None, utils=True):
                 if isinstance(cls, type) and 'message_aggregate' not in cls.__dict__ and hasattr(cls, 'propagate'):
                     _saved.append((cls, 'message_aggregate', None, False))
                     cls.message_aggregate = _fused_message_aggregate
+                    _patched_classes.append(cls)
                     count += 1
+    if fuse_layers:
+        _reinspect_live_instances()
     return count
+
+
+_patched_classes = []
+
+
+def _reinspect_live_instances():
+    """Refresh the Inspector entry of `message_aggregate` on every live instance of the patched classes (see module doc)."""
+    import gc
+    import warnings
+    classes = tuple(_patched_classes)
+    if not classes:
+        return
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')      # isinstance() on lazy module proxies may emit deprecation warnings
+        for obj in gc.get_objects():
+            try:
+                if isinstance(obj, classes) and hasattr(obj, 'inspector') and hasattr(obj.inspector, 'inspect'):
+                    obj.inspector.inspect(obj.message_aggregate)
+            except Exception:   # objects that misbehave under isinstance / getattr are not ours
+                continue
 
 
 def disable():
@@ -116,3 +144,5 @@ def disable():
             setattr(obj, name, old)
         elif name in obj.__dict__:
             delattr(obj, name)
+    _reinspect_live_instances()          # back to the base signature on the instances
+    del _patched_classes[:]
