@@ -104,14 +104,17 @@ def build_csr(key, other, n_rows, n_other=None):
 
 
 class Graph:
-    """Forward (by destination) and transposed (by source) CSR of one edge_index[2,E]."""
+    """Forward (by destination) and transposed (by source) CSR of one edge_index[2,E].
+    Bipartite graphs (SAGEConv's (src_feat, dst_feat) blocks, sage_conv.py:75-92; sampled mini-batch blocks): n_src source
+    rows and n_dst destination rows; N (= n_dst) keeps the square-graph meaning for the callers that only know one size."""
 
-    def __init__(self, edge_index, num_nodes):
+    def __init__(self, edge_index, num_nodes, num_src=None):
         require_cuda(edge_index, 'edge_index')
         if edge_index.dim() != 2 or edge_index.shape[0] != 2:
             raise ValueError('edge_index must have shape [2, E], got %s' % (tuple(edge_index.shape),))
         self.edge_index = edge_index
-        self.N = int(num_nodes)
+        self.N = self.n_dst = int(num_nodes)
+        self.n_src = self.n_dst if num_src is None else int(num_src)
         self.E = int(edge_index.shape[1])
         self._fwd = None
         self._bwd = None
@@ -119,13 +122,13 @@ class Graph:
     @property
     def fwd(self):  # rows = dst (edge_index[1]), col = src
         if self._fwd is None:
-            self._fwd = build_csr(self.edge_index[1], self.edge_index[0], self.N)
+            self._fwd = build_csr(self.edge_index[1], self.edge_index[0], self.n_dst, n_other=self.n_src)
         return self._fwd
 
     @property
     def bwd(self):  # rows = src, col = dst
         if self._bwd is None:
-            self._bwd = build_csr(self.edge_index[0], self.edge_index[1], self.N)
+            self._bwd = build_csr(self.edge_index[0], self.edge_index[1], self.n_src, n_other=self.n_dst)
         return self._bwd
 
 
@@ -158,13 +161,18 @@ class _Lru:
         self.d.clear()
 
 
-_graphs = _Lru(4)
-_segments = _Lru(8)
+import os as _os
+
+# hetero models keep one graph per relation alive: capacities are configurable (GGLB200_GRAPH_CACHE / GGLB200_SEGMENT_CACHE)
+_graphs = _Lru(int(_os.environ.get('GGLB200_GRAPH_CACHE', '16')))
+_segments = _Lru(int(_os.environ.get('GGLB200_SEGMENT_CACHE', '16')))
 
 
-def graph_of(edge_index, num_nodes):
-    """Cached Graph for an edge_index tensor (built on first use; CSR build cost is paid once per graph)."""
-    return _graphs.get(edge_index, int(num_nodes), lambda: Graph(edge_index, num_nodes))
+def graph_of(edge_index, num_nodes, num_src=None):
+    """Cached Graph for an edge_index tensor (built on first use; CSR build cost is paid once per graph).
+    num_src: number of source rows when it differs from num_nodes (= destination rows): bipartite blocks."""
+    n_src = int(num_nodes) if num_src is None else int(num_src)
+    return _graphs.get(edge_index, (int(num_nodes), n_src), lambda: Graph(edge_index, num_nodes, n_src))
 
 
 def segment_csr_of(segment_ids, num_segments):

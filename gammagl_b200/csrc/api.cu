@@ -91,7 +91,7 @@ extern "C" size_t gglb200_spmm_workspace_bytes(int64_t E, int64_t K, int reduce)
   return gglb200_spmm_workspace_bytes_for_chunks(plan_max_chunks_host(E), K, reduce);
 }
 
-static int spmm_entry(const void* const* x_table, int32_t owner_shift, int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
+static int spmm_entry(bool arg_eid, const void* const* x_table, int32_t owner_shift, int reduce, const int32_t* rowptr, const int32_t* col, const int32_t* plan,
                                 const float* w, const int32_t* wperm, int32_t heads, const void* x, void* out,
                                 int64_t* arg, int64_t arg_empty, const float* out_scale, const float* bias, int relu, int64_t n_rows, int64_t n_src,
                                 int64_t E, int64_t K, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
@@ -104,6 +104,8 @@ static int spmm_entry(const void* const* x_table, int32_t owner_shift, int reduc
   GGL_REQUIRE(heads >= 1, GGL_EINVAL, "spmm: heads must be >= 1");
   GGL_REQUIRE(heads == 1 || (w != nullptr && K % heads == 0), GGL_EINVAL, "spmm: heads=%d needs w and K %% heads == 0 (K=%lld)", heads, (long long)K);
   GGL_REQUIRE(arg == nullptr || reduce == GGL_MAX, GGL_EINVAL, "spmm: arg is only produced by GGL_MAX");
+  GGL_REQUIRE(!arg_eid || (reduce == GGL_MAX && arg != nullptr && wperm != nullptr), GGL_EINVAL,
+              "spmm: edge-id arg needs GGL_MAX, arg and the CSR's perm");
   GGL_REQUIRE(out_scale == nullptr || (reduce == GGL_SUM && (dtype == GGL_F32 || dtype == GGL_BF16 || dtype == GGL_F16)), GGL_EINVAL,
               "spmm: out_scale needs GGL_SUM and a floating dtype");
   GGL_REQUIRE((bias == nullptr && relu == 0) || (reduce == GGL_SUM && (dtype == GGL_F32 || dtype == GGL_BF16 || dtype == GGL_F16)), GGL_EINVAL,
@@ -111,7 +113,7 @@ static int spmm_entry(const void* const* x_table, int32_t owner_shift, int reduc
 
   SpmmArgs p;
   p.reduce = reduce; p.rowptr = rowptr; p.col = col; p.plan = plan; p.w = w; p.wperm = wperm; p.heads = heads;
-  p.x = x; p.x_table = x_table; p.owner_shift = owner_shift; p.out = out; p.arg = arg; p.arg_empty = arg_empty; p.out_scale = out_scale; p.bias = bias; p.relu = relu; p.n_rows = n_rows; p.E = E; p.K = K; p.n_src = n_src;
+  p.x = x; p.x_table = x_table; p.owner_shift = owner_shift; p.out = out; p.arg = arg; p.arg_empty = arg_empty; p.arg_eid = arg_eid; p.out_scale = out_scale; p.bias = bias; p.relu = relu; p.n_rows = n_rows; p.E = E; p.K = K; p.n_src = n_src;
   p.part_val = nullptr; p.part_arg = nullptr; p.stream = (cudaStream_t)stream;
   p.n_tiles = plan_n_tiles(E);
   p.tile_row = plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E));
@@ -144,7 +146,7 @@ extern "C" int gglb200_spmm_csr(int reduce, const int32_t* rowptr, const int32_t
                                 const float* w, const int32_t* wperm, int32_t heads, const void* x, void* out,
                                 int64_t* arg, int64_t arg_empty, const float* out_scale, int64_t n_rows, int64_t n_src,
                                 int64_t E, int64_t K, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
-  return spmm_entry(nullptr, 0, reduce, rowptr, col, plan, w, wperm, heads, x, out, arg, arg_empty, out_scale, nullptr, 0, n_rows, n_src, E, K,
+  return spmm_entry(false, nullptr, 0, reduce, rowptr, col, plan, w, wperm, heads, x, out, arg, arg_empty, out_scale, nullptr, 0, n_rows, n_src, E, K,
                     dtype, workspace, workspace_bytes, stream);
 }
 
@@ -152,7 +154,7 @@ extern "C" int gglb200_spmm_csr_epilogue(const int32_t* rowptr, const int32_t* c
                                          const int32_t* wperm, int32_t heads, const void* x, void* out, const float* out_scale,
                                          const float* bias, int relu, int64_t n_rows, int64_t n_src, int64_t E, int64_t K,
                                          int dtype, void* workspace, size_t workspace_bytes, void* stream) {
-  return spmm_entry(nullptr, 0, GGL_SUM, rowptr, col, plan, w, wperm, heads, x, out, nullptr, 0, out_scale, bias, relu, n_rows, n_src,
+  return spmm_entry(false, nullptr, 0, GGL_SUM, rowptr, col, plan, w, wperm, heads, x, out, nullptr, 0, out_scale, bias, relu, n_rows, n_src,
                     E, K, dtype, workspace, workspace_bytes, stream);
 }
 
@@ -162,6 +164,15 @@ extern "C" int gglb200_spmm_csr_peer(int reduce, const int32_t* rowptr, const in
                                      int64_t K, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
   GGL_REQUIRE(x_table != nullptr && owner_shift >= 1 && owner_shift <= 30, GGL_EINVAL, "spmm_peer: bad x_table / owner_shift");
   GGL_REQUIRE(reduce == GGL_SUM || reduce == GGL_MEAN, GGL_EUNSUPPORTED, "spmm_peer: sum / mean only");
-  return spmm_entry(x_table, owner_shift, reduce, rowptr, col, plan, w, wperm, heads, nullptr, out, nullptr, 0, out_scale, nullptr, 0, n_rows,
+  return spmm_entry(false, x_table, owner_shift, reduce, rowptr, col, plan, w, wperm, heads, nullptr, out, nullptr, 0, out_scale, nullptr, 0, n_rows,
                     (int64_t)1 << owner_shift, E, K, dtype, workspace, workspace_bytes, stream);
+}
+
+extern "C" int gglb200_spmm_csr_max_edge(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* plan,
+                                         const float* w, const void* x, void* out, int64_t* arg_eid, int64_t arg_empty,
+                                         int64_t n_rows, int64_t n_src, int64_t E, int64_t K, int dtype, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  GGL_REQUIRE(perm != nullptr || E == 0, GGL_EINVAL, "spmm_max_edge: perm must not be NULL");
+  return spmm_entry(true, nullptr, 0, GGL_MAX, rowptr, col, plan, w, perm, 1, x, out, arg_eid, arg_empty, nullptr, nullptr, 0, n_rows, n_src,
+                    E, K, dtype, workspace, workspace_bytes, stream);
 }

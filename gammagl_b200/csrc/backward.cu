@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) spmm_max_bwd_kernel(const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
                                                            const float* __restrict__ w, const int32_t* __restrict__ wperm,
                                                            const float* __restrict__ g, const int64_t* __restrict__ argsrc,
-                                                           float* __restrict__ gx, int64_t n_rows, int32_t K) {
+                                                           float* __restrict__ gx, int64_t n_rows, int32_t K,
+                                                           const int32_t* __restrict__ eid_t /* NULL: arg holds source ids */) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_rows; s += warps) {
@@ -335,7 +336,10 @@ __global__ void __launch_bounds__(256) spmm_max_bwd_kernel(const int32_t* __rest
       for (int32_t i = b; i < e; ++i) {
         const int64_t d = __ldg(col_t + i);
         const float wi = w ? __ldg(w + (wperm ? __ldg(wperm + i) : i)) : 1.f;
-        if (k < K && __ldg(argsrc + d * K + k) == s) acc = __fadd_rn(acc, __fmul_rn(wi, __ldg(g + d * K + k)));
+        // edge-id form: only the ONE winning edge of (d, k) is credited (unsorted_segment_max semantics on the message,
+        // src/segment_max.cpp:48-61); source-id form: every parallel edge of the winning source (cpu/spmm_max_cpu.cpp:84-96)
+        const int64_t want = eid_t ? (int64_t)__ldg(eid_t + i) : s;
+        if (k < K && __ldg(argsrc + d * K + k) == want) acc = __fadd_rn(acc, __fmul_rn(wi, __ldg(g + d * K + k)));
       }
       if (k < K) gx[s * K + k] = acc;
     }
@@ -553,7 +557,20 @@ extern "C" int gglb200_spmm_max_bwd(const int32_t* rowptr_t, const int32_t* col_
   GGL_REQUIRE(n_rows >= 0 && K >= 0, GGL_EINVAL, "spmm_max_bwd: negative size");
   if (n_rows == 0 || K == 0) return GGL_OK;
   GGL_REQUIRE(rowptr_t && g && argsrc && gx, GGL_EINVAL, "spmm_max_bwd: NULL pointer");
-  spmm_max_bwd_kernel<<<grid_for(n_rows * 32), 256, 0, stream>>>(rowptr_t, col_t, w, wperm, g, argsrc, gx, n_rows, (int32_t)K);
+  spmm_max_bwd_kernel<<<grid_for(n_rows * 32), 256, 0, stream>>>(rowptr_t, col_t, w, wperm, g, argsrc, gx, n_rows, (int32_t)K, nullptr);
   GGL_LAUNCHED("spmm_max_bwd");
+  return GGL_OK;
+}
+
+extern "C" int gglb200_spmm_max_edge_bwd(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* perm_t, const float* w,
+                                         const float* g, const int64_t* arg_eid, float* gx, int64_t n_rows, int64_t K,
+                                         void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(n_rows >= 0 && K >= 0, GGL_EINVAL, "spmm_max_edge_bwd: negative size");
+  if (n_rows == 0 || K == 0) return GGL_OK;
+  GGL_REQUIRE(rowptr_t && perm_t && g && arg_eid && gx, GGL_EINVAL, "spmm_max_edge_bwd: NULL pointer");
+  spmm_max_bwd_kernel<<<grid_for(n_rows * 32), 256, 0, stream>>>(rowptr_t, col_t, w, w ? perm_t : nullptr, g, arg_eid, gx, n_rows,
+                                                                 (int32_t)K, perm_t);
+  GGL_LAUNCHED("spmm_max_edge_bwd");
   return GGL_OK;
 }

@@ -15,7 +15,11 @@ namespace ggl {
 // no long-row path.  The g row of the current destination lives in registers (the next row's is prefetched); a lane
 // owns 4 consecutive channels of one head and the C/4 lanes of a head combine with xor-shuffles.
 // Requires C % 4 == 0 with C/4 a power of two <= LPR (heads never straddle a 128-column tile).
-template <int LPR>
+// SPAN = true lifts that: any head width C >= 4 with K = H*C a multiple of 4 and K <= 128 (one column tile).  A lane's four
+// channels may then reach into the next head: it forms two partial dots (its own head | the next one), hands the second to its
+// right neighbour (whose first channel always belongs to that head when C >= 4), and the lanes of a head -- a contiguous run of
+// arbitrary length -- combine with a segmented shuffle scan; the last lane of each run writes gw[e, h].
+template <int LPR, bool SPAN>
 __global__ void __launch_bounds__(32) sddmm_ring_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                         const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_row,
                                                         const int64_t n_tiles, const int32_t tile_edges, const int32_t E,
@@ -34,8 +38,15 @@ __global__ void __launch_bounds__(32) sddmm_ring_kernel(const int32_t* __restric
   const int32_t K = H * C;
   const int32_t kcol = ((int32_t)blockIdx.y * LPR + sub) * VEC;
   const bool col_active = kcol < K;
-  const int32_t head = col_active ? kcol / C : 0;
-  const int LH = C / VEC;  // lanes per head
+  const int32_t head = col_active ? kcol / C : (SPAN ? -1 - sub : 0);
+  const int LH = C / VEC;  // lanes per head (SPAN = false)
+  int32_t nlo = 4;         // SPAN: channels [0, nlo) of this lane belong to `head`, the rest to head + 1
+  bool run_last = false;   // SPAN: this lane is the last one of its head's run
+  if constexpr (SPAN) {
+    if (col_active) nlo = min(4, (head + 1) * C - kcol);
+    const int32_t next_head = __shfl_down_sync(gmask, head, 1);
+    run_last = col_active && (sub == LPR - 1 || next_head != head);
+  }
   const float* xt = x + (int64_t)blockIdx.y * LPR * VEC;
   const uint32_t rowb = (uint32_t)min(LPR * 16, K * 4 - (int32_t)blockIdx.y * LPR * 16);
 
@@ -116,13 +127,34 @@ __global__ void __launch_bounds__(32) sddmm_ring_kernel(const int32_t* __restric
           gnext = load_g(gnext_row);
           g_valid = true;
         }
-        float dot = 0.f;
-        if (col_active) {
-          const Pack<float, 4> v = lds_pack<float, 4>(src + u * pitch);
-          dot = fmaf(v.v[3], gv.v[3], fmaf(v.v[2], gv.v[2], fmaf(v.v[1], gv.v[1], v.v[0] * gv.v[0])));
+        if constexpr (!SPAN) {
+          float dot = 0.f;
+          if (col_active) {
+            const Pack<float, 4> v = lds_pack<float, 4>(src + u * pitch);
+            dot = fmaf(v.v[3], gv.v[3], fmaf(v.v[2], gv.v[2], fmaf(v.v[1], gv.v[1], v.v[0] * gv.v[0])));
+          }
+          for (int off = LH >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(gmask, dot, off);
+          if (col_active && (sub & (LH - 1)) == 0) gw[(int64_t)eid[u] * H + head] = dot;
+        } else {
+          float lo = 0.f, hi = 0.f;
+          if (col_active) {
+            const Pack<float, 4> v = lds_pack<float, 4>(src + u * pitch);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float pr = v.v[i] * gv.v[i];
+              if (i < nlo) lo += pr; else hi += pr;
+            }
+          }
+          const float from_left = __shfl_up_sync(gmask, hi, 1);      // the left neighbour's spill-over belongs to this lane's head
+          float dot = lo + (sub > 0 ? from_left : 0.f);
+#pragma unroll
+          for (int d = 1; d < LPR; d <<= 1) {                         // segmented inclusive scan over runs of equal head
+            const float t = __shfl_up_sync(gmask, dot, d);
+            const int32_t hh = __shfl_up_sync(gmask, head, d);
+            if (sub >= d && hh == head) dot += t;
+          }
+          if (run_last) gw[(int64_t)eid[u] * H + head] = dot;
         }
-        for (int off = LH >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(gmask, dot, off);
-        if (col_active && (sub & (LH - 1)) == 0) gw[(int64_t)eid[u] * H + head] = dot;
       }
     }
   }
@@ -270,11 +302,14 @@ extern "C" int gglb200_bspmm_bwd_w(const int32_t* rowptr, const int32_t* col, co
   GGL_REQUIRE(rowptr && col && perm && plan && x && g && gw, GGL_EINVAL, "bspmm_bwd_w: NULL pointer");
   const int64_t K = (int64_t)H * C;
   const int lh = C / 4;
-  const bool fast = C % 4 == 0 && lh >= 1 && lh <= 32 && (lh & (lh - 1)) == 0 && (((uintptr_t)x | (uintptr_t)g) % 16 == 0);
-  if (fast) {
+  const bool aligned = (((uintptr_t)x | (uintptr_t)g) % 16 == 0);
+  const bool fast = C % 4 == 0 && lh >= 1 && lh <= 32 && (lh & (lh - 1)) == 0 && aligned;
+  // any other head width (H=4, C=25 ...): spanning lanes, one column tile
+  const bool span = !fast && C >= 4 && K % 4 == 0 && K <= 128 && aligned;
+  if (fast || span) {
     int lpr = lpr_for(K, 4);
     if (lpr < 4) lpr = 4;
-    if (lpr < lh) lpr = lh;
+    if (fast && lpr < lh) lpr = lh;
     const int tiles = (int)((K + (int64_t)lpr * 4 - 1) / ((int64_t)lpr * 4));
     const int64_t n_tiles = plan_n_tiles(E);
     const int32_t* tile_row = plan + plan_tile_off(plan_max_chunks(E), plan_max_long(E));
@@ -284,11 +319,18 @@ extern "C" int gglb200_bspmm_bwd_w(const int32_t* rowptr, const int32_t* col, co
     using Cfg = RingCfg<L_>;                                                                                                \
     constexpr int GPW = 32 / L_;                                                                                            \
     const size_t smem = (size_t)GPW * Cfg::STAGES * Cfg::R * pitch + (size_t)GPW * Cfg::STAGES * 8;                          \
-    GGL_CUDA(cudaFuncSetAttribute(sddmm_ring_kernel<L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));          \
     const int64_t blocks = (n_tiles + GPW - 1) / GPW;                                                                       \
-    sddmm_ring_kernel<L_><<<dim3((unsigned)blocks, tiles), 32, smem, stream>>>(rowptr, col, perm, tile_row, n_tiles,        \
-                                                                               tile_edges(), (int32_t)E, x, g, gw,          \
-                                                                               (int32_t)n_rows, H, C, pitch);               \
+    if (span) {                                                                                                             \
+      GGL_CUDA(cudaFuncSetAttribute(sddmm_ring_kernel<L_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));  \
+      sddmm_ring_kernel<L_, true><<<dim3((unsigned)blocks, tiles), 32, smem, stream>>>(rowptr, col, perm, tile_row, n_tiles, \
+                                                                                       tile_edges(), (int32_t)E, x, g, gw,  \
+                                                                                       (int32_t)n_rows, H, C, pitch);       \
+    } else {                                                                                                                \
+      GGL_CUDA(cudaFuncSetAttribute(sddmm_ring_kernel<L_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+      sddmm_ring_kernel<L_, false><<<dim3((unsigned)blocks, tiles), 32, smem, stream>>>(rowptr, col, perm, tile_row, n_tiles, \
+                                                                                        tile_edges(), (int32_t)E, x, g, gw, \
+                                                                                        (int32_t)n_rows, H, C, pitch);      \
+    }                                                                                                                       \
   } while (0)
     switch (lpr) {
       case 4: GGL_SDDMM(4); break;

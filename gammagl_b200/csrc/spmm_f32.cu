@@ -11,6 +11,9 @@ int launch_spmm<float>(const SpmmArgs& p) {
   int vec = 1;
   if (K > 4) {
     if (K % 4 == 0 && C % 4 == 0 && al % 16 == 0) vec = 4;
+    // per-head weights with a head width that is not a multiple of 4 (H=4, C=25 ...): 16-byte lanes that may span two heads
+    // (WMODE 3) instead of four scalar column tiles -- the row is still one aligned 16-byte-multiple bulk copy
+    else if (p.heads > 1 && K % 4 == 0 && C >= 4 && al % 16 == 0 && p.x_table == nullptr) vec = 4;
     else if (K % 2 == 0 && C % 2 == 0 && al % 8 == 0) vec = 2;
   }
   const int lpr = lpr_for(K, vec);

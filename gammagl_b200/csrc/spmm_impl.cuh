@@ -52,6 +52,7 @@ struct SpmmArgs {
   void* out;
   int64_t* arg;             // MAX only, may be NULL
   int64_t arg_empty;
+  bool arg_eid;             // MAX: arg records wperm[i] (the ORIGINAL EDGE ID of the winning edge) instead of col[i]; needs wperm
   const float* out_scale;   // NULL, or [n_rows] fp32: out[r,:] = out_scale[r] * reduce(...) (folded GCN normalisation)
   const float* bias;        // NULL, or [K] fp32 added after out_scale (GCNConv's bias, gcn_conv.py:104-106); SUM, floating out
   int32_t relu;             // != 0: out = max(out, 0) after the bias (the activation the models apply next)
@@ -76,13 +77,18 @@ template <int LPR> __device__ __forceinline__ unsigned group_mask(int lane) {
   else return ((1u << LPR) - 1u) << (lane & ~(LPR - 1));
 }
 
+// WMODE: 0 = unweighted, 1 = w[E], 2 = w[E,H] with every lane inside one head, 3 = w[E,H] with lanes that may span TWO heads
+// (head width C not a multiple of VEC, C >= VEC: elements [0, nlo) take wv, the rest wv_hi).
 template <typename T, int VEC, int WMODE, bool ISMAX>
 __device__ __forceinline__ void accumulate(typename Elem<T>::acc_t (&acc)[VEC], int32_t (&argv)[VEC], const Pack<T, VEC>& v,
-                                           float wv, int32_t c) {
+                                           float wv, int32_t c, float wv_hi = 0.f, int nlo = VEC) {
   using acc_t = typename Elem<T>::acc_t;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     acc_t xv = Elem<T>::to_acc(v.v[i]);
+    if constexpr (WMODE == 3) {
+      if (i >= nlo) wv = wv_hi;
+    }
     if constexpr (WMODE != 0 && Elem<T>::is_float && sizeof(T) == 2 && !ISMAX) {
       // 16-bit storage has no bit-exact reference (the reference is fp32-only here; north_star tolerance 1e-2): one fused
       // multiply-add per element instead of two separately rounded operations -- these rows are issue-bound, not byte-bound
@@ -125,7 +131,9 @@ __device__ __forceinline__ void reduce_range(typename Elem<T>::acc_t (&acc)[VEC]
       if (sub < n) {
         const int32_t idx = start + base + sub;
         mycol = ld_stream_i32(p.col + idx);
-        if constexpr (WMODE != 0) myeid = p.wperm ? ld_stream_i32(p.wperm + idx) : idx;
+        if constexpr (WMODE != 0 || ISMAX) {
+          if (WMODE != 0 || p.arg_eid) myeid = p.wperm ? ld_stream_i32(p.wperm + idx) : idx;
+        }
         if constexpr (WMODE == 1) myw = p.wperm ? __ldg(p.w + myeid) : ld_stream_f32(p.w + myeid);
       }
     }
@@ -133,12 +141,14 @@ __device__ __forceinline__ void reduce_range(typename Elem<T>::acc_t (&acc)[VEC]
     for (int j = 0; j < n; j += U) {
       Pack<T, VEC> v[U];
       int32_t c[U];
+      int32_t ai[U];
       float wv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int jj = j + u;
         if constexpr (LPR > 1) {
           c[u] = __shfl_sync(gmask, mycol, gbase + (jj & (LPR - 1)));
+          if constexpr (ISMAX) ai[u] = p.arg_eid ? __shfl_sync(gmask, myeid, gbase + (jj & (LPR - 1))) : c[u];
           wv[u] = 1.f;
           if constexpr (WMODE == 1) wv[u] = __shfl_sync(gmask, myw, gbase + (jj & (LPR - 1)));
           if constexpr (WMODE == 2) {
@@ -147,9 +157,11 @@ __device__ __forceinline__ void reduce_range(typename Elem<T>::acc_t (&acc)[VEC]
           }
         } else {
           c[u] = 0; wv[u] = 1.f;
+          if constexpr (ISMAX) ai[u] = 0;
           if (jj < n) {
             const int32_t idx = start + base + jj;
             c[u] = ld_stream_i32(p.col + idx);
+            if constexpr (ISMAX) ai[u] = p.arg_eid ? (p.wperm ? ld_stream_i32(p.wperm + idx) : idx) : c[u];
             if constexpr (WMODE != 0) {
               const int32_t eid = p.wperm ? ld_stream_i32(p.wperm + idx) : idx;
               wv[u] = (WMODE == 1) ? __ldg(p.w + eid) : __ldg(p.w + (int64_t)eid * p.heads + head);
@@ -160,7 +172,7 @@ __device__ __forceinline__ void reduce_range(typename Elem<T>::acc_t (&acc)[VEC]
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (j + u < n && col_active) accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v[u], wv[u], c[u]);
+        if (j + u < n && col_active) accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v[u], wv[u], ISMAX ? ai[u] : c[u]);
       }
     }
   }
@@ -298,7 +310,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) spmm_tiles_kernel(cons
     const int32_t idx = at + sub;
     if (idx < e_end) {
       bcol = ld_stream_i32(p.col + idx);
-      if constexpr (WMODE != 0) beid = p.wperm ? ld_stream_i32(p.wperm + idx) : idx;
+      if constexpr (WMODE != 0 || ISMAX) {
+        if (WMODE != 0 || p.arg_eid) beid = p.wperm ? ld_stream_i32(p.wperm + idx) : idx;
+      }
       if constexpr (WMODE == 1) bw = p.wperm ? __ldg(p.w + beid) : ld_stream_f32(p.w + beid);
     }
   };
@@ -313,11 +327,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) spmm_tiles_kernel(cons
     for (int j = 0; j < nb; j += U) {
       Pack<T, VEC> v[U];
       int32_t c[U];
+      int32_t ai[U];
       float wv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int jj = j + u;
         c[u] = __shfl_sync(gmask, mycol, gbase + (jj & (LPR - 1)));
+        if constexpr (ISMAX) ai[u] = p.arg_eid ? __shfl_sync(gmask, myeid, gbase + (jj & (LPR - 1))) : c[u];
         wv[u] = 1.f;
         if constexpr (WMODE == 1) wv[u] = __shfl_sync(gmask, myw, gbase + (jj & (LPR - 1)));
         if constexpr (WMODE == 2) {
@@ -331,7 +347,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) spmm_tiles_kernel(cons
         const int jj = j + u;
         if (jj < nb) {
           while (e + jj == rc.cur_end) next_row();
-          if (col_active) accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v[u], wv[u], c[u]);
+          if (col_active) accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v[u], wv[u], ISMAX ? ai[u] : c[u]);
         }
       }
     }
@@ -419,7 +435,15 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
   const int64_t g = (int64_t)blockIdx.x * GPW + gib;
   const int32_t kcol = ((int32_t)blockIdx.y * LPR + sub) * VEC;
   const bool col_active = kcol < p.K;
-  const int32_t head = (WMODE == 2 && col_active) ? kcol / (int32_t)(p.K / p.heads) : 0;
+  const int32_t head = ((WMODE == 2 || WMODE == 3) && col_active) ? kcol / (int32_t)(p.K / p.heads) : 0;
+  // WMODE 3: the lane's VEC elements may reach into the next head (head width not a multiple of VEC): elements [0, nlo) belong
+  // to `head`, the rest to `head_hi`
+  int32_t nlo = VEC, head_hi = head;
+  if constexpr (WMODE == 3) {
+    const int32_t Cw = (int32_t)(p.K / p.heads);
+    nlo = min(VEC, (head + 1) * Cw - kcol);
+    head_hi = min(head + 1, p.heads - 1);
+  }
   const int64_t K = p.K;
   const T* xt = reinterpret_cast<const T*>(p.x) + (int64_t)blockIdx.y * LPR * VEC;  // first column of this column tile
   // bytes of one row inside this column tile, and the bytes copied per row
@@ -478,7 +502,9 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
     if (pos < n) {
       const int32_t idx = e0 + pos;
       t.col = ld_stream_i32(p.col + idx);
-      if constexpr (WMODE != 0) t.eid = p.wperm ? ld_stream_i32(p.wperm + idx) : idx;
+      if constexpr (WMODE != 0 || ISMAX) {
+        if (WMODE != 0 || p.arg_eid) t.eid = p.wperm ? ld_stream_i32(p.wperm + idx) : idx;
+      }
     }
     return t;
   };
@@ -543,17 +569,25 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
     issue(s + LAG);
     // per-edge scalars of this slot, fetched in convergent code
     float wv[R];
+    float wv_hi[WMODE == 3 ? R : 1];
     int32_t cc[R];
+    int32_t ai[R];   // MAX: what `arg` records for the edge (source id, or the original edge id with arg_eid)
 #pragma unroll
     for (int u = 0; u < R; ++u) {
       wv[u] = 1.f; cc[u] = 0;
       if constexpr (ISMAX || !ALIGNED) cc[u] = __shfl_sync(gmask, A.col, gbase + ((pos0 + u) & (LPR - 1)));
+      if constexpr (ISMAX) ai[u] = p.arg_eid ? __shfl_sync(gmask, A.eid, gbase + ((pos0 + u) & (LPR - 1))) : cc[u];
       if constexpr (WMODE == 1) wv[u] = __shfl_sync(gmask, A.w, gbase + ((pos0 + u) & (LPR - 1)));
-      if constexpr (WMODE == 2) {
+      if constexpr (WMODE == 2 || WMODE == 3) {
         const int32_t eid = __shfl_sync(gmask, A.eid, gbase + ((pos0 + u) & (LPR - 1)));
         wv[u] = __ldg(p.w + (int64_t)eid * p.heads + head);
+        if constexpr (WMODE == 3) wv_hi[u] = __ldg(p.w + (int64_t)eid * p.heads + head_hi);
       }
     }
+    auto acc_edge = [&](int u, const Pack<T, VEC>& v) {
+      if constexpr (WMODE == 3) accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v, wv[u], ISMAX ? ai[u] : cc[u], wv_hi[u], nlo);
+      else accumulate<T, VEC, WMODE, ISMAX>(acc, argv, v, wv[u], ISMAX ? ai[u] : cc[u]);
+    };
     mbar_wait(bars + (uint32_t)cstage * 8, cparity);
     const uint32_t src = ring + (uint32_t)(cstage * R) * pitch + (uint32_t)sub * VB;
     if (++cstage == STAGES) { cstage = 0; cparity ^= 1u; }
@@ -572,7 +606,7 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
       // fast path: the whole slot lies inside the current row
       if (col_active) {
 #pragma unroll
-        for (int u = 0; u < R; ++u) accumulate<T, VEC, WMODE, ISMAX>(acc, argv, fetch(u), wv[u], cc[u]);
+        for (int u = 0; u < R; ++u) acc_edge(u, fetch(u));
       }
     } else {
 #pragma unroll
@@ -580,7 +614,7 @@ __global__ void __launch_bounds__(32) spmm_ring_kernel(const SpmmArgs p, const i
         const int32_t pos = pos0 + u;
         if (pos < n) {  // group-uniform
           while (e0 + pos == rc.cur_end) next_row();
-          if (col_active) accumulate<T, VEC, WMODE, ISMAX>(acc, argv, fetch(u), wv[u], cc[u]);
+          if (col_active) acc_edge(u, fetch(u));
         }
       }
     }
@@ -725,6 +759,11 @@ int launch_config(const SpmmArgs& p) {
   GGL_REQUIRE(tiles <= 65535, GGL_EUNSUPPORTED, "spmm: K=%lld needs too many column tiles", (long long)p.K);
   // floating rows of at least 4 lanes stream through the shared-memory ring; the rest (K <= 4 elements per row,
   // f64, integers) through the register-staged kernels
+  if constexpr (WMODE == 3) {
+    // spanning lanes exist on the bulk-copy ring only (fp32, 16-byte lanes)
+    if constexpr (Elem<T>::is_float && sizeof(T) == 4 && VEC == 4 && LPR >= 4) return launch_ring<T, VEC, LPR, WMODE, ISMAX>(p, tiles);
+    else return set_error(GGL_EUNSUPPORTED, "spmm: head width not a multiple of the lane width is fp32 / 16-byte lanes only");
+  } else {
   if constexpr (Elem<T>::is_float && sizeof(T) <= 4 && LPR >= 4) {
     if (tune_ring() != 0 || p.x_table) {
       GGL_REQUIRE(p.x_table == nullptr || (sizeof(T) * VEC == 16 && !ISMAX), GGL_EUNSUPPORTED,
@@ -751,16 +790,23 @@ int launch_config(const SpmmArgs& p) {
     GGL_LAUNCHED("spmm_finalize");
   }
   return GGL_OK;
+  }  // WMODE != 3
 }
 
 template <typename T, int VEC, int LPR>
 int launch_modes(const SpmmArgs& p, bool allow_weight) {
-  const int wmode = p.w == nullptr ? 0 : (p.heads > 1 ? 2 : 1);
+  int wmode = p.w == nullptr ? 0 : (p.heads > 1 ? 2 : 1);
+  if (wmode == 2 && (p.K / p.heads) % VEC != 0) wmode = 3;   // lanes span two heads (the caller guarantees C >= VEC)
   const bool ismax = p.reduce == GGL_MAX;
   if (wmode == 0) return ismax ? launch_config<T, VEC, LPR, 0, true>(p) : launch_config<T, VEC, LPR, 0, false>(p);
   if constexpr (Elem<T>::is_float) {
     if (allow_weight) {
       if (wmode == 1) return ismax ? launch_config<T, VEC, LPR, 1, true>(p) : launch_config<T, VEC, LPR, 1, false>(p);
+      if (wmode == 3) {
+        if constexpr (sizeof(T) == 4 && VEC == 4 && LPR >= 4)
+          return ismax ? launch_config<T, VEC, LPR, 3, true>(p) : launch_config<T, VEC, LPR, 3, false>(p);
+        else return set_error(GGL_EUNSUPPORTED, "spmm: head width %lld is not a multiple of the lane width", (long long)(p.K / p.heads));
+      }
       return ismax ? launch_config<T, VEC, LPR, 2, true>(p) : launch_config<T, VEC, LPR, 2, false>(p);
     }
   }

@@ -50,13 +50,14 @@ class MessagePassing(torch.nn.Module):
     """message_passing.py:35-167.  propagate() takes the fused branch when the subclass did not override
     `message` (the base message is gather x weight, exactly what gspmm fuses) and `fused` is on."""
 
-    def __init__(self, fused=True, fuse_max=False):
+    def __init__(self, fused=True, fuse_max=True):
         super().__init__()
         self.fused = fused
         # aggr='max': the reference layer runs message + unsorted_segment_max, whose backward credits the FIRST winning edge
-        # only (src/segment_max.cpp:48-61); its gspmm-max operator credits every parallel edge of the winning source
-        # (cpu/spmm_max_cpu.cpp:84-96).  Both operators are reproduced exactly, so on multigraphs the fused form would change
-        # the layer's gradients: max is fused only on request (graphs without parallel edges), sum / mean always.
+        # only (src/segment_max.cpp:48-61), while its gspmm-max operator credits every parallel edge of the winning source
+        # (cpu/spmm_max_cpu.cpp:84-96).  The fused max used here (mpops.gspmm_max_edge) records the winning EDGE, so it
+        # reproduces the layer's gradients on multigraphs as well and never materialises the [E, K] message;
+        # fuse_max=False keeps the decomposition (size-guarded).
         self.fuse_max = fuse_max
 
     def message(self, x, edge_index, edge_weight=None):
@@ -75,14 +76,16 @@ class MessagePassing(torch.nn.Module):
             return mpops.unsorted_segment_max(msg, dst_index, num_nodes)
         raise NotImplementedError('Not support for this opearator')
 
-    def message_aggregate(self, x, edge_index, edge_weight=None, aggr='sum'):
+    def message_aggregate(self, x, edge_index, edge_weight=None, aggr='sum', num_nodes=None):
         if edge_weight is not None and edge_weight.dim() == 2 and x.dim() == 3:
             return mpops.bspmm(edge_index, edge_weight, x, aggr)            # per-head weights (GAT)
         if mpops.weight_needs_grad(edge_weight) and x.dim() == 2 and aggr == 'sum':
             # gspmm has no gradient for the weight (src/gspmm.cpp:30,79) but the reference layer's message * weight has:
             # the one-head bspmm is the same forward kernel plus the SDDMM weight gradient
             return mpops.bspmm(edge_index, edge_weight.reshape(-1, 1), x.unsqueeze(1), 'sum').squeeze(1)
-        return mpops.gspmm(edge_index, edge_weight, x, aggr)                # message_passing.py:99-104
+        if aggr == 'max':
+            return mpops.gspmm_max_edge(edge_index, edge_weight, x, num_dst=num_nodes)
+        return mpops.gspmm(edge_index, edge_weight, x, aggr, num_dst=num_nodes)   # message_passing.py:99-104 (+ bipartite rows)
 
     def update(self, x):
         return x
@@ -91,17 +94,25 @@ class MessagePassing(torch.nn.Module):
         if kwargs.get('num_nodes') is None:
             kwargs['num_nodes'] = x.shape[0]                                # message_passing.py:141-142
         edge_weight = kwargs.get('edge_weight')
+        n_dst = kwargs['num_nodes']
         base_message = type(self).message is MessagePassing.message
-        square = kwargs['num_nodes'] == x.shape[0]                          # gspmm output rows = x rows (no bipartite)
-        differentiable_w = mpops.weight_needs_grad(edge_weight) and not (aggr == 'sum' and x.dim() in (2, 3))
-        if self.fused and base_message and square and (aggr != 'max' or self.fuse_max) and not differentiable_w:
-            out = self.message_aggregate(x, edge_index, edge_weight=edge_weight, aggr=aggr)
+        square = n_dst == x.shape[0]
+        w_grad = mpops.weight_needs_grad(edge_weight)
+        per_head = edge_weight is not None and edge_weight.dim() == 2 and x.dim() == 3
+        fusable = (self.fused and base_message
+                   and (square or not (per_head or (w_grad and aggr == 'sum')))          # bspmm is square-only
+                   and (not w_grad or (aggr == 'sum' and x.dim() in (2, 3)))                # weight gradient: sum only (bspmm)
+                   and (aggr != 'max' or (self.fuse_max and not per_head and not w_grad)))
+        if fusable:
+            out = self.message_aggregate(x, edge_index, edge_weight=edge_weight, aggr=aggr, num_nodes=n_dst)
         else:
             if base_message:
+                mpops.check_message_bytes(edge_index.shape[1], x[0].numel() if x.dim() > 1 else 1, x.element_size(),
+                                          '%s.propagate(aggr=%r)' % (type(self).__name__, aggr))
                 msg = self.message(x, edge_index, edge_weight)
             else:
                 msg = self.message(x, edge_index)
-            out = self.aggregate(msg, edge_index, num_nodes=kwargs['num_nodes'], aggr=aggr)
+            out = self.aggregate(msg, edge_index, num_nodes=n_dst, aggr=aggr)
         return self.update(out)
 
 

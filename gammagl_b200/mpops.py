@@ -213,10 +213,11 @@ def _check_spmm_args(index, weight, x):
 
 class _SpMM(torch.autograd.Function):
     """SpMMSum / SpMMMean / SpMMMax (torch_ext/src/gspmm.cpp:26-202).  No gradient for `weight`
-    (mark_non_differentiable, src/gspmm.cpp:30,79)."""
+    (mark_non_differentiable, src/gspmm.cpp:30,79).  n_dst (extension): number of output rows when the graph is bipartite
+    (x holds the n_src source rows); None = x.shape[0] like the reference operator."""
 
     @staticmethod
-    def forward(ctx, index, weight, x, reduce):
+    def forward(ctx, index, weight, x, reduce, n_dst=None):
         _check_spmm_args(index, weight, x)
         E = index.shape[1]
         if weight is not None and weight.numel() != E:
@@ -225,9 +226,10 @@ class _SpMM(torch.autograd.Function):
         # weight=None is the reference's torch.ones(E) (torch.py:332-333): 1.0 * x is exact, so the unweighted kernel
         # gives the identical result without streaming E ones
         weight = weight.contiguous().view(-1) if weight is not None else None
-        N = x.shape[0]
-        g = graph_of(index, N)
-        x2d = x.view(N, -1)
+        n_src = x.shape[0]
+        n_dst = n_src if n_dst is None else int(n_dst)
+        g = graph_of(index, n_dst, n_src)
+        x2d = x.view(n_src, -1)
         out, arg = spmm_csr(g.fwd, g.fwd.col, x2d, reduce, w=weight, wperm=g.fwd.perm if weight is not None else None,
                             want_arg=(reduce == _lib.GGL_MAX), arg_empty=0)
         ctx.graph, ctx.reduce, ctx.x_shape = g, reduce, tuple(x.shape)
@@ -235,33 +237,90 @@ class _SpMM(torch.autograd.Function):
         if weight is not None:
             ctx.save_for_backward(weight)
         ctx.arg = arg
-        return out.view(x.shape)
+        return out.view((n_dst,) + tuple(x.shape[1:]))
 
     @staticmethod
     def backward(ctx, grad_out):
         lib = _lib.load()
         weight = ctx.saved_tensors[0] if ctx.has_w else None
         g = ctx.graph
-        grad = grad_out.contiguous().view(g.N, -1)
+        grad = grad_out.contiguous().view(g.n_dst, -1)
         K = grad.shape[1]
         dev = grad.device
         with torch.cuda.device(dev):
             if ctx.reduce == _lib.GGL_MAX:
                 if grad.dtype != torch.float32:
                     raise _lib.GglError('gspmm(max) backward is float32 only')
-                gx = torch.empty_like(grad)
+                gx = torch.empty((g.n_src, K), dtype=grad.dtype, device=dev)
                 _lib.check(lib.gglb200_spmm_max_bwd(_ptr(g.bwd.rowptr), _ptr(g.bwd.col), _ptr(weight), _ptr(g.bwd.perm) if ctx.has_w else None,
-                                                    _ptr(grad), _ptr(ctx.arg), _ptr(gx), g.N, K, _stream(dev)),
+                                                    _ptr(grad), _ptr(ctx.arg), _ptr(gx), g.n_src, K, _stream(dev)),
                            'spmm_max_bwd')
             else:
                 if ctx.reduce == _lib.GGL_MEAN:
                     if grad.dtype != torch.float32:
                         raise _lib.GglError('gspmm(mean) backward is float32 only')
                     scaled = torch.empty_like(grad)
-                    _lib.check(lib.gglb200_scale_rows_by_count(_ptr(grad), _ptr(g.fwd.rowptr), _ptr(scaled), g.N, K,
+                    _lib.check(lib.gglb200_scale_rows_by_count(_ptr(grad), _ptr(g.fwd.rowptr), _ptr(scaled), g.n_dst, K,
                                                                _stream(dev)), 'scale_rows_by_count')
                     grad = scaled
                 gx, _ = spmm_csr(g.bwd, g.bwd.col, grad, _lib.GGL_SUM, w=weight, wperm=g.bwd.perm if ctx.has_w else None)
+        return None, None, gx.view(ctx.x_shape), None, None
+
+
+class _SpMMMaxEdge(torch.autograd.Function):
+    """max over in-edges of w[e] * x[src[e]] with the winning EDGE recorded -- `message` + `unsorted_segment_max`
+    (message_passing.py:56-59,88-90; src/segment_max.cpp:37-61) as one kernel, no [E,K] message tensor.  Differs from
+    c_spmm_max only in the backward on multigraphs: one edge per (dst, k) receives the gradient (the first maximal edge,
+    like segment_max's arg), not every parallel edge of the winning source (cpu/spmm_max_cpu.cpp:84-96)."""
+
+    @staticmethod
+    def forward(ctx, index, weight, x, n_dst=None):
+        lib = _lib.load()
+        _check_spmm_args(index, weight, x)
+        E = index.shape[1]
+        if weight is not None and weight.numel() != E:
+            raise ValueError('weight must have num_edges elements')
+        x = x.contiguous()
+        weight = weight.contiguous().view(-1) if weight is not None else None
+        n_src = x.shape[0]
+        n_dst = n_src if n_dst is None else int(n_dst)
+        g = graph_of(index, n_dst, n_src)
+        c = g.fwd
+        x2d = x.view(n_src, -1)
+        K = x2d.shape[1]
+        dev = x.device
+        with torch.cuda.device(dev):
+            _lib.tune_device(dev.index)
+            c.use_on_current_stream()
+            out = torch.empty((n_dst, K), dtype=x.dtype, device=dev)
+            arg = torch.empty((n_dst, K), dtype=torch.int64, device=dev)
+            ws, nb = c.workspace(K, _lib.GGL_MAX)
+            _lib.check(lib.gglb200_spmm_csr_max_edge(_ptr(c.rowptr), _ptr(c.col), _ptr(c.perm), _ptr(c.plan), _ptr(weight), _ptr(x2d),
+                                                     _ptr(out), _ptr(arg), E, n_dst, n_src, E, K, _dtype_code(x2d), _ptr(ws), nb,
+                                                     _stream(dev)), 'spmm_csr_max_edge')
+        ctx.graph, ctx.arg, ctx.x_shape = g, arg, tuple(x.shape)
+        ctx.has_w = weight is not None
+        if weight is not None:
+            ctx.save_for_backward(weight)
+        ctx.mark_non_differentiable(arg)
+        return out.view((n_dst,) + tuple(x.shape[1:])), arg.view((n_dst,) + tuple(x.shape[1:]))
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_arg):
+        lib = _lib.load()
+        weight = ctx.saved_tensors[0] if ctx.has_w else None
+        g = ctx.graph
+        grad = grad_out.contiguous().view(g.n_dst, -1)
+        if grad.dtype != torch.float32:
+            raise _lib.GglError('gspmm_max_edge backward is float32 only')
+        K = grad.shape[1]
+        dev = grad.device
+        with torch.cuda.device(dev):
+            t = g.bwd
+            t.use_on_current_stream()
+            gx = torch.empty((g.n_src, K), dtype=grad.dtype, device=dev)
+            _lib.check(lib.gglb200_spmm_max_edge_bwd(_ptr(t.rowptr), _ptr(t.col), _ptr(t.perm), _ptr(weight), _ptr(grad), _ptr(ctx.arg),
+                                                     _ptr(gx), g.n_src, K, _stream(dev)), 'spmm_max_edge_bwd')
         return None, None, gx.view(ctx.x_shape), None
 
 
@@ -309,16 +368,25 @@ class _BSpMM(torch.autograd.Function):
         return None, gw, gx
 
 
-def c_spmm_sum(index, weight, x):
-    return _SpMM.apply(index, weight, x, _lib.GGL_SUM)
+def c_spmm_sum(index, weight, x, num_dst=None):
+    return _SpMM.apply(index, weight, x, _lib.GGL_SUM, num_dst)
 
 
-def c_spmm_mean(index, weight, x):
-    return _SpMM.apply(index, weight, x, _lib.GGL_MEAN)
+def c_spmm_mean(index, weight, x, num_dst=None):
+    return _SpMM.apply(index, weight, x, _lib.GGL_MEAN, num_dst)
 
 
-def c_spmm_max(index, weight, x):
-    return _SpMM.apply(index, weight, x, _lib.GGL_MAX)
+def c_spmm_max(index, weight, x, num_dst=None):
+    return _SpMM.apply(index, weight, x, _lib.GGL_MAX, num_dst)
+
+
+def gspmm_max_edge(index, weight=None, x=None, num_dst=None, return_arg=False):
+    """Fused `message` + `unsorted_segment_max`: out[dst] = max over in-edges of weight[e] * x[src[e]] (empty rows =
+    lowest(), like the compiled reference extension), the gradient credits the first maximal EDGE only.  This is what
+    SAGEConv(aggr='pool') and aggr='max' layers compute (sage_conv.py:89-92), without the [E, K] message tensor.
+    return_arg: also return the int64 [num_dst, ...] original edge ids of the winners (E for empty rows)."""
+    out, arg = _SpMMMaxEdge.apply(index, weight, x, num_dst)
+    return (out, arg) if return_arg else out
 
 
 def c_bspmm_sum(index, weight, x):
@@ -400,20 +468,37 @@ def gcn_propagate(edge_index, x, norm='both', bias=None, relu=False):
     return _GcnPropagate.apply(x, edge_index, norm, bias, relu)
 
 
+# The unfused decomposition (`message` -> [E, K] tensor -> segment reduce) exists for call shapes no fused kernel covers
+# (differentiable weights under mean / max, user-defined message functions).  At ogbn-products scale that tensor is 49.5 GB:
+# refuse instead of silently allocating it (GGLB200_MAX_MESSAGE_BYTES raises or lowers the bar; 0 disables the check).
+MAX_MESSAGE_BYTES = int(os.environ.get('GGLB200_MAX_MESSAGE_BYTES', str(8 << 30)))
+
+
+def check_message_bytes(num_edges, row_numel, elem_size, what):
+    need = int(num_edges) * int(row_numel) * int(elem_size)
+    if MAX_MESSAGE_BYTES and need > MAX_MESSAGE_BYTES:
+        raise _lib.GglError('%s would materialise a [%d, %d] message tensor (%.1f GB > GGLB200_MAX_MESSAGE_BYTES = %.1f GB): '
+                            'this call shape has no fused kernel; use fixed (non-differentiable) edge weights, aggr sum / mean / '
+                            'max on 2-D features, or raise the limit' % (what, num_edges, row_numel, need / 1e9, MAX_MESSAGE_BYTES / 1e9))
+
+
 def weight_needs_grad(weight):
     """True when autograd must reach an edge weight: gspmm cannot provide that gradient (no grad for weight in the reference
     operator either, src/gspmm.cpp:30,79), the callers then use bspmm (sum) or the message + aggregate decomposition."""
     return weight is not None and weight.requires_grad and torch.is_grad_enabled()
 
 
-def gspmm(index, weight=None, x=None, reduce='sum'):
-    """Generalized SpMM: out[dst] (+|mean|max)= weight[e] * x[src]  (torch.py:302-351)."""
+def gspmm(index, weight=None, x=None, reduce='sum', num_dst=None):
+    """Generalized SpMM: out[dst] (+|mean|max)= weight[e] * x[src]  (torch.py:302-351).
+    num_dst (extension; None = x.shape[0] like the reference): output rows of a bipartite block whose sources are the
+    rows of x -- SAGEConv's (src_feat, dst_feat) call and sampled mini-batch blocks run fused instead of materialising
+    the [E, K] message."""
     if reduce == 'sum':
-        return c_spmm_sum(index, weight, x)
+        return c_spmm_sum(index, weight, x, num_dst)
     elif reduce == 'mean':
-        return c_spmm_mean(index, weight, x)
+        return c_spmm_mean(index, weight, x, num_dst)
     elif reduce == 'max':
-        return c_spmm_max(index, weight, x)
+        return c_spmm_max(index, weight, x, num_dst)
     raise Exception("Unsupported reduce type, please choose from ['sum', 'mean', 'max'].")
 
 
@@ -566,4 +651,5 @@ def segment_softmax(data, segment_ids, num_segments):
 
 __all__ = ['use_ext', 'unsorted_segment_sum', 'unsorted_segment_mean', 'unsorted_segment_max', 'segment_sum',
            'segment_mean', 'segment_max', 'gspmm', 'bspmm', 'c_segment_sum', 'c_segment_mean', 'c_segment_max',
-           'c_spmm_sum', 'c_spmm_mean', 'c_spmm_max', 'c_bspmm_sum', 'segment_softmax', 'gcn_propagate', 'gat_aggregate']
+           'c_spmm_sum', 'c_spmm_mean', 'c_spmm_max', 'c_bspmm_sum', 'segment_softmax', 'gcn_propagate', 'gat_aggregate',
+           'gspmm_max_edge']

@@ -52,21 +52,30 @@ def _cuda_or_original(new, old):
 
 
 def _fused_message_aggregate(self, x, edge_index, edge_weight=None, aggr='sum', num_nodes=None):
-    """Fused gather x weight -> reduce.  Falls back to the reference's own decomposition (still on the B200 segment
-    operators) for bipartite calls, where gspmm's output row count (= x rows) would be wrong, and for aggr='max'."""
-    differentiable_w = mpops.weight_needs_grad(edge_weight)
-    if differentiable_w and aggr == 'sum' and x.dim() == 2 and edge_weight.dim() == 1 and (num_nodes is None or num_nodes == x.shape[0]):
-        # the reference layer's message * weight is differentiable in the weight, gspmm is not (src/gspmm.cpp:30,79):
-        # one-head bspmm = the same forward kernel + the SDDMM weight gradient
-        return mpops.bspmm(edge_index, edge_weight.reshape(-1, 1), x.unsqueeze(1), 'sum').squeeze(1)
-    if (num_nodes is not None and num_nodes != x.shape[0]) or aggr == 'max' or (differentiable_w and not (edge_weight.dim() == 2 and x.dim() == 3)):
-        # max: message + unsorted_segment_max credits the first winning edge only, gspmm-max every parallel edge of the winning
-        # source (cpu/spmm_max_cpu.cpp:84-96) -- the layer keeps the reference layer's gradients on multigraphs
-        msg = self.message(x, edge_index, edge_weight) if edge_weight is not None else self.message(x, edge_index)
-        return self.aggregate(msg, edge_index, num_nodes=num_nodes, aggr=aggr)
-    if edge_weight is not None and edge_weight.dim() == 2 and x.dim() == 3:
+    """Fused gather x weight -> reduce for the call shapes of the reference layers:
+      [N,K] x, 1-D / no weights, sum | mean    -> gspmm (bipartite calls: num_dst = num_nodes output rows)
+      [N,K] x, 1-D / no weights, max           -> gspmm_max_edge (winning EDGE recorded: the gradient of message +
+                                                   unsorted_segment_max, src/segment_max.cpp:48-61, on multigraphs too)
+      [N,H,C] x, [E,H] weights, sum            -> bspmm (gradient for the weights through the SDDMM kernel)
+      differentiable 1-D weights, sum          -> one-head bspmm (gspmm has no weight gradient, src/gspmm.cpp:30,79)
+    Anything else runs the reference's own decomposition on the B200 segment operators, size-guarded: the [E,K] message
+    is refused above GGLB200_MAX_MESSAGE_BYTES instead of being allocated silently."""
+    w_grad = mpops.weight_needs_grad(edge_weight)
+    square = num_nodes is None or num_nodes == x.shape[0]
+    per_head = edge_weight is not None and edge_weight.dim() == 2 and x.dim() == 3
+    if per_head and square and aggr == 'sum':
         return mpops.bspmm(edge_index, edge_weight, x, aggr)
-    return mpops.gspmm(edge_index, edge_weight, x, aggr)
+    if w_grad and aggr == 'sum' and x.dim() == 2 and edge_weight.dim() == 1 and square:
+        return mpops.bspmm(edge_index, edge_weight.reshape(-1, 1), x.unsqueeze(1), 'sum').squeeze(1)
+    if not w_grad and not per_head and (edge_weight is None or edge_weight.dim() == 1):
+        if aggr == 'max':
+            return mpops.gspmm_max_edge(edge_index, edge_weight, x, num_dst=num_nodes)
+        if aggr in ('sum', 'mean'):
+            return mpops.gspmm(edge_index, edge_weight, x, aggr, num_dst=num_nodes)
+    mpops.check_message_bytes(edge_index.shape[1], x[0].numel() if x.dim() > 1 else 1, x.element_size(),
+                              '%s.message_aggregate(aggr=%r)' % (type(self).__name__, aggr))
+    msg = self.message(x, edge_index, edge_weight) if edge_weight is not None else self.message(x, edge_index)
+    return self.aggregate(msg, edge_index, num_nodes=num_nodes, aggr=aggr)
 
 
 # MessagePassing.__init__ registers the method with Inspector.inspect(), which files the signature under func.__name__

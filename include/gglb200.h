@@ -182,6 +182,20 @@ GGL_API int    gglb200_spmm_csr(int reduce,
                         int64_t n_rows, int64_t n_src, int64_t E, int64_t K, int dtype,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* MAX with the winning EDGE recorded: the fused form of `message` + `unsorted_segment_max` (message_passing.py:56-59,
+ * 88-90; src/segment_max.cpp:37-61) that SAGEConv(aggr='pool') and every aggr='max' layer run -- without the [E,K]
+ * message tensor.  out[r,k] = max_i w[perm[i]] * x[col[i],k] exactly like gglb200_spmm_csr(GGL_MAX), but
+ * arg_eid[r,k] = perm[i*] = the ORIGINAL edge id of the first maximal edge (ascending edge id, strict <; arg_empty for rows
+ * without edges).  Backward on the transposed CSR (rows = source): gx[s,k] = sum over out-edges e = (s -> d) with
+ * arg_eid[d,k] == e of w[e] * g[d,k] -- one edge per (d,k), so parallel edges are NOT double counted (the gradient of
+ * the reference's layers on multigraphs). */
+GGL_API int gglb200_spmm_csr_max_edge(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const int32_t* plan,
+                              const float* w, const void* x, void* out, int64_t* arg_eid, int64_t arg_empty,
+                              int64_t n_rows, int64_t n_src, int64_t E, int64_t K, int dtype, void* workspace,
+                              size_t workspace_bytes, void* stream);
+GGL_API int gglb200_spmm_max_edge_bwd(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* perm_t, const float* w,
+                              const float* g, const int64_t* arg_eid, float* gx, int64_t n_rows, int64_t K, void* stream);
+
 /* Multi-GPU variant (1-D node partition): the same kernel with x spread over the GPUs of one node.
  * x_table is a DEVICE array of P base pointers (x shard of every rank, mapped into this process: CUDA IPC /
  * symmetric memory; all shards [rows_r, K] with the same K and dtype) and col[i] = owner << owner_shift | local_row.

@@ -80,12 +80,8 @@ def test_sage_conv(aggr):
     from gammagl_b200.layers import SAGEConv
     N, E, F, H = 250, 3000, 24, 12
     ei = graph(N, E, 3)[:, :E] if aggr == 'gcn' else graph(N, E, 3)
-    if aggr == 'pool':
-        # duplicate (src,dst) pairs: the reference's gspmm-max backward credits EVERY parallel edge of the winning
-        # source (cpu/spmm_max_cpu.cpp:84-96) while segment_max credits the first edge only -- both are reproduced
-        # exactly, so the gspmm-max form (fuse_max=True) and the layer's default message + segment_max form agree only
-        # on a coalesced graph.
-        ei = torch.unique(ei, dim=1)
+    # aggr == 'pool' runs on the multigraph as generated (duplicate (src, dst) pairs included): the fused max records the
+    # winning EDGE (mpops.gspmm_max_edge), so its gradients equal message + unsorted_segment_max there as well
     if aggr == 'gcn':
         ei[0, 0] = N - 1          # the layer sizes the graph by 1 + max(src) (sage_conv.py:84-86)
     x = torch.randn(N, F, generator=torch.Generator().manual_seed(4))

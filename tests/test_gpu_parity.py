@@ -246,7 +246,10 @@ def test_segment_max_arg_indices_bit_exact(mp):
 
 
 @pytest.mark.parametrize('N,E,H,C,hub', [(2000, 40000, 8, 8, 0), (1500, 30000, 8, 64, 1500), (900, 9000, 4, 16, 0),
-                                          (500, 6000, 3, 5, 0), (700, 8000, 1, 32, 1200), (400, 5000, 2, 128, 0)])
+                                          (500, 6000, 3, 5, 0), (700, 8000, 1, 32, 1200), (400, 5000, 2, 128, 0),
+                                          # head widths that are not a multiple of the 16-byte lane: lanes span two heads
+                                          (1200, 30000, 4, 25, 0), (1200, 30000, 4, 25, 2500), (800, 12000, 3, 12, 0),
+                                          (800, 12000, 6, 7, 1500), (600, 9000, 5, 6, 0), (600, 9000, 2, 50, 0)])
 def test_bspmm_vs_oracle(mp, N, E, H, C, hub):
     index = make_graph(N, E, seed=H * 100 + C, hub=hub)
     g = torch.Generator().manual_seed(13)
@@ -421,3 +424,81 @@ def test_sparse_structures_vs_oracle(mp):
     assert np.array_equal(val.cpu().numpy()[sg.csr2csc().cpu().numpy()], w.numpy()[corder])
     reft, _ = O.spmm_fwd('sum', index.numpy(), w.numpy(), h.numpy())       # transposed: out[col] += w * h[row]
     assert rel_err(sg.t().matmul(cu(h)).cpu().numpy(), reft) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------
+# bipartite blocks and the fused max with the winning edge recorded
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('reduce', ['sum', 'mean', 'max'])
+@pytest.mark.parametrize('Ns,Nd,E,K,hub', [(3000, 700, 40000, 100, 2000), (500, 2500, 20000, 32, 0), (900, 900, 15000, 47, 0)])
+def test_gspmm_bipartite_rows(mp, reduce, Ns, Nd, E, K, hub):
+    """gspmm(..., num_dst=Nd): x holds the Ns source rows, the output the Nd destination rows (SAGEConv's (src, dst) call,
+    sage_conv.py:75-92; sampled blocks).  Oracle: message + segment reduce over Nd (what the reference layer computes)."""
+    g = torch.Generator().manual_seed(Ns + Nd)
+    ei = torch.stack([torch.randint(0, Ns, (E,), generator=g), torch.randint(0, Nd, (E,), generator=g)])
+    if hub:
+        ei[1, :hub] = 5
+    x = torch.randn(Ns, K, generator=g)
+    w = torch.rand(E, generator=g)
+    gout = torch.randn(Nd, K, generator=g)
+    xx = x.to(DEV).requires_grad_(True)
+    out = mp.gspmm(ei.to(DEV), w.to(DEV), xx, reduce, num_dst=Nd)
+    assert tuple(out.shape) == (Nd, K)
+    out.backward(gout.to(DEV))
+    msg = (x * 1.0)[ei[0]].numpy() * w.numpy()[:, None]
+    short = np.bincount(ei[1].numpy(), minlength=Nd) <= 1024
+    got = out.detach().cpu().numpy()
+    if reduce == 'max':
+        ref, arg = O.segment('max', msg, ei[1].numpy(), Nd)
+        assert np.array_equal(got, ref)
+        # gspmm-max credits every edge (s -> d) whose SOURCE won (cpu/spmm_max_cpu.cpp:84-96)
+        nonempty = np.bincount(ei[1].numpy(), minlength=Nd) > 0
+        src_win = np.where(nonempty[:, None], ei[0].numpy()[np.minimum(arg, E - 1)], -1)
+        gx = np.zeros((Ns, K))
+        s_np, d_np = ei[0].numpy(), ei[1].numpy()
+        hit = src_win[d_np] == s_np[:, None]
+        np.add.at(gx, s_np, np.where(hit, w.numpy()[:, None].astype(np.float64) * gout.numpy()[d_np], 0.0))
+        assert rel_err(xx.grad.cpu().numpy(), gx) < 1e-5
+    else:
+        ref = O.segment(reduce, msg, ei[1].numpy(), Nd) if reduce == 'sum' else None
+        if reduce == 'sum':
+            assert np.array_equal(got[short], ref[short])
+            assert rel_err(got, ref) < 1e-5
+            gm = gout.numpy()[ei[1].numpy()].astype(np.float64)
+        else:
+            cnt = np.maximum(np.bincount(ei[1].numpy(), minlength=Nd), 1).astype(np.float64)
+            sm = np.zeros((Nd, K))
+            np.add.at(sm, ei[1].numpy(), msg.astype(np.float64))
+            assert rel_err(got, sm / cnt[:, None]) < 1e-5
+            gm = (gout.numpy() / cnt[:, None])[ei[1].numpy()]
+        gx = np.zeros((Ns, K))
+        np.add.at(gx, ei[0].numpy(), gm * w.numpy()[:, None].astype(np.float64))
+        assert rel_err(xx.grad.cpu().numpy(), gx) < 1e-5
+
+
+@pytest.mark.parametrize('weighted', [False, True])
+@pytest.mark.parametrize('Ns,Nd,E,K,hub', [(1500, 1500, 30000, 64, 3000), (2000, 300, 25000, 100, 0), (400, 400, 6000, 3, 0),
+                                           (300, 900, 8000, 16, 1200)])
+def test_gspmm_max_edge_is_message_plus_segment_max(mp, weighted, Ns, Nd, E, K, hub):
+    """Fused max with the winning EDGE recorded == `message` + `unsorted_segment_max` of the reference (values, int64 edge
+    ids and gradients bit-exact), on a MULTIGRAPH with ties: integer-valued features, duplicated edges."""
+    g = torch.Generator().manual_seed(7 * Ns + K)
+    ei = torch.stack([torch.randint(0, Ns, (E,), generator=g), torch.randint(0, Nd, (E,), generator=g)])
+    ei[:, E // 2:E // 2 + E // 8] = ei[:, :E // 8]                        # parallel edges
+    if hub:
+        ei[1, :hub] = 2
+    x = torch.randint(-4, 5, (Ns, K), generator=g).float()                # ties everywhere
+    w = (torch.randint(1, 4, (E,), generator=g).float() * 0.5) if weighted else None
+    gout = torch.randn(Nd, K, generator=g)
+    xx = x.to(DEV).requires_grad_(True)
+    out, arg = mp.gspmm_max_edge(ei.to(DEV), None if w is None else w.to(DEV), xx, num_dst=Nd, return_arg=True)
+    out.backward(gout.to(DEV))
+    msg = x.numpy()[ei[0].numpy()] * (w.numpy()[:, None] if weighted else 1.0)
+    ref, arg_ref = O.segment('max', msg.astype(np.float32), ei[1].numpy(), Nd)
+    assert np.array_equal(out.detach().cpu().numpy(), ref)
+    nonempty = np.bincount(ei[1].numpy(), minlength=Nd) > 0
+    assert np.array_equal(arg.cpu().numpy(), np.where(nonempty[:, None], arg_ref, E))   # empty rows: the oracle's sentinel is N, ours E
+    gm = O.segment_bwd('max', gout.numpy(), ei[1].numpy(), E, arg_ref)
+    gx = np.zeros((Ns, K), dtype=np.float64)
+    np.add.at(gx, ei[0].numpy(), gm.astype(np.float64) * (w.numpy()[:, None] if weighted else 1.0))
+    assert rel_err(xx.grad.cpu().numpy(), gx) < 1e-6

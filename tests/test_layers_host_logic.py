@@ -40,11 +40,43 @@ def seg_max(x, ids, n=None):
     return out.scatter_reduce(0, _bshape(ids, x), x, 'amax', include_self=True)
 
 
-def gspmm(index, weight=None, x=None, reduce='sum'):
+def gspmm(index, weight=None, x=None, reduce='sum', num_dst=None):
     msg = x[index[0]]
     if weight is not None:
         msg = msg * weight.detach().reshape((-1,) + (1,) * (x.dim() - 1))     # no gradient for the weight (src/gspmm.cpp:30,79)
-    return {'sum': seg_sum, 'mean': seg_mean, 'max': seg_max}[reduce](msg, index[1], x.shape[0])
+    return {'sum': seg_sum, 'mean': seg_mean, 'max': seg_max}[reduce](msg, index[1], x.shape[0] if num_dst is None else num_dst)
+
+
+class _FirstEdgeMax(torch.autograd.Function):
+    """message + unsorted_segment_max with the reference's gradient: the FIRST maximal edge of (dst, k) gets it."""
+
+    @staticmethod
+    def forward(ctx, msg, ids, n):
+        E = msg.shape[0]
+        out = torch.full((n,) + tuple(msg.shape[1:]), torch.finfo(msg.dtype).min, dtype=msg.dtype)
+        arg = torch.full(out.shape, E, dtype=torch.int64)
+        for e in range(E):                                                      # serial loop of cpu/segment_max_cpu.cpp:54-62
+            r = int(ids[e])
+            better = out[r] < msg[e]
+            out[r] = torch.where(better, msg[e], out[r])
+            arg[r] = torch.where(better, torch.full_like(arg[r], e), arg[r])
+        ctx.save_for_backward(arg)
+        ctx.E = E
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        gm = torch.zeros((ctx.E + 1,) + tuple(g.shape[1:]), dtype=g.dtype)
+        gm.scatter_(0, arg, g)
+        return gm[:-1], None, None
+
+
+def gspmm_max_edge(index, weight=None, x=None, num_dst=None, return_arg=False):
+    msg = x[index[0]]
+    if weight is not None:
+        msg = msg * weight.detach().reshape((-1,) + (1,) * (x.dim() - 1))
+    return _FirstEdgeMax.apply(msg, index[1], x.shape[0] if num_dst is None else num_dst)
 
 
 def bspmm(index, weight=None, x=None, reduce='sum'):
@@ -82,7 +114,7 @@ def gat_aggregate(edge_index, x, s_src, s_dst, negative_slope=0.2):
 @pytest.fixture()
 def host(monkeypatch):
     for name, fn in (('unsorted_segment_sum', seg_sum), ('unsorted_segment_mean', seg_mean), ('unsorted_segment_max', seg_max),
-                     ('gspmm', gspmm), ('bspmm', bspmm), ('segment_softmax', segment_softmax), ('gcn_propagate', gcn_propagate),
+                     ('gspmm', gspmm), ('gspmm_max_edge', gspmm_max_edge), ('bspmm', bspmm), ('segment_softmax', segment_softmax), ('gcn_propagate', gcn_propagate),
                      ('gat_aggregate', gat_aggregate)):
         monkeypatch.setattr(mpops, name, fn)
     monkeypatch.setattr(L, 'degree', lambda index, num_nodes=None, dtype=torch.float32:
@@ -138,9 +170,11 @@ def test_layer_mirror_reproduces_reference_layer(host, tag, fused):
 
 
 def test_routing_of_propagate(host):
-    """sum / mean fuse; max keeps message + segment_max unless fuse_max; a weight that needs grad is never dropped."""
+    """sum / mean / max fuse (max through the edge-id form, bipartite calls through num_dst); a weight that needs grad is never
+    dropped: sum goes to bspmm, everything else to the size-guarded decomposition."""
     calls = []
-    real = {k: getattr(mpops, k) for k in ('gspmm', 'bspmm', 'unsorted_segment_max', 'unsorted_segment_sum', 'unsorted_segment_mean')}
+    names = ('gspmm', 'gspmm_max_edge', 'bspmm', 'unsorted_segment_max', 'unsorted_segment_sum', 'unsorted_segment_mean')
+    real = {k: getattr(mpops, k) for k in names}
     for k, f in real.items():
         setattr(mpops, k, (lambda k, f: lambda *a, **kw: (calls.append(k), f(*a, **kw))[1])(k, f))
     try:
@@ -148,20 +182,31 @@ def test_routing_of_propagate(host):
         ei = torch.tensor([[0, 1, 2, 2, 3], [1, 2, 1, 0, 3]])
         x = torch.arange(8, dtype=torch.float32).reshape(4, 2)
         w = torch.rand(5)
-        for aggr, want in (('sum', 'gspmm'), ('mean', 'gspmm'), ('max', 'unsorted_segment_max')):
+        for aggr, want in (('sum', 'gspmm'), ('mean', 'gspmm'), ('max', 'gspmm_max_edge')):
             calls.clear()
             mp.propagate(x, ei, aggr=aggr, edge_weight=w)
             assert calls == [want], (aggr, calls)
-        mp.fuse_max = True
-        calls.clear(); mp.propagate(x, ei, aggr='max'); assert calls == ['gspmm']
         mp.fuse_max = False
+        calls.clear(); mp.propagate(x, ei, aggr='max'); assert calls == ['unsorted_segment_max']
+        mp.fuse_max = True
         wg = w.clone().requires_grad_(True)
         calls.clear(); out = mp.propagate(x, ei, edge_weight=wg); assert calls == ['bspmm']
         out.sum().backward(); assert wg.grad is not None and float(wg.grad.abs().sum()) > 0
         calls.clear(); mp.propagate(x, ei, edge_weight=wg, aggr='mean'); assert calls == ['unsorted_segment_mean']
+        calls.clear(); mp.propagate(x, ei, edge_weight=wg, aggr='max'); assert calls == ['unsorted_segment_max']
         with torch.no_grad():
             calls.clear(); mp.propagate(x, ei, edge_weight=wg); assert calls == ['gspmm']
-        calls.clear(); mp.propagate(x, ei, num_nodes=6); assert calls == ['unsorted_segment_sum']      # bipartite: no fusion
+        calls.clear(); o6 = mp.propagate(x, ei, num_nodes=6); assert calls == ['gspmm'] and o6.shape[0] == 6   # bipartite: fused, 6 rows
+        calls.clear(); o6 = mp.propagate(x, ei, num_nodes=6, aggr='max'); assert calls == ['gspmm_max_edge'] and o6.shape[0] == 6
+        calls.clear(); mp.propagate(x, ei, num_nodes=6, edge_weight=wg); assert calls == ['unsorted_segment_sum']   # bspmm is square-only
+        # the decomposition is size-guarded: a message above the limit raises instead of being allocated
+        old = mpops.MAX_MESSAGE_BYTES
+        mpops.MAX_MESSAGE_BYTES = 16
+        try:
+            with pytest.raises(Exception, match='message tensor'):
+                mp.propagate(x, ei, edge_weight=wg, aggr='mean')
+        finally:
+            mpops.MAX_MESSAGE_BYTES = old
         # reference KAT (tests/layers/conv/test_message_passing.py:12-24)
         assert mp.propagate(x, ei, aggr='sum').tolist() == [[4.0, 5.0], [4.0, 6.0], [2.0, 3.0], [6.0, 7.0]]
         assert mp.propagate(x, ei, aggr='mean').tolist() == [[4.0, 5.0], [2.0, 3.0], [2.0, 3.0], [6.0, 7.0]]

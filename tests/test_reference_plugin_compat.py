@@ -31,10 +31,21 @@ def ref():
     from gammagl_b200 import mpops as b200_mpops, plugin
     ref_mpops = sys.modules['gammagl.mpops']
 
+    def ref_gspmm(index, weight=None, x=None, reduce='sum', num_dst=None):
+        assert num_dst is None or num_dst == x.shape[0]          # the reference operator is square-only
+        return ref_mpops.gspmm(index, weight, x, reduce)
+
+    def ref_gspmm_max_edge(index, weight=None, x=None, num_dst=None, return_arg=False):
+        # the semantics the fused kernel reproduces: message + unsorted_segment_max of the reference itself
+        msg = x[index[0]] if weight is None else x[index[0]] * weight.reshape((-1,) + (1,) * (x.dim() - 1))
+        return ref_mpops.unsorted_segment_max(msg, index[1], x.shape[0] if num_dst is None else num_dst)
+
     class RefOps:                                   # the reference's CPU operators in the role of gammagl_b200.mpops
-        gspmm = staticmethod(ref_mpops.gspmm)
+        gspmm = staticmethod(ref_gspmm)
+        gspmm_max_edge = staticmethod(ref_gspmm_max_edge)
         bspmm = staticmethod(ref_mpops.bspmm)
         weight_needs_grad = staticmethod(b200_mpops.weight_needs_grad)
+        check_message_bytes = staticmethod(b200_mpops.check_message_bytes)
     old = plugin.mpops
     plugin.mpops = RefOps
     yield G, L, plugin, sys.modules['tensorlayerx']
