@@ -180,6 +180,31 @@ def segment_csr_of(segment_ids, num_segments):
     return _segments.get(segment_ids, int(num_segments), lambda: build_csr(segment_ids, None, num_segments))
 
 
+# ids seen by the sort-free path: key -> number of sightings (the CSR is built from the second sighting on)
+_sightings = _Lru(int(_os.environ.get('GGLB200_SEGMENT_CACHE', '16')) * 4)
+
+
+def segment_csr_if_cached(segment_ids, num_segments):
+    """The cached CSR of these ids, or None (never builds)."""
+    if segment_ids.is_inference():
+        return None
+    hit = _segments.d.get(_Lru.key_of(segment_ids, int(num_segments)))
+    if hit is None:
+        return None
+    _segments.d.move_to_end(_Lru.key_of(segment_ids, int(num_segments)))
+    return hit[1]
+
+
+def note_sighting(segment_ids, num_segments):
+    """How many times (including this one) these very ids have been reduced without a CSR: 1 = first time."""
+    if segment_ids.is_inference():
+        return 1
+    box = _sightings.get(segment_ids, int(num_segments), lambda: [0])
+    box[0] += 1
+    return box[0]
+
+
 def clear_caches():
     _graphs.clear()
     _segments.clear()
+    _sightings.clear()

@@ -23,7 +23,7 @@ import os
 import torch
 
 from . import _lib
-from .csr import _ptr, _stream, graph_of, require_cuda, segment_csr_of
+from .csr import _ptr, _stream, graph_of, note_sighting, require_cuda, segment_csr_if_cached, segment_csr_of
 
 use_ext = True  # mirrors the module flag of the reference (torch.py:2-7); always the native path here
 PROFILE = None  # bench.py sets this to a list: spmm_csr then appends (n_rows, start_event, end_event) per launch
@@ -97,6 +97,61 @@ _SEG_BWD = os.environ.get('GGLB200_SEG_BWD', 'auto')
 _SEG_BWD_L2_BYTES = 64 << 20
 
 
+# Which path reduces an unsorted segment op (fp32; other dtypes always take the CSR path):
+#   csr      sort the ids once (cached per ids tensor), then gather x[perm[i]] per pass: fp32 sums bit-identical to the
+#            reference's serial CPU loop
+#   oneshot  sort-free streaming pass with L2 reductions (csrc/oneshot.cu): no build, x read coalesced; max (+ arg) is
+#            bit-exact there too, fp32 sums / means depend on arrival order (rounding only, <= 1e-6 relative; exact for
+#            integer-valued data such as degree())
+# GGLB200_SEGMENT = auto (default) | fast | csr | oneshot.
+#   auto  rows of at most GGLB200_ONESHOT_ROW_BYTES (16: K <= 4 fp32 -- degree() and calc_gcn_norm() reduce K = 1 rows, whose
+#         permuted 4-byte gather wastes 7/8 of every DRAM sector) go one-shot for every reducer; max additionally goes
+#         one-shot the first time an ids tensor is seen (ids that change per step never pay the 6 ms sort) and builds the
+#         CSR from the second sighting on; wider sums / means stay on the bit-exact CSR path.
+#   fast  like auto, and sums / means of wider rows also go one-shot on the first sighting.
+# With torch.use_deterministic_algorithms(True) sums and means always take the CSR path.
+_SEGMENT_MODE = os.environ.get('GGLB200_SEGMENT', 'auto')
+_ONESHOT_ROW_BYTES = int(os.environ.get('GGLB200_ONESHOT_ROW_BYTES', '16'))
+
+
+def _segment_path(x, index, N, reduce):
+    if x.dtype != torch.float32 or _SEGMENT_MODE == 'csr' or x.shape[0] >= (1 << 32) - 1:
+        return 'csr'
+    if _SEGMENT_MODE == 'oneshot':
+        return 'oneshot'
+    exact = reduce == _lib.GGL_MAX
+    if not exact and torch.are_deterministic_algorithms_enabled():
+        return 'csr'
+    row_bytes = (x.numel() // max(x.shape[0], 1)) * x.element_size()
+    if row_bytes <= _ONESHOT_ROW_BYTES:
+        return 'oneshot'
+    if not exact and _SEGMENT_MODE != 'fast':
+        return 'csr'
+    if segment_csr_if_cached(index, N) is not None:
+        return 'csr'
+    return 'oneshot' if note_sighting(index, N) == 1 else 'csr'
+
+
+def segment_reduce_oneshot(x2d, ids, N, reduce):
+    """Launch gglb200_segment_reduce.  x2d [E, K] fp32 contiguous, ids [E] int64.  Returns (out, arg | None, cnt | None)."""
+    lib = _lib.load()
+    E, K = x2d.shape
+    dev = x2d.device
+    with torch.cuda.device(dev):
+        out = torch.empty((N, K), dtype=torch.float32, device=dev)
+        arg = torch.empty((N, K), dtype=torch.int64, device=dev) if reduce == _lib.GGL_MAX else None
+        cnt = torch.empty(N, dtype=torch.int32, device=dev) if reduce != _lib.GGL_SUM else None
+        n_bad = torch.empty(1, dtype=torch.int64, device=dev)
+        nb = lib.gglb200_segment_reduce_workspace_bytes(reduce, N, K)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev) if nb else None
+        _lib.check(lib.gglb200_segment_reduce(reduce, _ptr(x2d), _ptr(ids), _ptr(out), _ptr(arg), N, _ptr(cnt), _ptr(n_bad), E, K, N,
+                                              _lib.GGL_F32, _ptr(ws), nb, _stream(dev)), 'segment_reduce')
+        bad = int(n_bad.item())             # range errors are raised, never folded silently (one host sync, like the CSR build's)
+        if bad:
+            raise IndexError('index out of range: %d segment ids outside [0, %d)' % (bad, N))
+    return out, arg, cnt
+
+
 class _SegmentReduce(torch.autograd.Function):
     """SegmentSum / SegmentMean / SegmentMax (torch_ext/src/segment_{sum,mean,max}.cpp)."""
 
@@ -114,13 +169,26 @@ class _SegmentReduce(torch.autograd.Function):
             return torch.zeros(out_shape, dtype=x.dtype, device=x.device)
         ctx.empty = False
         E = x.shape[0]
-        csr = segment_csr_of(index, N)
         x2d = x.view(E, -1)
-        out, arg = spmm_csr(csr, csr.perm, x2d, reduce, want_arg=(reduce == _lib.GGL_MAX), arg_empty=N)
-        ctx.csr = csr
         ctx.index = index if index.dtype == torch.int64 and index.is_contiguous() else index.to(torch.int64).contiguous()
+        if _segment_path(x, index, N, reduce) == 'oneshot':
+            out, arg, cnt = segment_reduce_oneshot(x2d, ctx.index, N, reduce)
+            ctx.csr, ctx.cnt = None, cnt
+        else:
+            csr = segment_csr_of(index, N)
+            out, arg = spmm_csr(csr, csr.perm, x2d, reduce, want_arg=(reduce == _lib.GGL_MAX), arg_empty=N)
+            ctx.csr, ctx.cnt = csr, None
         ctx.arg = arg
         return out.view(out_shape)
+
+    @staticmethod
+    def _rowptr(ctx, dev):
+        """rowptr of the segments: the CSR's, or the prefix sum of the one-shot pass's counts."""
+        if ctx.csr is not None:
+            return ctx.csr.rowptr
+        rp = torch.zeros(ctx.N + 1, dtype=torch.int32, device=dev)
+        torch.cumsum(ctx.cnt, 0, out=rp[1:])
+        return rp
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -134,22 +202,24 @@ class _SegmentReduce(torch.autograd.Function):
         with torch.cuda.device(dev):
             gx = torch.empty(ctx.x_shape, dtype=g.dtype, device=dev)
             if ctx.reduce == _lib.GGL_MAX:
-                _lib.check(lib.gglb200_segment_max_bwd(_ptr(g), _ptr(ctx.arg), _ptr(ctx.csr.rowptr), _ptr(gx), E, ctx.N, K,
+                rowptr = _SegmentReduce._rowptr(ctx, dev)
+                _lib.check(lib.gglb200_segment_max_bwd(_ptr(g), _ptr(ctx.arg), _ptr(rowptr), _ptr(gx), E, ctx.N, K,
                                                        _dtype_code(g), _stream(dev)), 'segment_max_bwd')
             else:
                 reduce, c = ctx.reduce, ctx.csr
+                rowptr = _SegmentReduce._rowptr(ctx, dev) if reduce == _lib.GGL_MEAN else None
                 if reduce == _lib.GGL_MEAN and g.dtype == torch.float32:
                     # g[r] / count[r] once per segment row instead of once per message: same operands, same quotient
                     gs = torch.empty_like(g)
-                    _lib.check(lib.gglb200_scale_rows_by_count(_ptr(g), _ptr(c.rowptr), _ptr(gs), ctx.N, K, _stream(dev)),
+                    _lib.check(lib.gglb200_scale_rows_by_count(_ptr(g), _ptr(rowptr), _ptr(gs), ctx.N, K, _stream(dev)),
                                'scale_rows_by_count')
                     g, reduce = gs, _lib.GGL_SUM
-                if _SEG_BWD == 'expand' or (_SEG_BWD == 'auto' and g.numel() * g.element_size() > _SEG_BWD_L2_BYTES):
+                if c is not None and (_SEG_BWD == 'expand' or (_SEG_BWD == 'auto' and g.numel() * g.element_size() > _SEG_BWD_L2_BYTES)):
                     _lib.check(lib.gglb200_segment_expand_bwd(reduce, _ptr(g), _ptr(c.rowptr), _ptr(c.perm), _ptr(c.plan),
                                                               _ptr(gx), E, ctx.N, K, _dtype_code(g), _stream(dev)),
                                'segment_expand_bwd')
                 else:
-                    _lib.check(lib.gglb200_segment_gather_bwd(reduce, _ptr(g), _ptr(ctx.index), _ptr(c.rowptr),
+                    _lib.check(lib.gglb200_segment_gather_bwd(reduce, _ptr(g), _ptr(ctx.index), _ptr(rowptr),
                                                               _ptr(gx), E, K, _dtype_code(g), _stream(dev)),
                                'segment_gather_bwd')
         return gx, None, None, None

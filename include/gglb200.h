@@ -223,6 +223,22 @@ GGL_API int gglb200_gather_rows_peer(const void* const* x_table, int32_t owner_s
                              int64_t n, int64_t row_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Sort-free unsorted segment reduce (the role of mpops/torch_ext/cuda/segment_{sum,mean,max}_cuda.cu -- scalar atomicAdd /
+ * CAS loops there): ONE streaming pass over x[E,K] in its original order, reductions resolved by the L2.
+ *   SUM   vector reductions (red.global.add.v4.f32); fp32 sums differ from the serial loop by rounding only (exact for
+ *         integer-valued data, e.g. degree() = unsorted_segment_sum(ones), utils/degree.py:35-40)
+ *   MEAN  SUM, cnt[N] (int32 out, required), rows with cnt > 1 divided (cpu/segment_mean_cpu.cpp:67-76)
+ *   MAX   bit-exact and deterministic incl. arg[N,K] (first maximal edge, cpu/segment_max_cpu.cpp:54-62); cnt required;
+ *         workspace = gglb200_segment_reduce_workspace_bytes(GGL_MAX, N, K)
+ * ids outside [0,N) are skipped and counted in *n_bad (device int64, may be NULL).  float32 only.  Use the CSR path
+ * (gglb200_csr_build + gglb200_spmm_csr(col = perm)) when the same ids are reduced again and again.
+ * ------------------------------------------------------------------------------------------- */
+GGL_API size_t gglb200_segment_reduce_workspace_bytes(int reduce, int64_t N, int64_t K);
+GGL_API int gglb200_segment_reduce(int reduce, const void* x, const int64_t* ids, void* out, int64_t* arg, int64_t arg_empty,
+                           int32_t* cnt, int64_t* n_bad, int64_t E, int64_t K, int64_t N, int dtype, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Backward helpers of the segment ops (src/segment_sum.cpp:43-54, src/segment_mean.cpp:44-63,
  * src/segment_max.cpp:48-61).
  *   gather:  gx[e, k] = g[ids[e], k]            (SUM)
