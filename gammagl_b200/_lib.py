@@ -41,6 +41,7 @@ SIGNATURES = {
     'gglb200_spmm_max_edge_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     'gglb200_segment_reduce_workspace_bytes': (_sz, [_int, _i64, _i64]),
     'gglb200_segment_reduce': (_int, [_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _int, _vp, _sz, _vp]),
+    'gglb200_linear_tf32x3': (_int, [_vp, _vp, _vp, _int, _vp, _i64, _i64, _i64, _vp]),
     'gglb200_gather_rows_peer': (_int, [_vp, _i32, _vp, _vp, _i64, _i64, _vp]),
     'gglb200_scale_rows': (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
     'gglb200_degree_power': (_int, [_vp, _vp, _i64, _c.c_float, _vp]),

@@ -1,0 +1,216 @@
+// linear_tc.cu -- the dense feature x weight GEMM next to the aggregation on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+//   out[M, N] = act( A[M, K] @ W[K, N] + bias[N] )            fp32 in, fp32 out, act = identity | ReLU
+//
+// This is the Linear of GCNConv / SAGEConv / GINConv (/root/reference/gammagl/layers/conv/gcn_conv.py:79, sage_conv.py:80,
+// gin_conv.py:57; tlx.layers.Linear = torch matmul on fp32 SIMT cores in the reference) applied to the aggregated rows when a
+// layer aggregates first (F_in < F_out: `GCNConv(aggregate_first)`), with the bias + ReLU epilogue of gcn_conv.py:104-106 fused.
+// A is the [N_nodes, F_in] output of the aggregation kernel, so F_in is small (100 / 128): the whole K extent of a 128-row tile
+// lives in shared memory at once and the kernel is bound by reading A and writing out, not by math.
+//
+// fp32 accuracy on TF32 tensor cores (3xTF32): a = a_hi + a_lo with a_hi = a truncated to TF32 (top 19 bits) and a_lo = a - a_hi
+// (exact), likewise w; D = a_hi.w_hi + a_hi.w_lo + a_lo.w_hi in the fp32 TMEM accumulator.  The dropped a_lo.w_lo term and the
+// truncation of the lo parts are O(2^-21) relative: parity with the fp32 reference at 1e-5 is tested, plain TF32 (2^-11) would
+// not pass it.
+//
+// Layout / instructions (cta_group::1, one CTA per 128 output rows, 256 threads):
+//   * operands in the canonical NO-SWIZZLE K-major layout of tcgen05 shared-memory descriptors: 8-row x 16-byte core matrices;
+//     element (r, k) of a [R, K] operand sits at  (k / 4) * R * 16  +  r * 16  +  (k % 4) * 4   (K-chunk stride LBO = 16 R,
+//     8-row-group stride SBO = 128).  Threads write A_hi/A_lo (lane <-> row: conflict-free 16-byte stores) and, per 64-column
+//     chunk of the output, W_hi/W_lo transposed to [n, k];
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (UTCMMA; M = 128, N = 64, K = 8 per instruction), three per
+//     K step, accumulating into TMEM columns [n0, n0 + 64); tcgen05.commit arrives on an mbarrier when the chunk's MMAs retire;
+//   * epilogue: 8 warps read the 128 x N fp32 accumulator with tcgen05.ld.32x32b.x16 (warp w: TMEM lanes 32 (w % 4) .., column
+//     half w / 4), add the bias, apply ReLU, and store 64-byte row pieces.
+#include "common.cuh"
+
+namespace ggl {
+
+constexpr int kBM = 128;   // rows per CTA (UMMA M)
+constexpr int kNC = 64;    // output columns per MMA chunk (UMMA N)
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // SmemDescriptor (sm_100): start address >> 4 [0,14) | leading byte offset >> 4 [16,30) | stride byte offset >> 4 [32,46) |
+  // version = 1 [46,48) | base offset 0 | lbo mode 0 | layout type SWIZZLE_NONE = 0 [61,64)
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);   // the 19 bits a TF32 operand keeps
+  lo = v - hi;                                              // exact in fp32
+}
+
+template <int KC /* K chunks of 4 elements, even */>
+__global__ void __launch_bounds__(256, 1) linear_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                                                               const float* __restrict__ bias, const int relu, float* __restrict__ out,
+                                                               const int64_t M, const int32_t K, const int32_t N, const int32_t tmem_cols) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long mma_bar;
+  __shared__ uint32_t tmem_base_slot;
+  constexpr uint32_t A_BYTES = KC * kBM * 16;   // one of A_hi / A_lo
+  constexpr uint32_t B_BYTES = KC * kNC * 16;   // one of W_hi / W_lo for a 64-column chunk
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = smem + A_BYTES;
+  unsigned char* b_hi = smem + 2 * A_BYTES;
+  unsigned char* b_lo = smem + 2 * A_BYTES + B_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * kBM;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mma_bar);
+
+  if (warp == 0) {   // TMEM allocation by one full warp; the address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_base_slot)),
+                 "r"((uint32_t)tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // ---- A tile -> A_hi / A_lo (canonical layout).  lane <-> row inside a 32-row band, warp strides over (band, K chunk) ----
+  for (int item = warp; item < 4 * KC; item += 8) {
+    const int band = item & 3, kc = item >> 2;
+    const int r = band * 32 + lane;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < M && kc * 4 < K) v = __ldg(reinterpret_cast<const float4*>(A + (row0 + r) * K + kc * 4));
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    const uint32_t off = (uint32_t)kc * (kBM * 16) + (uint32_t)r * 16;
+    *reinterpret_cast<float4*>(a_hi + off) = h;
+    *reinterpret_cast<float4*>(a_lo + off) = l;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(a_hi), a_lo_s = (uint32_t)__cvta_generic_to_shared(a_lo);
+  const uint32_t b_hi_s = (uint32_t)__cvta_generic_to_shared(b_hi), b_lo_s = (uint32_t)__cvta_generic_to_shared(b_lo);
+
+  const int n_chunks = (N + kNC - 1) / kNC;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int n0 = c * kNC;
+    if (c > 0) {   // the previous chunk's MMAs have read W_hi / W_lo: wait for them before overwriting
+      const uint32_t parity = (uint32_t)(c - 1) & 1u;
+      asm volatile("{\n\t.reg .pred p;\n\tLW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LD;\n\tbra LW;\n\tLD:\n\t}"
+                   ::"r"(bar), "r"(parity) : "memory");
+    }
+    // ---- W[:, n0 : n0 + 64] -> W_hi / W_lo transposed to [n, k]: a thread owns (n, K chunk): 4 coalesced loads, one 16-byte store ----
+    for (int item = tid; item < kNC * KC; item += 256) {
+      const int n = item & (kNC - 1), kc = item / kNC;
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = kc * 4 + i;
+        v[i] = (k < K && n0 + n < N) ? __ldg(W + (int64_t)k * N + n0 + n) : 0.f;
+      }
+      float4 h, l;
+      split_tf32(v[0], h.x, l.x); split_tf32(v[1], h.y, l.y); split_tf32(v[2], h.z, l.z); split_tf32(v[3], h.w, l.w);
+      const uint32_t off = (uint32_t)kc * (kNC * 16) + (uint32_t)n * 16;
+      *reinterpret_cast<float4*>(b_hi + off) = h;
+      *reinterpret_cast<float4*>(b_lo + off) = l;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d = tmem_base + (uint32_t)n0;
+#pragma unroll 1
+      for (int ks = 0; ks < KC / 2; ++ks) {   // one MMA K step = 8 elements = 2 chunks
+        const uint64_t ah = umma_desc(a_hi_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
+        const uint64_t al = umma_desc(a_lo_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
+        const uint64_t bh = umma_desc(b_hi_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
+        const uint64_t bl = umma_desc(b_lo_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
+        umma_tf32(d, al, bh, IDESC, ks > 0 ? 1u : 0u);   // small terms first
+        umma_tf32(d, ah, bl, IDESC, 1u);
+        umma_tf32(d, ah, bh, IDESC, 1u);
+      }
+      // arrives on the mbarrier when every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+  }
+  {
+    const uint32_t parity = (uint32_t)(n_chunks - 1) & 1u;
+    asm volatile("{\n\t.reg .pred p;\n\tLW2:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LD2;\n\tbra LW2;\n\tLD2:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- epilogue: TMEM -> registers -> bias / ReLU -> global ----
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int64_t r = row0 + q * 32 + lane;
+    const int n_cols = n_chunks * kNC;
+    const int c_lo = half * (n_cols / 2), c_hi = c_lo + n_cols / 2;
+    for (int col = c_lo; col < c_hi; col += 16) {
+      uint32_t v[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                     "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                   : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (r < M && col < N) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          if (col + j >= N) break;
+          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + j));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          __stcs(reinterpret_cast<float4*>(out + r * N + col + j), o);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols) : "memory");
+  }
+}
+
+}  // namespace ggl
+
+using namespace ggl;
+
+extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float* bias, int relu, float* out, int64_t M, int64_t K,
+                                     int64_t N, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(M >= 0 && K > 0 && N > 0, GGL_EINVAL, "linear: bad sizes M=%lld K=%lld N=%lld", (long long)M, (long long)K, (long long)N);
+  if (M == 0) return GGL_OK;
+  GGL_REQUIRE(A && W && out, GGL_EINVAL, "linear: NULL pointer");
+  GGL_REQUIRE(K % 4 == 0 && K <= 128, GGL_EUNSUPPORTED, "linear: K = %lld (supported: multiples of 4 up to 128)", (long long)K);
+  GGL_REQUIRE(N % 4 == 0 && N <= 256, GGL_EUNSUPPORTED, "linear: N = %lld (supported: multiples of 4 up to 256)", (long long)N);
+  GGL_REQUIRE((((uintptr_t)A | (uintptr_t)out | (uintptr_t)bias) & 15) == 0, GGL_EUNSUPPORTED, "linear: 16-byte aligned A / out / bias");
+  GGL_REQUIRE((M + kBM - 1) / kBM < INT32_MAX, GGL_ERANGE, "linear: M too large");
+  const int n_chunks = (int)((N + kNC - 1) / kNC);
+  int tmem_cols = 32;
+  while (tmem_cols < n_chunks * kNC) tmem_cols <<= 1;
+  const int kc = (int)((K + 7) / 8) * 2;   // K chunks of 4, rounded up to whole MMA K steps (zero padded)
+  const unsigned grid = (unsigned)((M + kBM - 1) / kBM);
+#define GGL_LIN(KC_)                                                                                                        \
+  do {                                                                                                                      \
+    const size_t smem = (size_t)2 * KC_ * kBM * 16 + (size_t)2 * KC_ * kNC * 16;                                            \
+    GGL_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    linear_tf32x3_kernel<KC_><<<grid, 256, smem, stream>>>(A, W, bias, relu, out, M, (int32_t)K, (int32_t)N, tmem_cols);    \
+  } while (0)
+  if (kc <= 8) GGL_LIN(8);
+  else if (kc <= 16) GGL_LIN(16);
+  else if (kc <= 26) GGL_LIN(26);
+  else GGL_LIN(32);
+#undef GGL_LIN
+  GGL_LAUNCHED("linear_tf32x3");
+  return GGL_OK;
+}

@@ -168,7 +168,11 @@ class GCNConv(MessagePassing):
             # bias and activation ride in the aggregation kernel's epilogue (bit-identical to the separate passes)
             return mpops.gcn_propagate(edge_index, self.linear(x), self._norm, bias=self.bias if self.add_bias else None, relu=relu)
         if self.aggregate_first:
-            out = self.linear(self._aggregate(x, edge_index, edge_weight))
+            agg = self._aggregate(x, edge_index, edge_weight)
+            if self.fused and mpops.linear_tc_supported(agg, self.linear.weights):
+                # (A X) W + b (+ ReLU) in ONE tcgen05 GEMM with the epilogue fused (fp32-accurate 3xTF32, csrc/linear_tc.cu)
+                return mpops.linear_tc(agg, self.linear.weights, self.bias if self.add_bias else None, relu)
+            out = self.linear(agg)
         else:
             out = self._aggregate(self.linear(x), edge_index, edge_weight)  # gcn_conv.py:79
         out = out + self.bias if self.add_bias else out                     # gcn_conv.py:104-106

@@ -552,6 +552,56 @@ def check_message_bytes(num_edges, row_numel, elem_size, what):
                             'max on 2-D features, or raise the limit' % (what, num_edges, row_numel, need / 1e9, MAX_MESSAGE_BYTES / 1e9))
 
 
+class _LinearTC(torch.autograd.Function):
+    """out = act(A @ W + bias) on the tcgen05 tensor cores with fp32 accuracy (csrc/linear_tc.cu, 3xTF32, TMEM accumulator):
+    the Linear + bias + ReLU that follows the aggregation when a layer aggregates first (gcn_conv.py:79,104-106).  The two
+    backward GEMMs are plain library GEMMs (torch.matmul)."""
+
+    @staticmethod
+    def forward(ctx, a, w, bias, relu):
+        lib = _lib.load()
+        a = a.contiguous()
+        w = w.contiguous()
+        M, K = a.shape
+        N = w.shape[1]
+        dev = a.device
+        bflat = None if bias is None else bias.detach().reshape(-1).to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            out = torch.empty((M, N), dtype=torch.float32, device=dev)
+            _lib.check(lib.gglb200_linear_tf32x3(_ptr(a), _ptr(w), _ptr(bflat), int(bool(relu)), _ptr(out), M, K, N, _stream(dev)),
+                       'linear_tf32x3')
+        ctx.relu = bool(relu)
+        ctx.bias_shape = None if bias is None else tuple(bias.shape)
+        ctx.save_for_backward(a, w, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, w, out = ctx.saved_tensors
+        g = g.contiguous()
+        if ctx.relu:
+            g = g * (out > 0).to(g.dtype)
+        ga = g @ w.t() if ctx.needs_input_grad[0] else None
+        gw = a.t() @ g if ctx.needs_input_grad[1] else None
+        gb = g.sum(dim=0).reshape(ctx.bias_shape) if ctx.bias_shape is not None and ctx.needs_input_grad[2] else None
+        return ga, gw, gb, None
+
+
+def linear_tc_supported(a, w):
+    return (a.is_cuda and a.dtype == torch.float32 and w.dtype == torch.float32 and a.dim() == 2 and w.dim() == 2
+            and a.shape[1] == w.shape[0] and a.shape[1] % 4 == 0 and a.shape[1] <= 128 and w.shape[1] % 4 == 0 and w.shape[1] <= 256)
+
+
+def linear_tc(a, w, bias=None, relu=False):
+    """act(a @ w + bias) for a [M, K <= 128] fp32, w [K, N <= 256] fp32 (K, N multiples of 4) on the tcgen05 tensor cores at fp32
+    accuracy; raises for other shapes (see linear_tc_supported)."""
+    require_cuda(a, 'a')
+    require_cuda(w, 'w')
+    if not linear_tc_supported(a, w):
+        raise _lib.GglError('linear_tc: unsupported shapes / dtypes %s @ %s' % (tuple(a.shape), tuple(w.shape)))
+    return _LinearTC.apply(a, w, bias, relu)
+
+
 def weight_needs_grad(weight):
     """True when autograd must reach an edge weight: gspmm cannot provide that gradient (no grad for weight in the reference
     operator either, src/gspmm.cpp:30,79), the callers then use bspmm (sum) or the message + aggregate decomposition."""
@@ -722,4 +772,4 @@ def segment_softmax(data, segment_ids, num_segments):
 __all__ = ['use_ext', 'unsorted_segment_sum', 'unsorted_segment_mean', 'unsorted_segment_max', 'segment_sum',
            'segment_mean', 'segment_max', 'gspmm', 'bspmm', 'c_segment_sum', 'c_segment_mean', 'c_segment_max',
            'c_spmm_sum', 'c_spmm_mean', 'c_spmm_max', 'c_bspmm_sum', 'segment_softmax', 'gcn_propagate', 'gat_aggregate',
-           'gspmm_max_edge']
+           'gspmm_max_edge', 'linear_tc']

@@ -223,6 +223,17 @@ GGL_API int gglb200_gather_rows_peer(const void* const* x_table, int32_t owner_s
                              int64_t n, int64_t row_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The dense feature x weight GEMM next to the aggregation, on the tcgen05 tensor cores with a TMEM accumulator:
+ *   out[M,N] = act(A[M,K] @ W[K,N] + bias[N]),  fp32 in / out, act = ReLU when relu != 0, bias may be NULL.
+ * The Linear of GCNConv / SAGEConv / GINConv (layers/conv/gcn_conv.py:79,104-106, sage_conv.py:80, gin_conv.py:57) applied to
+ * aggregated rows (K = F_in <= 128, a multiple of 4; N <= 256, a multiple of 4).  fp32-accurate on TF32 tensor cores by
+ * operand splitting (3xTF32: a_hi.w_hi + a_hi.w_lo + a_lo.w_hi), ~1e-6 relative.  Other shapes: GGL_EUNSUPPORTED (the
+ * host side then uses the library GEMM).
+ * ------------------------------------------------------------------------------------------- */
+GGL_API int gglb200_linear_tf32x3(const float* A, const float* W, const float* bias, int relu, float* out, int64_t M, int64_t K,
+                          int64_t N, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Sort-free unsorted segment reduce (the role of mpops/torch_ext/cuda/segment_{sum,mean,max}_cuda.cu -- scalar atomicAdd /
  * CAS loops there): ONE streaming pass over x[E,K] in its original order, reductions resolved by the L2.
  *   SUM   vector reductions (red.global.add.v4.f32); fp32 sums differ from the serial loop by rounding only (exact for

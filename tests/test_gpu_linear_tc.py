@@ -1,0 +1,90 @@
+"""GPU tests of the tcgen05 GEMM next to the aggregation (csrc/linear_tc.cu, gglb200_linear_tf32x3): fp32 accuracy of the
+3xTF32 split against an fp64 matmul (1e-5 relative is the north_star bar for fp32 features; plain TF32 would sit at ~5e-4),
+bias / ReLU epilogue, ragged M, every K / N class the dispatcher has, autograd, and GCNConv(aggregate_first) end to end."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize('M,K,N', [(1000, 100, 256), (333, 128, 64), (128, 4, 4), (5000, 36, 100), (129, 64, 192), (77, 8, 16),
+                                   (4096, 104, 128), (1, 100, 256)])
+@pytest.mark.parametrize('bias,relu', [(False, False), (True, True)])
+def test_linear_tc_matches_fp64(M, K, N, bias, relu):
+    from gammagl_b200 import mpops
+    g = torch.Generator().manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g)
+    a[::3] *= 37.0                                        # mixed magnitudes: the split must hold across exponents
+    w = torch.randn(K, N, generator=g) * 0.3
+    b = torch.randn(N, generator=g) if bias else None
+    ref = a.double() @ w.double()
+    if bias:
+        ref = ref + b.double()
+    if relu:
+        ref = torch.relu(ref)
+    out = mpops.linear_tc(a.to(DEV), w.to(DEV), None if b is None else b.to(DEV), relu)
+    assert out.shape == (M, N) and out.dtype == torch.float32
+    assert rel(out, ref) < 1e-5
+    # and it is as accurate as the fp32 library GEMM itself (not merely within the bar)
+    lib = a.to(DEV) @ w.to(DEV)
+    if bias:
+        lib = lib + b.to(DEV)
+    if relu:
+        lib = torch.relu(lib)
+    assert rel(out, ref) < 4 * max(rel(lib, ref), 2e-7)
+
+
+def test_linear_tc_autograd():
+    from gammagl_b200 import mpops
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 700, 100, 64
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(K, N, generator=g) * 0.2
+    b = torch.randn(1, N, generator=g)
+    go = torch.randn(M, N, generator=g)
+    ad, wd, bd = (t.double().requires_grad_(True) for t in (a, w, b))
+    torch.relu(ad @ wd + bd).backward(go.double())
+    ac, wc, bc = (t.to(DEV).requires_grad_(True) for t in (a, w, b))
+    mpops.linear_tc(ac, wc, bc, True).backward(go.to(DEV))
+    assert rel(ac.grad, ad.grad) < 1e-5 and rel(wc.grad, wd.grad) < 1e-5 and rel(bc.grad, bd.grad) < 1e-5
+
+
+def test_gcn_conv_aggregate_first_runs_the_tensor_core_gemm():
+    from gammagl_b200 import _lib, mpops
+    from gammagl_b200.layers import GCNConv
+    N, E, F, H = 3000, 40000, 100, 256
+    g = torch.Generator().manual_seed(9)
+    ei = torch.randint(0, N, (2, E), generator=g)
+    x = torch.randn(N, F, generator=g)
+    layer = GCNConv(F, H, aggregate_first=True, fused_activation='relu').to(DEV)
+    taken = []
+    real = mpops.linear_tc
+    mpops.linear_tc = lambda *a, **k: (taken.append(1), real(*a, **k))[1]
+    try:
+        xx = x.to(DEV).requires_grad_(True)
+        out = layer(xx, ei.to(DEV))
+        out.square().sum().backward()
+    finally:
+        mpops.linear_tc = real
+    assert taken
+    # dense fp64 restatement of gcn_conv.py:78-106 (norm='both', unit weights) + ReLU
+    src, dst = ei
+    A = torch.zeros(N, N, dtype=torch.float64)
+    A.index_put_((dst, src), torch.ones(E, dtype=torch.float64), accumulate=True)
+    ds = torch.bincount(src, minlength=N).double().pow(-0.5)
+    dd = torch.bincount(dst, minlength=N).double().pow(-0.5)
+    ds[torch.isinf(ds)] = 0
+    dd[torch.isinf(dd)] = 0
+    xd = x.double().requires_grad_(True)
+    W = layer.linear.weights.detach().double().cpu()
+    od = torch.relu((dd[:, None] * (A @ (ds[:, None] * xd))) @ W + layer.bias.detach().double().cpu())
+    od.square().sum().backward()
+    assert rel(out, od) < 1e-5
+    assert rel(xx.grad, xd.grad) < 1e-5
