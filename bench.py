@@ -487,6 +487,19 @@ def run_configs(torch, dev, args, peak):
     gy = torch.randn_like(og)
     ms = median_ms(torch, lambda: og.backward(gy, retain_graph=True), reps)
     c4['gat_fused_bwd'] = entry(ms, 2 * (bs_b - 4 * H * E), 2 * E, op='two passes: grad x + grad s_src | grad s_dst')
+    # the same layer with the reference's other head width, C = 64 (K = 512, x' = 477 MB: not L2-resident): head groups of 2
+    del x3, ssrc, sdst, og, gy
+    C2 = 64
+    x3 = torch.randn(N, H, C2, generator=g, device=dev).requires_grad_(True)
+    ssrc = torch.randn(N, H, generator=g, device=dev).requires_grad_(True)
+    sdst = torch.randn(N, H, generator=g, device=dev).requires_grad_(True)
+    b64 = E * (H * C2 * 4 + 4) + N * H * C2 * 4
+    ms = median_ms(torch, lambda: mpops.gat_aggregate(ei, x3, ssrc, sdst, 0.2), reps)
+    c4['gat_fused_fwd_c64'] = entry(ms, b64, E, op='H=8, C=64 (K=512): 4 head-group launches of the fused kernel')
+    og = mpops.gat_aggregate(ei, x3, ssrc, sdst, 0.2)
+    gy = torch.randn_like(og)
+    ms = median_ms(torch, lambda: og.backward(gy, retain_graph=True), reps)
+    c4['gat_fused_bwd_c64'] = entry(ms, 2 * b64, 2 * E)
     c4['note'] = "x' (N*K*4 = %.0f MB) is L2-resident: these operators run against the L2 / issue roof, the HBM fraction is reported for continuity" % (N * K * 4 / 1e6)
     out['c4_gat'] = c4
     del ei, x3, wh, x2, og, gy, ssrc, sdst, dst

@@ -259,7 +259,7 @@ class GATConv(MessagePassing):
         # (same arithmetic association per half; avoids materialising [E, H, 2C])
         a_src, a_dst = self.att[..., :self.out_channels], self.att[..., self.out_channels:]
         if (self.fused and self.fuse_attention and x.dtype == torch.float32 and num_nodes == x.shape[0]
-                and mpops.gat_fusable(self.heads, self.out_channels) and not (self.training and self.dropout_rate > 0)):
+                and mpops.gat_fusable_grouped(self.heads, self.out_channels) and not (self.training and self.dropout_rate > 0)):
             # logits, edge softmax and aggregation in one streaming pass per direction: no [E, H] tensor at all
             out = mpops.gat_aggregate(edge_index, x, (x * a_src).sum(-1), (x * a_dst).sum(-1), self.negetive_slop)
             out = out.reshape(-1, self.heads * self.out_channels) if self.concat else out.mean(dim=1)

@@ -758,10 +758,35 @@ class _GatAggregate(torch.autograd.Function):
         return gx.view(N, H, C), gs_src, gs_dst, None, None
 
 
+def gat_head_groups(H, C):
+    """Heads per fused launch: the kernel holds H_g * C <= 128 columns per row; heads are independent in GAT, so wider layers
+    (the reference default-shaped 8 x 64) run as ceil(H / H_g) launches over column slices.  0 = not fusable at all."""
+    lh = C // 4
+    if C % 4 != 0 or lh < 1 or (lh & (lh - 1)) != 0 or C > 128:
+        return 0
+    return min(H, 128 // C)
+
+
+def gat_fusable_grouped(H, C):
+    return gat_head_groups(H, C) > 0
+
+
 def gat_aggregate(edge_index, x, s_src, s_dst, negative_slope=0.2):
     """out[i,h,:] = sum over in-edges (j -> i) of softmax_i(leaky_relu(s_src[j,h] + s_dst[i,h])) * x[j,h,:]
-    -- GATConv's attention + propagate (gat_conv.py:103-112) as one fused op; gradients for x, s_src and s_dst."""
-    return _GatAggregate.apply(x, s_src, s_dst, edge_index, negative_slope)
+    -- GATConv's attention + propagate (gat_conv.py:103-112) as one fused op; gradients for x, s_src and s_dst.
+    H * C > 128 runs head group by head group (gat_head_groups)."""
+    N, H, C = x.shape
+    if gat_fusable(H, C):
+        return _GatAggregate.apply(x, s_src, s_dst, edge_index, negative_slope)
+    hg = gat_head_groups(H, C)
+    if hg == 0:
+        raise _lib.GglError('gat_aggregate needs float32 x [N,H,C] with C %% 4 == 0, C/4 a power of two, C <= 128 (got H=%d C=%d)' % (H, C))
+    outs = []
+    for h0 in range(0, H, hg):
+        h1 = min(H, h0 + hg)
+        outs.append(_GatAggregate.apply(x[:, h0:h1].contiguous(), s_src[:, h0:h1].contiguous(), s_dst[:, h0:h1].contiguous(),
+                                        edge_index, negative_slope))
+    return torch.cat(outs, dim=1)
 
 
 def segment_softmax(data, segment_ids, num_segments):

@@ -223,6 +223,21 @@ GGL_API int gglb200_gather_rows_peer(const void* const* x_table, int32_t owner_s
                              int64_t n, int64_t row_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Neighbour sampling for the mini-batch path (ops/sparse/cpu/sample.cpp:10-135 `sample_adj`, the per-hop rule of
+ * ops/sparse/cpu/neighbor_sample.cpp:22-100; ops/sparse/cuda/neighbor_sample.cu): for every seed idx[i] pick `fanout` of its
+ * neighbours in the int64 CSR (rowptr, col) -- all of them when fanout < 0 or (no replacement and fanout >= degree),
+ * uniformly with replacement, or without replacement by Floyd's algorithm (the reference's rule).
+ *   count   out_ptr[n_seeds+1] = exclusive scan of the edges per seed (out_ptr[n_seeds] = total); *n_bad = seeds outside [0,n_nodes)
+ *   pick    e_id[total] = picked CSR positions grouped by seed, nbr[total] = col[e_id]; deterministic in (seed, inputs)
+ * ------------------------------------------------------------------------------------------- */
+GGL_API size_t gglb200_sample_workspace_bytes(int64_t n_seeds);
+GGL_API int gglb200_sample_count(const int64_t* rowptr, const int64_t* idx, int64_t n_seeds, int64_t n_nodes, int64_t fanout,
+                         int replace, int64_t* out_ptr, int64_t* n_bad, void* workspace, size_t workspace_bytes, void* stream);
+GGL_API int gglb200_sample_pick(const int64_t* rowptr, const int64_t* col, const int64_t* idx, int64_t n_seeds, int64_t n_nodes,
+                        int64_t fanout, int replace, uint64_t seed, const int64_t* out_ptr, int64_t* e_id, int64_t* nbr,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * The dense feature x weight GEMM next to the aggregation, on the tcgen05 tensor cores with a TMEM accumulator:
  *   out[M,N] = act(A[M,K] @ W[K,N] + bias[N]),  fp32 in / out, act = ReLU when relu != 0, bias may be NULL.
  * The Linear of GCNConv / SAGEConv / GINConv (layers/conv/gcn_conv.py:79,104-106, sage_conv.py:80, gin_conv.py:57) applied to

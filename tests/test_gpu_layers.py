@@ -209,7 +209,9 @@ def test_gcn_propagate_folded_vs_oracle(norm):
     assert rel(ob.float(), torch.from_numpy(ref)) < 2e-2
 
 
-@pytest.mark.parametrize('H,C,hub', [(8, 8, 3000), (2, 64, 0), (4, 16, 2500), (1, 4, 0), (8, 16, 1500), (3, 8, 2000)])
+@pytest.mark.parametrize('H,C,hub', [(8, 8, 3000), (2, 64, 0), (4, 16, 2500), (1, 4, 0), (8, 16, 1500), (3, 8, 2000),
+                                     # H * C > 128: head groups (the reference default-shaped 8 x 64 layer, K = 512)
+                                     (8, 64, 2000), (3, 128, 0), (5, 32, 1500)])
 def test_gat_aggregate_fused_vs_composed(H, C, hub):
     """mpops.gat_aggregate (one streaming pass per direction, online softmax, no [E,H] tensor) against the composition
     the reference executes -- leaky_relu(s_src[src] + s_dst[dst]) -> segment_softmax -> bspmm -- in fp64 on the CPU;
