@@ -668,7 +668,43 @@ def run_partitioned(torch, dist, dev, world, rank, args, ei_global_fn):
             s5 = max(2, min(steps, 4))
             ms, kms = time_partitioned(torch, dist, dev, world, graph, x, gout, s5, 2)
             byt, gbps = nvlink(graph, K5, kms)
-            res['c5_shard_' + kind] = {'workload': desc5.replace('halo all-to-all', 'fused peer gather + halo cache') + ' (weak scaling)',
+            # the model BASELINE.json configs[4] names: GCN, 3 layers, full graph -- Linear (128 -> 128) -> normalised
+            # propagate over the partition -> ReLU, three times, forward + backward through autograd
+            gcn3 = None
+            try:
+                Ws = [torch.nn.Parameter(torch.randn(K5, K5, generator=g, device=dev) * (K5 ** -0.5)) for _ in range(3)]
+
+                def gcn3_step():
+                    x.grad = None
+                    for w_ in Ws:
+                        w_.grad = None
+                    h = x
+                    for li, w_ in enumerate(Ws):
+                        h = P.peer_gcn_propagate(graph, h @ w_, 'both')
+                        if li < 2:
+                            h = torch.relu(h)
+                    h.backward(gout)
+                for _ in range(2):
+                    gcn3_step()
+                dist.barrier()
+                torch.cuda.synchronize()
+                a3, b3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a3.record()
+                for _ in range(s5):
+                    gcn3_step()
+                b3.record()
+                dist.barrier()
+                torch.cuda.synchronize()
+                t3 = torch.tensor([a3.elapsed_time(b3) / s5], device=dev)
+                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+                gcn3 = {'model': 'GCN, 3 layers, hidden 128 (Linear -> partitioned normalised propagate -> ReLU), forward + backward',
+                        'ms_per_step': float(t3.item()), 'edge_passes_per_step': 6,
+                        'value': world * 6 * Eg / (float(t3.item()) * 1e-3), 'unit': 'edges/s'}
+                del Ws
+            except Exception as ex:
+                gcn3 = {'error': repr(ex)[:300]}
+            res['c5_shard_' + kind] = {'gcn_3_layer': gcn3,
+                                       'workload': desc5.replace('halo all-to-all', 'fused peer gather + halo cache') + ' (weak scaling)',
                                        'graph': kind, 'N_total': N5, 'E_total': Eg * world, 'K': K5,
                                        'value': world * 2 * Eg / (ms * 1e-3), 'unit': 'edges/s', 'ms_per_step': ms, 'kernel_ms': kms,
                                        'nvlink_bytes_in_per_gpu_per_step': byt, 'nvlink_GBps_in': gbps, 'plan_build_ms': plan_ms,

@@ -284,6 +284,68 @@ class GATConv(MessagePassing):
         return x
 
 
+class GATV2Conv(MessagePassing):
+    """gatv2_conv.py:58-125.  The reference's logit is mean_c(leaky_relu(x_j) * att_src + leaky_relu(x_i) * att_dst): a sum of
+    a source-node and a destination-node scalar with NO non-linearity after the sum, so the attention is the fused GAT
+    kernel with slope 1 (identity) on s_src[j] + s_dst[i] -- no [E, H, C] gathers, no [E, H] tensor."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout_rate=0., add_bias=True, fused=True):
+        super().__init__(fused)
+        self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
+        self.negetive_slop, self.dropout_rate, self.add_bias = negative_slope, dropout_rate, add_bias
+        self.linear = Linear(in_channels, out_channels * heads)
+        self.att_src = torch.nn.Parameter(torch.nn.init.trunc_normal_(torch.empty(1, heads, out_channels), std=0.05))
+        self.att_dst = torch.nn.Parameter(torch.nn.init.trunc_normal_(torch.empty(1, heads, out_channels), std=0.05))
+        self.dropout = torch.nn.Dropout(dropout_rate)
+        if add_bias:
+            self.bias = torch.nn.Parameter(torch.zeros(heads * out_channels if concat else out_channels))
+
+    def forward(self, x, edge_index, num_nodes=None):
+        x = self.linear(x).reshape(-1, self.heads, self.out_channels)       # gatv2_conv.py:113
+        num_nodes = x.shape[0] if num_nodes is None else num_nodes
+        lx = torch.nn.functional.leaky_relu(x, self.negetive_slop)
+        s_src = (lx * self.att_src).mean(-1)                                # gatv2_conv.py:99-101, per node instead of per edge
+        s_dst = (lx * self.att_dst).mean(-1)
+        if (self.fused and x.dtype == torch.float32 and num_nodes == x.shape[0] and mpops.gat_fusable_grouped(self.heads, self.out_channels)
+                and not (self.training and self.dropout_rate > 0)):
+            out = mpops.gat_aggregate(edge_index, x, s_src, s_dst, 1.0)
+        else:
+            src, dst = edge_index[0], edge_index[1]
+            alpha = self.dropout(mpops.segment_softmax(s_src[src] + s_dst[dst], dst, num_nodes))   # gatv2_conv.py:103-104
+            out = self.propagate(x, edge_index, num_nodes=num_nodes, edge_weight=alpha)            # per-head weighted sum (bspmm)
+        out = out.reshape(-1, self.heads * self.out_channels) if self.concat else out.mean(dim=1)
+        return out + self.bias if self.add_bias else out
+
+
+GATv2Conv = GATV2Conv      # the reference exports the class as GATV2Conv (layers/conv/gatv2_conv.py:9)
+
+
+class AGNNConv(MessagePassing):
+    """agnn_conv.py:40-73: alpha = softmax_i(beta * cos(x_j, x_i)), out_i = sum_j alpha x_j.  The cosine logits are an SDDMM
+    over the normalised rows (mpops.sddmm: no [E, K] gathers), the weighted sum the one-head bspmm (gradient for alpha)."""
+
+    def __init__(self, in_channels, require_grad=True, fused=True):
+        super().__init__(fused)
+        self.in_channels = in_channels
+        if require_grad:
+            self.beta = torch.nn.Parameter(torch.rand(1))
+        else:
+            self.register_buffer('beta', torch.zeros(1))
+
+    def forward(self, x, edge_index, num_nodes=None):
+        num_nodes = x.shape[0] if num_nodes is None else num_nodes
+        src, dst = edge_index[0], edge_index[1]
+        xn = torch.nn.functional.normalize(x, p=2.0, dim=-1, eps=1e-12)      # tlx.l2_normalize
+        if self.fused and x.dtype == torch.float32 and num_nodes == x.shape[0] and x.dim() == 2:
+            cos = mpops.sddmm(edge_index, xn.unsqueeze(1), xn.unsqueeze(1)).reshape(-1)
+            alpha = mpops.segment_softmax(cos * self.beta, dst, num_nodes)
+            return mpops.bspmm(edge_index, alpha.reshape(-1, 1), x.unsqueeze(1), 'sum').squeeze(1)
+        cos = (xn[src] * xn[dst]).sum(-1)                                    # agnn_conv.py:64-66
+        mpops.check_message_bytes(edge_index.shape[1], x[0].numel(), x.element_size(), 'AGNNConv (unfused)')
+        alpha = mpops.segment_softmax(cos * self.beta, dst, num_nodes)
+        return mpops.unsorted_segment_sum(alpha.unsqueeze(-1) * x[src], dst, num_nodes)
+
+
 class GINConv(MessagePassing):
     def __init__(self, nn, eps=0., train_eps=False, fused=True):
         super().__init__(fused)

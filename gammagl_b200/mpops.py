@@ -438,6 +438,56 @@ class _BSpMM(torch.autograd.Function):
         return None, gw, gx
 
 
+class _SDDMM(torch.autograd.Function):
+    """e[edge, h] = <a[src, h, :], b[dst, h, :]> per edge and head (sampled dense-dense product) -- the logits of
+    dot-product attention layers (AGNNConv: agnn_conv.py:64-70 cos(x_src, x_dst); the same kernel is bspmm's weight
+    gradient, cpu/bspmm_sum_cpu.cpp:95-107).  No [E, H, C] gather is materialised.  Backward: two per-head weighted
+    SpMMs (grad a[s] = sum_e g[e] b[dst], grad b[d] = sum_e g[e] a[src])."""
+
+    @staticmethod
+    def forward(ctx, index, a, b):
+        lib = _lib.load()
+        _check_spmm_args(index, None, a)
+        require_cuda(b, 'b')
+        if a.dim() != 3 or tuple(a.shape) != tuple(b.shape) or a.dtype != torch.float32 or b.dtype != torch.float32:
+            raise _lib.GglError('sddmm expects float32 a, b of one shape [N, heads, channels]')
+        N, H, C = a.shape
+        a, b = a.contiguous(), b.contiguous()
+        g = graph_of(index, N)
+        dev = a.device
+        with torch.cuda.device(dev):
+            _lib.tune_device(dev.index)
+            f = g.fwd
+            f.use_on_current_stream()
+            e = torch.empty((g.E, H), dtype=torch.float32, device=dev)
+            _lib.check(lib.gglb200_bspmm_bwd_w(_ptr(f.rowptr), _ptr(f.col), _ptr(f.perm), _ptr(f.plan), _ptr(a), _ptr(b), _ptr(e),
+                                               N, g.E, H, C, _stream(dev)), 'sddmm')
+        ctx.graph = g
+        ctx.save_for_backward(a, b)
+        return e
+
+    @staticmethod
+    def backward(ctx, ge):
+        a, b = ctx.saved_tensors
+        g = ctx.graph
+        N, H, C = a.shape
+        ge = ge.contiguous()
+        ga = gb = None
+        with torch.cuda.device(a.device):
+            if ctx.needs_input_grad[1]:        # rows = sources: transposed CSR, gathers b[dst]
+                ga, _ = spmm_csr(g.bwd, g.bwd.col, b.view(N, H * C), _lib.GGL_SUM, w=ge, wperm=g.bwd.perm, heads=H)
+                ga = ga.view(N, H, C)
+            if ctx.needs_input_grad[2]:        # rows = destinations: forward CSR, gathers a[src]
+                gb, _ = spmm_csr(g.fwd, g.fwd.col, a.view(N, H * C), _lib.GGL_SUM, w=ge, wperm=g.fwd.perm, heads=H)
+                gb = gb.view(N, H, C)
+        return None, ga, gb
+
+
+def sddmm(index, a, b):
+    """e[edge, h] = sum_c a[src(edge), h, c] * b[dst(edge), h, c]; a, b [N, H, C] float32; differentiable in a and b."""
+    return _SDDMM.apply(index, a, b)
+
+
 def c_spmm_sum(index, weight, x, num_dst=None):
     return _SpMM.apply(index, weight, x, _lib.GGL_SUM, num_dst)
 
@@ -797,4 +847,4 @@ def segment_softmax(data, segment_ids, num_segments):
 __all__ = ['use_ext', 'unsorted_segment_sum', 'unsorted_segment_mean', 'unsorted_segment_max', 'segment_sum',
            'segment_mean', 'segment_max', 'gspmm', 'bspmm', 'c_segment_sum', 'c_segment_mean', 'c_segment_max',
            'c_spmm_sum', 'c_spmm_mean', 'c_spmm_max', 'c_bspmm_sum', 'segment_softmax', 'gcn_propagate', 'gat_aggregate',
-           'gspmm_max_edge', 'linear_tc']
+           'gspmm_max_edge', 'linear_tc', 'sddmm']

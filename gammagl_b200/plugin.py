@@ -78,6 +78,36 @@ def _fused_message_aggregate(self, x, edge_index, edge_weight=None, aggr='sum', 
     return self.aggregate(msg, edge_index, num_nodes=num_nodes, aggr=aggr)
 
 
+def _gatv2_message_aggregate(self, x, edge_index, edge_weight=None, num_nodes=None, aggr='sum'):
+    """GATv2Conv (layers/conv/gatv2_conv.py:95-108): its logit mean_c(leaky(x_j) att_src + leaky(x_i) att_dst) is a source-node
+    scalar plus a destination-node scalar, so attention + aggregation is the fused GAT kernel with slope 1 on those scalars."""
+    H, C = int(x.shape[1]), int(x.shape[2])
+    training = bool(getattr(self, 'is_train', getattr(self, 'training', False)))
+    if (edge_weight is None and aggr == 'sum' and x.is_cuda and x.dtype == torch.float32 and mpops.gat_fusable_grouped(H, C)
+            and (num_nodes is None or num_nodes == x.shape[0]) and not (training and float(getattr(self, 'dropout_rate', 0.)) > 0)):
+        lx = torch.nn.functional.leaky_relu(x, float(self.negetive_slop))
+        return mpops.gat_aggregate(edge_index, x, (lx * self.att_src).mean(-1), (lx * self.att_dst).mean(-1), 1.0)
+    mpops.check_message_bytes(edge_index.shape[1], x[0].numel(), x.element_size(), 'GATv2Conv.message')
+    return self.aggregate(self.message(x, edge_index, edge_weight, num_nodes), edge_index, num_nodes=num_nodes, aggr=aggr)
+
+
+def _agnn_message_aggregate(self, x, edge_index, num_nodes=None, edge_weight=None, aggr='sum'):
+    """AGNNConv (layers/conv/agnn_conv.py:57-70): cosine logits by SDDMM over the normalised rows, edge softmax, one-head bspmm."""
+    if edge_weight is None and aggr == 'sum' and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and (num_nodes is None or num_nodes == x.shape[0]):
+        xn = torch.nn.functional.normalize(x, p=2.0, dim=-1, eps=1e-12)
+        cos = mpops.sddmm(edge_index, xn.unsqueeze(1), xn.unsqueeze(1)).reshape(-1)
+        alpha = mpops.segment_softmax(cos * self.beta, edge_index[1], x.shape[0])
+        return mpops.bspmm(edge_index, alpha.reshape(-1, 1), x.unsqueeze(1), 'sum').squeeze(1)
+    mpops.check_message_bytes(edge_index.shape[1], x[0].numel(), x.element_size(), 'AGNNConv.message')
+    return self.aggregate(self.message(x, edge_index, num_nodes, edge_weight), edge_index, num_nodes=num_nodes, aggr=aggr)
+
+
+for _f in (_gatv2_message_aggregate, _agnn_message_aggregate):
+    _f.__name__ = _f.__qualname__ = 'message_aggregate'      # Inspector files signatures by __name__ (see below)
+# layers with their OWN message(): the attention they compute maps onto a fused operator as a whole
+_SPECIAL_LAYERS = {'GATV2Conv': _gatv2_message_aggregate, 'AGNNConv': _agnn_message_aggregate}
+
+
 # MessagePassing.__init__ registers the method with Inspector.inspect(), which files the signature under func.__name__
 # (utils/inspector.py:27-41) and then looks it up as 'message_aggregate' (message_passing.py:29-33): the installed function
 # must carry that name or constructing any patched layer raises KeyError.
@@ -114,11 +144,11 @@ def enable(fuse_layers=True, modules=None, utils=True):
                     setattr(mod, fn, _cuda_or_original(getattr(_utils, fn), old))
                     count += 1
         if fuse_layers:
-            for cls_name in _FUSED_LAYERS:
+            for cls_name in _FUSED_LAYERS + list(_SPECIAL_LAYERS):
                 cls = getattr(mod, cls_name, None)
                 if isinstance(cls, type) and 'message_aggregate' not in cls.__dict__ and hasattr(cls, 'propagate'):
                     _saved.append((cls, 'message_aggregate', None, False))
-                    cls.message_aggregate = _fused_message_aggregate
+                    cls.message_aggregate = _SPECIAL_LAYERS.get(cls_name, _fused_message_aggregate)
                     _patched_classes.append(cls)
                     count += 1
     if fuse_layers:

@@ -105,6 +105,7 @@ def make_tlx():
     tlx.concat = lambda xs, axis=0: torch.cat(list(xs), dim=axis)
     tlx.stack = lambda xs, axis=0: torch.stack(list(xs), dim=axis)
     tlx.reduce_sum = lambda x, axis=None: x.sum() if axis is None else x.sum(dim=axis)
+    tlx.l2_normalize = lambda x, axis=None, eps=1e-12: torch.nn.functional.normalize(x, p=2.0, dim=-1 if axis is None else axis, eps=eps)
     tlx.reduce_mean = lambda x, axis=None: x.mean() if axis is None else x.mean(dim=axis)
     tlx.reduce_max = lambda x, axis=None: x.max() if axis is None else x.max(dim=axis)[0]
     tlx.arange = lambda start, limit=None, delta=1, dtype=torch.int64: torch.arange(start, limit, delta, dtype=dtype)

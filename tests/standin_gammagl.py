@@ -130,10 +130,42 @@ def make():
         def forward(self, x, edge_index):
             return self.propagate(x, edge_index, edge_weight=None, aggr='sum')
 
+    class GATV2Conv(MessagePassing):                # gatv2_conv.py:95-123: own message() = attention + weighting
+        def __init__(self, heads, channels, negative_slope=0.2):
+            super().__init__()
+            self.negetive_slop, self.dropout_rate = negative_slope, 0.
+            g = torch.Generator().manual_seed(3)
+            self.att_src = torch.nn.Parameter(torch.randn(1, heads, channels, generator=g))
+            self.att_dst = torch.nn.Parameter(torch.randn(1, heads, channels, generator=g))
+
+        def message(self, x, edge_index, edge_weight=None, num_nodes=None):
+            src, dst = edge_index[0], edge_index[1]
+            lr = torch.nn.functional.leaky_relu
+            weight = (lr(x[src], self.negetive_slop) * self.att_src + lr(x[dst], self.negetive_slop) * self.att_dst).mean(-1)
+            alpha = S['segment_softmax'](weight, dst, num_nodes)
+            return x[src] * alpha.unsqueeze(-1)
+
+        def forward(self, x, edge_index, num_nodes=None):
+            return self.propagate(x, edge_index, num_nodes=num_nodes)
+
+    class AGNNConv(MessagePassing):                 # agnn_conv.py:57-73
+        def __init__(self):
+            super().__init__()
+            self.beta = torch.nn.Parameter(torch.tensor([0.7]))
+
+        def message(self, x, edge_index, num_nodes, edge_weight=None):
+            src, dst = edge_index[0], edge_index[1]
+            nrm = lambda t: torch.nn.functional.normalize(t, p=2.0, dim=-1, eps=1e-12)
+            cos = (nrm(x[src]) * nrm(x[dst])).sum(-1)
+            return S['segment_softmax'](cos * self.beta, dst, num_nodes).unsqueeze(-1) * x[src]
+
+        def forward(self, x, edge_index, num_nodes):
+            return self.propagate(x, edge_index, num_nodes=num_nodes)
+
     class HGTConv(MessagePassing):                  # a layer with its own message(): must stay unfused
         def message(self, x, edge_index, edge_weight=None):
             return x[edge_index[0]] * 2.0
-    for c in (GCNConv, SAGEConv, GATConv, GINConv, HGTConv):
+    for c in (GCNConv, SAGEConv, GATConv, GINConv, GATV2Conv, AGNNConv, HGTConv):
         setattr(conv, c.__name__, c)
     return {'gammagl': pkg, 'gammagl.mpops': mp, 'gammagl.mpops.torch': mpt, 'gammagl.layers.conv.message_passing': msgmod,
             'gammagl.layers.conv': conv, 'gammagl.utils.softmax': sm}

@@ -383,3 +383,85 @@ def test_gcn_conv_fused_activation():
     # explicit edge weights take the unfolded path: same semantics with the activation as a separate op
     w = torch.rand(ei.shape[1], generator=torch.Generator().manual_seed(15)).to(DEV)
     assert torch.equal(a(x.to(DEV), ei.to(DEV), w), torch.relu(b(x.to(DEV), ei.to(DEV), w)))
+
+
+@pytest.mark.parametrize('H,C', [(4, 16), (1, 32), (8, 64), (3, 5)])
+def test_sddmm_op_and_gradients(H, C):
+    """mpops.sddmm: e[edge, h] = <a[src, h], b[dst, h]> and its two SpMM gradients against an fp64 gather composition
+    (H=3, C=5: K = 15 is not a multiple of 4 -> the generic kernel)."""
+    from gammagl_b200 import mpops
+    N, E = 900, 20000
+    g = torch.Generator().manual_seed(7 * H + C)
+    ei = torch.stack([torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g)])
+    ei[1, :2500] = 11
+    a, b, ge = torch.randn(N, H, C, generator=g), torch.randn(N, H, C, generator=g), torch.randn(E, H, generator=g)
+    ad, bd = a.double().requires_grad_(True), b.double().requires_grad_(True)
+    (ad[ei[0]] * bd[ei[1]]).sum(-1).backward(ge.double())
+    ac, bc = a.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    e = mpops.sddmm(ei.to(DEV), ac, bc)
+    e.backward(ge.to(DEV))
+    assert rel(e, (a.double()[ei[0]] * b.double()[ei[1]]).sum(-1)) < 1e-5
+    assert rel(ac.grad, ad.grad) < 1e-5 and rel(bc.grad, bd.grad) < 1e-5
+
+
+def _dense_attention(x, ei, logits, N):
+    src, dst = ei
+    H = logits.shape[1]
+    mx = torch.full((N, H), -1e300, dtype=torch.float64).scatter_reduce(0, dst[:, None].expand(-1, H), logits, 'amax')
+    ex = torch.exp(logits - mx[dst].detach())
+    den = torch.zeros(N, H, dtype=torch.float64).index_add_(0, dst, ex)
+    alpha = ex / (den[dst] + 1e-16)
+    return torch.zeros((N,) + tuple(x.shape[1:]), dtype=torch.float64).index_add_(0, dst, alpha.reshape(alpha.shape + (1,) * (x.dim() - 2)) * x[src])
+
+
+@pytest.mark.parametrize('heads,concat', [(4, True), (2, False)])
+def test_gatv2_conv_mirror(heads, concat):
+    """layers.GATV2Conv (gatv2_conv.py:58-125): fused (gat_aggregate with slope 1) == unfused == dense fp64."""
+    from gammagl_b200.layers import GATV2Conv
+    N, E, F, C = 300, 5000, 20, 8
+    ei = graph(N, E, 12)
+    x = torch.randn(N, F, generator=torch.Generator().manual_seed(13))
+    fused = GATV2Conv(F, C, heads=heads, concat=concat).to(DEV)
+    with torch.no_grad():
+        fused.att_src.mul_(20)
+        fused.att_dst.mul_(20)
+    unfused = copy.deepcopy(fused)
+    unfused.fused = False
+    xf, xu = x.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
+    of, gf, go = run(fused, xf, ei.to(DEV))
+    ou, gu, _ = run(unfused, xu, ei.to(DEV))
+    xd = x.double().requires_grad_(True)
+    W = fused.linear.weights.detach().double().cpu()
+    h = (xd @ W + fused.linear.biases.detach().double().cpu()).reshape(N, heads, C)
+    lr = torch.nn.functional.leaky_relu
+    logits = (lr(h[ei[0]], 0.2) * fused.att_src.detach().double().cpu() + lr(h[ei[1]], 0.2) * fused.att_dst.detach().double().cpu()).mean(-1)
+    od = _dense_attention(h, ei, logits, N)
+    od = od.reshape(N, heads * C) if concat else od.mean(1)
+    od = od + fused.bias.detach().double().cpu()
+    od.backward(go.double().cpu())
+    assert rel(of, od) < 2e-5 and rel(ou, od) < 2e-5
+    assert rel(xf.grad, xd.grad) < 1e-4 and rel(xu.grad, xd.grad) < 1e-4
+
+
+def test_agnn_conv_mirror():
+    """layers.AGNNConv (agnn_conv.py:40-73): SDDMM logits + edge softmax + one-head bspmm == unfused == dense fp64."""
+    from gammagl_b200.layers import AGNNConv
+    N, E, K = 400, 7000, 36
+    ei = graph(N, E, 14)
+    x = torch.randn(N, K, generator=torch.Generator().manual_seed(15))
+    fused = AGNNConv(K).to(DEV)
+    with torch.no_grad():
+        fused.beta.fill_(3.0)
+    unfused = copy.deepcopy(fused)
+    unfused.fused = False
+    xf, xu = x.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
+    of, gf, go = run(fused, xf, ei.to(DEV))
+    ou, gu, _ = run(unfused, xu, ei.to(DEV))
+    xd = x.double().requires_grad_(True)
+    nrm = lambda t: torch.nn.functional.normalize(t, p=2.0, dim=-1, eps=1e-12)
+    logits = ((nrm(xd[ei[0]]) * nrm(xd[ei[1]])).sum(-1) * 3.0).unsqueeze(-1)
+    od = _dense_attention(xd, ei, logits, N)
+    od.backward(go.double().cpu())
+    assert rel(of, od) < 2e-5 and rel(ou, od) < 2e-5
+    assert rel(xf.grad, xd.grad) < 1e-4 and rel(xu.grad, xd.grad) < 1e-4
+    assert rel(fused.beta.grad, unfused.beta.grad) < 1e-4

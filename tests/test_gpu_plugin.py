@@ -144,3 +144,63 @@ def test_unfused_layer_still_runs_on_the_b200_segment_operators(tree):
     out = layer.propagate(x.to(DEV), ei.to(DEV))
     ref = O.segment('sum', 2.0 * x.numpy()[ei[0].numpy()], ei[1].numpy(), N)
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def _attention_reference(x, ei, logits, N):
+    """fp64: softmax of `logits` [E, H] over incoming edges, then out[i] = sum alpha x[src]."""
+    src, dst = ei
+    H = logits.shape[1]
+    mx = torch.full((N, H), -1e300, dtype=torch.float64).scatter_reduce(0, dst[:, None].expand(-1, H), logits, 'amax')
+    ex = torch.exp(logits - mx[dst].detach())
+    den = torch.zeros(N, H, dtype=torch.float64).index_add_(0, dst, ex)
+    alpha = ex / (den[dst] + 1e-16)
+    return torch.zeros((N,) + tuple(x.shape[1:]), dtype=torch.float64).index_add_(0, dst, alpha.reshape(alpha.shape + (1,) * (x.dim() - 2)) * x[src])
+
+
+def test_gatv2_and_agnn_take_their_fused_operators(tree):
+    mods, _ = tree
+    from gammagl_b200 import mpops
+    conv = mods['gammagl.layers.conv']
+    N, E = 700, 14000
+    ei, g = graph(N, N, E, 8)
+    # ---- GATv2 ----
+    H, C = 4, 16
+    layer = conv.GATV2Conv(H, C).to(DEV)
+    assert type(layer).message_aggregate.__name__ == 'message_aggregate'
+    x = torch.randn(N, H, C, generator=g)
+    gout = torch.randn(N, H, C, generator=g)
+    called = []
+    real = mpops.gat_aggregate
+    mpops.gat_aggregate = lambda *a, **k: (called.append('gat'), real(*a, **k))[1]
+    try:
+        xx = x.to(DEV).requires_grad_(True)
+        out = layer(xx, ei.to(DEV), N)
+        out.backward(gout.to(DEV))
+    finally:
+        mpops.gat_aggregate = real
+    assert called == ['gat']
+    xd = x.double().requires_grad_(True)
+    lr = torch.nn.functional.leaky_relu
+    a_s, a_d = layer.att_src.detach().double().cpu(), layer.att_dst.detach().double().cpu()
+    logits = (lr(xd[ei[0]], 0.2) * a_s + lr(xd[ei[1]], 0.2) * a_d).mean(-1)
+    ref = _attention_reference(xd, ei, logits, N)
+    ref.backward(gout.double())
+    assert rel(out.detach().cpu().numpy(), ref.detach().numpy()) < 2e-5
+    assert rel(xx.grad.cpu().numpy(), xd.grad.numpy()) < 1e-4
+    # ---- AGNN ----
+    K = 48
+    layer = conv.AGNNConv().to(DEV)
+    x = torch.randn(N, K, generator=g)
+    gout = torch.randn(N, K, generator=g)
+    xx = x.to(DEV).requires_grad_(True)
+    out = layer(xx, ei.to(DEV), N)
+    out.backward(gout.to(DEV))
+    xd = x.double().requires_grad_(True)
+    beta = layer.beta.detach().double().cpu().requires_grad_(True)
+    nrm = lambda t: torch.nn.functional.normalize(t, p=2.0, dim=-1, eps=1e-12)
+    logits = ((nrm(xd[ei[0]]) * nrm(xd[ei[1]])).sum(-1) * beta).unsqueeze(-1)
+    ref = _attention_reference(xd, ei, logits, N)
+    ref.backward(gout.double())
+    assert rel(out.detach().cpu().numpy(), ref.detach().numpy()) < 2e-5
+    assert rel(xx.grad.cpu().numpy(), xd.grad.numpy()) < 1e-4
+    assert rel(layer.beta.grad.cpu().numpy(), beta.grad.numpy()) < 1e-4

@@ -180,3 +180,31 @@ def test_fused_branch_keeps_the_edge_weight_gradient_of_the_reference_layer(ref)
         del L['SGConv'].message_aggregate
     assert float(np.abs(gw0).sum()) > 0
     assert rel(o1, o0) < 1e-5 and rel(gx1, gx0) < 1e-5 and rel(gw1, gw0) < 1e-5
+
+
+def test_special_layers_accept_the_installed_signature(ref):
+    """GATv2Conv / AGNNConv of the reference (their own message()): the class-specific message_aggregate that enable() installs is
+    routed by the reference's switch and Inspector, and on CPU tensors (no fused operator) reproduces the stock result."""
+    G, L, plugin, tlx = ref
+    N, E = 90, 700
+    ei = G.graph(N, E, 3)
+    g = torch.Generator().manual_seed(4)
+    for cls_name, fname, build, call, xshape in (
+            ('GATV2Conv', 'gatv2_conv', lambda c: c(12, 5, heads=3), lambda m, x: m(x, ei, N), (N, 12)),
+            ('AGNNConv', 'agnn_conv', lambda c: c(12, require_grad=False), lambda m, x: m(x, ei, N), (N, 12))):
+        cls = G.load_extra_layer(cls_name, fname)
+        assert 'message_aggregate' not in cls.__dict__
+        x = torch.randn(*xshape, generator=g)
+        torch.manual_seed(0)
+        m = build(cls)
+        m.eval() if hasattr(m, 'eval') else None
+        o0 = call(m, x).detach().numpy()
+        cls.message_aggregate = plugin._SPECIAL_LAYERS[cls_name]
+        try:
+            torch.manual_seed(0)
+            m1 = build(cls)
+            m1.eval() if hasattr(m1, 'eval') else None
+            o1 = call(m1, x).detach().numpy()
+        finally:
+            del cls.message_aggregate
+        assert rel(o1, o0) < 1e-6, cls_name
