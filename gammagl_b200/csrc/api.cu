@@ -54,6 +54,16 @@ int tune_ring_stages() {
   return v;
 }
 
+int tune_narrow() {  // aligned fp32 rows of at most 256 bytes: 1 = lean register-staged kernel, 0 = bulk-copy ring (env GGLB200_NARROW=ldg|ring)
+  static int v = [] {
+    const char* e = getenv("GGLB200_NARROW");
+    if (e && e[0] == 'l') return 1;
+    if (e && e[0] == 'r') return 0;
+    return GGLB200_NARROW_DEFAULT;
+  }();
+  return v;
+}
+
 int tune_ring() {  // 1 = bulk-copy ring (default), 0 = register-staged kernels (env GGLB200_RING=none)
   static int v = [] {
     const char* e = getenv("GGLB200_RING");

@@ -40,6 +40,10 @@ extern std::atomic<int64_t> g_launches;
       return ::ggl::set_error((int)e__, "%s: %s", #call, cudaGetErrorString(e__));     \
   } while (0)
 
+// default path of aligned fp32 rows <= 256 bytes (decided by measurement: tools/probe_narrow.py, profiles/README.md)
+#ifndef GGLB200_NARROW_DEFAULT
+#define GGLB200_NARROW_DEFAULT 0
+#endif
 int sm_count();  // SMs of the current device (148 on B200: 2 dies x 74), queried once per device; api.cu
 
 // ---- plan layout (int32 array produced by gglb200_csr_build, consumed by the reduce kernels) --------

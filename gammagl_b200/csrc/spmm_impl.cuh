@@ -30,6 +30,8 @@
 //     GPU's HBM over NVLink -- the 1-D node partition needs no pack / all-to-all / halo buffer.
 //   * K wider than LPR*VEC is covered by blockIdx.y column tiles.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ggl {
@@ -356,6 +358,72 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) spmm_tiles_kernel(cons
   }
   while (rc.r < rc.r_end) next_row();  // last row of the tile + trailing empty rows
 }
+
+// ---- kernel 1c: lean register-staged tile kernel for NARROW aligned fp32 rows (<= 256 bytes) --------------------------------
+// tools/probe_tma.cu (profiles/probe_tma_r2_*.jsonl): a random gather of rows up to 256 bytes runs at 36-41 G rows/s with plain
+// 16-byte ld.global.nc and many threads in flight, against 18-26 G rows/s through one bulk copy (UBLKCP) per row -- for narrow rows
+// the TMA unit's per-copy cost binds, not bytes.  This kernel is that probe with the row bookkeeping added: a group of LPR lanes
+// owns one edge tile, every lane reads its own copy of the col / weight stream (broadcast loads inside the group: no shuffles,
+// no shared memory, no barriers), U independent 16-byte gathers in flight per lane, serial accumulation in edge order (same
+// bits as the ring kernel and the reference loop).  All tiles hold the same number of edges, so the groups of a warp run the
+// same trip counts and only part ways at row boundaries.
+template <int LPR, int WMODE /* 0 | 1 */, bool ISMAX>
+__global__ void __launch_bounds__(256) spmm_lean_kernel(const SpmmArgs p) {
+  constexpr int VEC = 4, U = 4;
+  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  if (tile >= p.n_tiles) return;  // group-uniform
+  const int sub = threadIdx.x & (LPR - 1);
+  const int32_t kcol = sub * VEC;
+  const bool col_active = kcol < p.K;
+  const float* xk = reinterpret_cast<const float*>(p.x) + kcol;
+  const int64_t K = p.K;
+  int32_t r0, r1, e, e_end;
+  if (!tile_ranges(p, tile, r0, r1, e, e_end)) return;
+  int32_t r = r0, row_start = e, row_end = __ldg(p.rowptr + r0 + 1);
+  float acc[VEC];
+  int32_t argv[VEC];
+  reset_acc<float, VEC, ISMAX>(acc, argv);
+  auto flush = [&]() {
+    if (col_active) finish_row<float, VEC, ISMAX>(acc, argv, p, r, kcol, row_end - row_start);
+    reset_acc<float, VEC, ISMAX>(acc, argv);
+    row_start = row_end;
+    ++r;
+    row_end = r < r1 ? __ldg(p.rowptr + r + 1) : INT32_MAX;
+  };
+  for (; e < e_end; e += U) {
+    int32_t c[U], ai[U];
+    float wv[U];
+    Pack<float, VEC> v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      c[u] = 0; ai[u] = 0; wv[u] = 1.f;
+      if (e + u < e_end) {
+        c[u] = __ldg(p.col + e + u);
+        ai[u] = c[u];
+        if constexpr (WMODE == 1 || ISMAX) {
+          if (WMODE == 1 || p.arg_eid) {
+            const int32_t eid = p.wperm ? __ldg(p.wperm + e + u) : e + u;
+            if constexpr (WMODE == 1) wv[u] = __ldg(p.w + eid);
+            if constexpr (ISMAX) { if (p.arg_eid) ai[u] = eid; }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (e + u < e_end && col_active) v[u] = ld_gather<float, VEC>(xk + (int64_t)c[u] * K);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (e + u < e_end) {
+        while (e + u == row_end) flush();
+        if (col_active) accumulate<float, VEC, WMODE, ISMAX>(acc, argv, v[u], wv[u], ai[u]);
+      }
+    }
+  }
+  while (r < r1) flush();  // last row of the tile + trailing empty rows
+}
+
+int tune_narrow();  // 1 = lean register-staged kernel for aligned fp32 rows <= 256 bytes, 0 = bulk-copy ring (env GGLB200_NARROW), api.cu
 
 // ---- kernel 1b: shared-memory ring tile kernel -------------------------------------------------------------------
 // Each lane group owns a ring of STAGES slots x R feature rows in shared memory and keeps it LAG = STAGES-1 slots
@@ -759,6 +827,22 @@ int launch_config(const SpmmArgs& p) {
   GGL_REQUIRE(tiles <= 65535, GGL_EUNSUPPORTED, "spmm: K=%lld needs too many column tiles", (long long)p.K);
   // floating rows of at least 4 lanes stream through the shared-memory ring; the rest (K <= 4 elements per row,
   // f64, integers) through the register-staged kernels
+  if constexpr (std::is_same<T, float>::value && VEC == 4 && LPR <= 16 && (WMODE == 0 || WMODE == 1)) {
+    if (tune_narrow() != 0 && p.x_table == nullptr && tiles == 1 && (((uintptr_t)p.x | (uintptr_t)p.out) & 15) == 0) {
+      const int64_t threads = p.n_tiles * LPR;
+      const int64_t blocks = (threads + 255) / 256;
+      GGL_REQUIRE(blocks < INT32_MAX, GGL_EUNSUPPORTED, "spmm: grid too large");
+      spmm_lean_kernel<LPR, WMODE, ISMAX><<<(unsigned)blocks, 256, 0, p.stream>>>(p);
+      GGL_LAUNCHED("spmm_lean");
+      if (p.has_long) {   // rows above GGLB200_LONG_ROW: chunk partials + ordered combine, as on the register-staged path
+        spmm_chunks_kernel<T, VEC, LPR, WMODE, ISMAX><<<dim3(sm_count() * 2, tiles), kWarpsPerBlock * 32, 0, p.stream>>>(p);
+        GGL_LAUNCHED("spmm_chunks");
+        spmm_finalize_kernel<T, VEC, LPR, ISMAX><<<dim3(sm_count(), tiles), kWarpsPerBlock * 32, 0, p.stream>>>(p);
+        GGL_LAUNCHED("spmm_finalize");
+      }
+      return GGL_OK;
+    }
+  }
   if constexpr (WMODE == 3) {
     // spanning lanes exist on the bulk-copy ring only (fp32, 16-byte lanes)
     if constexpr (Elem<T>::is_float && sizeof(T) == 4 && VEC == 4 && LPR >= 4) return launch_ring<T, VEC, LPR, WMODE, ISMAX>(p, tiles);

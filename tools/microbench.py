@@ -102,7 +102,10 @@ def main(cfg):
     go = torch.randn(N, Ks, generator=g, device=dev)
     m2 = msg.clone().requires_grad_(True)
     o = mpops.unsorted_segment_sum(m2, dst, N)
-    report('unsorted_segment_sum bwd through autograd (includes the [E,K] grad accumulation of torch)', timeit(lambda: o.backward(go, retain_graph=True)), E, seg_b, cfg=cfg)
+    def seg_bwd():                      # grad set to None first, as optimizer.zero_grad(set_to_none=True) does: otherwise torch ADDS the new
+        m2.grad = None                  # [E,K] gradient to the old one (3 extra passes over 14.7 GB -- the "10.9 ms" of the round-1 table)
+        o.backward(go, retain_graph=True)
+    report('unsorted_segment_sum bwd through autograd (grad reset per step)', timeit(seg_bwd), E, seg_b, cfg=cfg)
     from gammagl_b200.csr import segment_csr_of
     sc = segment_csr_of(dst, N)
     gxb = torch.empty(E, Ks, device=dev)
@@ -115,7 +118,13 @@ def main(cfg):
     report('segment_mean bwd kernel: scatter through the CSR', timeit(lambda: _lib.check(lib.gglb200_segment_expand_bwd(
         _lib.GGL_MEAN, _ptr(go), _ptr(sc.rowptr), _ptr(sc.perm), _ptr(sc.plan), _ptr(gxb), E, N, Ks, _lib.GGL_F32, _stream(dev)))), E, seg_b, cfg=cfg)
     ones = torch.ones(E, device=dev)
-    report('degree: unsorted_segment_sum(ones[E]) K=1', timeit(lambda: mpops.unsorted_segment_sum(ones, dst, N)), E, E * 12 + N * 4, cfg=cfg)
+    report('degree: unsorted_segment_sum(ones[E]) K=1 (policy auto: sort-free one-shot pass)', timeit(lambda: mpops.unsorted_segment_sum(ones, dst, N)), E, E * 12 + N * 4, cfg=cfg)
+    # the sort-free path on wider rows (what ids that change every step pay instead of sort + CSR pass)
+    for red, code in (('sum', _lib.GGL_SUM), ('mean', _lib.GGL_MEAN), ('max', _lib.GGL_MAX)):
+        report('segment_%s one-shot (gglb200_segment_reduce) K=%d' % (red, Ks), timeit(lambda: mpops.segment_reduce_oneshot(msg, dst, N, code)), E,
+               seg_b + (N * Ks * 8 if red == 'max' else 0), cfg=cfg)
+    m4 = torch.randn(E, 4, generator=g, device=dev)
+    report('segment_sum one-shot K=4', timeit(lambda: mpops.segment_reduce_oneshot(m4, dst, N, _lib.GGL_SUM)), E, E * 24 + N * 16, cfg=cfg)
 
 
 if __name__ == '__main__':
