@@ -887,13 +887,17 @@ def run_b200(args):
         barrier()
         ems = a.elapsed_time(b) / args.steps
         t = torch.tensor([ems], device=dev)
+        per_rank = [{'rank': rank, 'ms': ems, 'numa': numa}]
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, per_rank[0])
+            per_rank = gathered
         nb = N * K * esz
         e2e = {'value': world * 2 * E / (float(t.item()) * 1e-3), 'unit': 'edges/s', 'ms_per_step': float(t.item()),
                'h2d_bytes_per_step': 2 * nb, 'd2h_bytes_per_step': 2 * nb,
                'host_GBps_per_gpu_each_direction': 2 * nb / (float(t.item()) * 1e-3) / 1e9,
-               'host_memory_GBps_all_ranks': world * 4 * nb / (float(t.item()) * 1e-3) / 1e9, 'numa': numa,
+               'host_memory_GBps_all_ranks': world * 4 * nb / (float(t.item()) * 1e-3) / 1e9, 'numa': numa, 'per_rank': per_rank,
                'note': 'x and grad_out copied from pinned host memory, out and grad_x copied back, every step (uploads and '
                        'downloads on their own streams, event-ordered, device input buffers double-buffered); graph (CSR) resident'}
 

@@ -66,10 +66,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + objs
+    tmp = LIB + '.tmp.%d' % os.getpid()          # link next to the target, then rename: a reader never sees a half-written library
+    cmd = [NVCC] + ARCH + ['-shared', '-o', tmp] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+    os.replace(tmp, LIB)
     with open(STAMP, 'w') as f:
         f.write(_digest())
     return LIB

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) sample_count_kernel(const int64_t* __rest
   cnt[i] = (fanout < 0 || (!replace && fanout >= deg)) ? deg : (deg == 0 ? 0 : fanout);
 }
 
-constexpr int kMaxFloyd = 64;   // fanouts up to this run Floyd's algorithm in registers / local memory
+constexpr int64_t kCoopDegree = 64;   // "take every neighbour" rows above this degree are copied by a warp, not by one thread
 
 __global__ void __launch_bounds__(128) sample_pick_kernel(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ col,
                                                           const int64_t* __restrict__ idx, int64_t n_seeds, int64_t n_nodes, int64_t fanout,
@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(128) sample_pick_kernel(const int64_t* __restr
   const int64_t o = out_ptr[i], k = out_ptr[i + 1] - o;
   if (k == 0) return;
   if (k == deg && (fanout < 0 || !replace)) {            // every neighbour, in CSR order
+    if (deg > kCoopDegree) return;                        // hub rows: copied by the cooperative kernel below
     for (int64_t j = 0; j < deg; ++j) { e_id[o + j] = b + j; nbr[o + j] = col[b + j]; }
     return;
   }
@@ -75,6 +76,23 @@ __global__ void __launch_bounds__(128) sample_pick_kernel(const int64_t* __restr
     for (int64_t q = 0; q < n; ++q)
       if (e_id[o + q] == b + t) { t = j; break; }
     e_id[o + n] = b + t; nbr[o + n] = col[b + t];
+  }
+}
+
+// full-neighbourhood rows of hub seeds (fanout < 0 or fanout >= degree > kCoopDegree): one warp per seed, coalesced copy
+__global__ void __launch_bounds__(256) sample_copy_hubs_kernel(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ col,
+                                                               const int64_t* __restrict__ idx, int64_t n_seeds, int64_t n_nodes,
+                                                               int64_t fanout, int replace, const int64_t* __restrict__ out_ptr,
+                                                               int64_t* __restrict__ e_id, int64_t* __restrict__ nbr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_seeds; i += warps) {
+    const int64_t w = idx[i];
+    if (w < 0 || w >= n_nodes) continue;
+    const int64_t b = rowptr[w], deg = rowptr[w + 1] - b;
+    const int64_t o = out_ptr[i], k = out_ptr[i + 1] - o;
+    if (!(k == deg && (fanout < 0 || !replace)) || deg <= kCoopDegree) continue;
+    for (int64_t j = lane; j < deg; j += 32) { e_id[o + j] = b + j; nbr[o + j] = col[b + j]; }
   }
 }
 
@@ -123,5 +141,12 @@ extern "C" int gglb200_sample_pick(const int64_t* rowptr, const int64_t* col, co
   sample_pick_kernel<<<(unsigned)((n_seeds + 127) / 128), 128, 0, stream>>>(rowptr, col, idx, n_seeds, n_nodes, fanout, replace, seed,
                                                                             out_ptr, e_id, nbr);
   GGL_LAUNCHED("sample_pick");
+  if (fanout < 0 || !replace) {   // rows taken whole: hubs are copied warp-wide
+    int64_t grid = (n_seeds + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    sample_copy_hubs_kernel<<<(unsigned)grid, 256, 0, stream>>>(rowptr, col, idx, n_seeds, n_nodes, fanout, replace, out_ptr, e_id, nbr);
+    GGL_LAUNCHED("sample_copy_hubs");
+  }
   return GGL_OK;
 }
