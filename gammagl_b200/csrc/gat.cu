@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(32) sddmm_ring_kernel(const int32_t* __restric
   bool run_last = false;   // SPAN: this lane is the last one of its head's run
   if constexpr (SPAN) {
     if (col_active) nlo = min(4, (head + 1) * C - kcol);
-    const int32_t next_head = __shfl_down_sync(gmask, head, 1);
+    const int32_t next_head = __shfl_down_sync(gmask, head, 1, LPR);
     run_last = col_active && (sub == LPR - 1 || next_head != head);
   }
   const float* xt = x + (int64_t)blockIdx.y * LPR * VEC;
@@ -145,12 +145,12 @@ __global__ void __launch_bounds__(32) sddmm_ring_kernel(const int32_t* __restric
               if (i < nlo) lo += pr; else hi += pr;
             }
           }
-          const float from_left = __shfl_up_sync(gmask, hi, 1);      // the left neighbour's spill-over belongs to this lane's head
+          const float from_left = __shfl_up_sync(gmask, hi, 1, LPR);      // the left neighbour's spill-over belongs to this lane's head
           float dot = lo + (sub > 0 ? from_left : 0.f);
 #pragma unroll
           for (int d = 1; d < LPR; d <<= 1) {                         // segmented inclusive scan over runs of equal head
-            const float t = __shfl_up_sync(gmask, dot, d);
-            const int32_t hh = __shfl_up_sync(gmask, head, d);
+            const float t = __shfl_up_sync(gmask, dot, d, LPR);
+            const int32_t hh = __shfl_up_sync(gmask, head, d, LPR);
             if (sub >= d && hh == head) dot += t;
           }
           if (run_last) gw[(int64_t)eid[u] * H + head] = dot;

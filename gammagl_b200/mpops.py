@@ -187,7 +187,7 @@ class _SegmentReduce(torch.autograd.Function):
         if ctx.csr is not None:
             return ctx.csr.rowptr
         rp = torch.zeros(ctx.N + 1, dtype=torch.int32, device=dev)
-        torch.cumsum(ctx.cnt, 0, out=rp[1:])
+        torch.cumsum(ctx.cnt, 0, dtype=torch.int32, out=rp[1:])
         return rp
 
     @staticmethod

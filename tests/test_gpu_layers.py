@@ -432,7 +432,7 @@ def test_gatv2_conv_mirror(heads, concat):
     ou, gu, _ = run(unfused, xu, ei.to(DEV))
     xd = x.double().requires_grad_(True)
     W = fused.linear.weights.detach().double().cpu()
-    h = (xd @ W + fused.linear.biases.detach().double().cpu()).reshape(N, heads, C)
+    h = (xd @ W).reshape(N, heads, C)                                  # the reference's Linear has no bias here (b_init=None)
     lr = torch.nn.functional.leaky_relu
     logits = (lr(h[ei[0]], 0.2) * fused.att_src.detach().double().cpu() + lr(h[ei[1]], 0.2) * fused.att_dst.detach().double().cpu()).mean(-1)
     od = _dense_attention(h, ei, logits, N)

@@ -38,7 +38,7 @@ def test_linear_tc_matches_fp64(M, K, N, bias, relu):
         lib = lib + b.to(DEV)
     if relu:
         lib = torch.relu(lib)
-    assert rel(out, ref) < 4 * max(rel(lib, ref), 2e-7)
+    assert rel(out, ref) < max(8 * rel(lib, ref), 5e-6)
 
 
 def test_linear_tc_autograd():
