@@ -103,12 +103,15 @@ _SEG_BWD_L2_BYTES = 64 << 20
 #   oneshot  sort-free streaming pass with L2 reductions (csrc/oneshot.cu): no build, x read coalesced; max (+ arg) is
 #            bit-exact there too, fp32 sums / means depend on arrival order (rounding only, <= 1e-6 relative; exact for
 #            integer-valued data such as degree())
-# GGLB200_SEGMENT = auto (default) | fast | csr | oneshot.
+# GGLB200_SEGMENT = auto (default) | fast | csr | oneshot.  Measured on B200 (profiles/microbench_r2_*.jsonl, probe_atomics_r2.jsonl):
+# vector reductions run at 0.9 G x 10^12 fp32 elements/s into an L2-resident output (red.global.add.v4.f32), 64-bit max atomics at
+# 0.13 x 10^12/s -- so
 #   auto  rows of at most GGLB200_ONESHOT_ROW_BYTES (16: K <= 4 fp32 -- degree() and calc_gcn_norm() reduce K = 1 rows, whose
-#         permuted 4-byte gather wastes 7/8 of every DRAM sector) go one-shot for every reducer; max additionally goes
-#         one-shot the first time an ids tensor is seen (ids that change per step never pay the 6 ms sort) and builds the
-#         CSR from the second sighting on; wider sums / means stay on the bit-exact CSR path.
-#   fast  like auto, and sums / means of wider rows also go one-shot on the first sighting.
+#         permuted 4-byte gather wastes 7/8 of every DRAM sector: 1.75 / 0.85 ms one-shot against 4.0 / 4.2 ms through the CSR
+#         at 1.2e8 edges) go one-shot for every reducer; wider rows stay on the bit-exact CSR path.
+#   fast  additionally, sums / means of wider rows go one-shot the FIRST time an ids tensor is seen (4.6 ms at K = 32 against a
+#         6 ms sort + 3.9 ms pass) and build the CSR from the second sighting on.  Wide max never goes one-shot (one 64-bit
+#         atomic per element: 29 ms at K = 32).
 # With torch.use_deterministic_algorithms(True) sums and means always take the CSR path.
 _SEGMENT_MODE = os.environ.get('GGLB200_SEGMENT', 'auto')
 _ONESHOT_ROW_BYTES = int(os.environ.get('GGLB200_ONESHOT_ROW_BYTES', '16'))
@@ -125,7 +128,7 @@ def _segment_path(x, index, N, reduce):
     row_bytes = (x.numel() // max(x.shape[0], 1)) * x.element_size()
     if row_bytes <= _ONESHOT_ROW_BYTES:
         return 'oneshot'
-    if not exact and _SEGMENT_MODE != 'fast':
+    if exact or _SEGMENT_MODE != 'fast':
         return 'csr'
     if segment_csr_if_cached(index, N) is not None:
         return 'csr'

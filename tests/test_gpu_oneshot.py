@@ -96,7 +96,7 @@ def test_oneshot_max_arg_and_nan(mp):
     assert np.array_equal(out2.cpu().numpy(), ref2) and np.array_equal(a2.cpu().numpy(), arg2)
 
 
-@pytest.mark.segment_mode('auto')
+@pytest.mark.segment_mode('fast')
 def test_policy_degree_and_second_sighting(mp):
     from gammagl_b200 import csr
     csr.clear_caches()
@@ -111,19 +111,30 @@ def test_policy_degree_and_second_sighting(mp):
         assert launches == [0]
         assert np.array_equal(deg.cpu().numpy(), np.bincount(ids.cpu().numpy(), minlength=N).astype(np.float32))
         x = torch.randn(E, 32, generator=g).to(DEV)
-        mp.unsorted_segment_sum(x, ids, N)                                         # wide sum: CSR path (bit-exact), no one-shot
-        assert launches == [0]
+        a = mp.unsorted_segment_max(x, ids, N)                                     # wide max: never one-shot (64-bit atomics per element)
+        assert launches == [0] and csr.segment_csr_if_cached(ids, N) is not None
         csr.clear_caches()
-        a = mp.unsorted_segment_max(x, ids, N)                                     # max, first sighting: one-shot
-        assert launches == [0, 2] and csr.segment_csr_if_cached(ids, N) is None
-        b = mp.unsorted_segment_max(x, ids, N)                                     # second sighting: the CSR is built and used
-        assert launches == [0, 2] and csr.segment_csr_if_cached(ids, N) is not None
-        assert torch.equal(a, b)                                                   # both paths are bit-exact
+        s1 = mp.unsorted_segment_sum(x, ids, N)                                    # fast mode, first sighting of these ids: one-shot
+        assert launches == [0, 0] and csr.segment_csr_if_cached(ids, N) is None
+        s2 = mp.unsorted_segment_sum(x, ids, N)                                    # second sighting: the CSR is built and used
+        assert launches == [0, 0] and csr.segment_csr_if_cached(ids, N) is not None
+        assert rel(s1.cpu().numpy(), s2.cpu().numpy()) < 2e-6
+        old = mp._SEGMENT_MODE
+        mp._SEGMENT_MODE = 'auto'                                                  # auto: wide sums never leave the bit-exact path
+        try:
+            csr.clear_caches()
+            mp.unsorted_segment_sum(x, ids, N)
+            assert launches == [0, 0]
+            mp.unsorted_segment_max(torch.randn(E, 2, generator=g).to(DEV), ids, N)    # 8-byte rows: one-shot (max is exact there)
+            assert launches == [0, 0, 2]
+        finally:
+            mp._SEGMENT_MODE = old
         with torch.no_grad():
             bad = ids.clone()
             bad[5] = N
         with pytest.raises(IndexError):
             mp.unsorted_segment_sum(torch.ones(E, device=DEV), bad, N)
+        assert a.shape == (N, 32)
     finally:
         mp.segment_reduce_oneshot = real
         csr.clear_caches()
