@@ -292,6 +292,8 @@ struct GatBwdSrcState {
   GatDims d;
   const float* xcat; int64_t xstride; int32_t n_rows;
   float* gx; float* gs_src; float* part;  // partials: [chunk][K + H]
+  float* gs_dst;      // merged backward: grad s_dst[i, h] accumulated by L2 reductions from this pass (NULL = separate pass)
+  int32_t id_off;     // merged backward: float offset of the destination id stored behind the per-head statistics of a gathered row
   float4 xs, xs_next; float ss, ss_next; int32_t next_row;
   float4 acc; float gss;
   __device__ __forceinline__ void reset() { acc = make_float4(0, 0, 0, 0); gss = 0.f; }
@@ -323,7 +325,14 @@ struct GatBwdSrcState {
     if (active) {
       acc.x = fmaf(alpha, g4.x, acc.x); acc.y = fmaf(alpha, g4.y, acc.y);
       acc.z = fmaf(alpha, g4.z, acc.z); acc.w = fmaf(alpha, g4.w, acc.w);
-      gss = fmaf(alpha * (dotp - D), pre > 0.f ? 1.f : d.slope, gss);
+      const float ge = alpha * (dotp - D) * (pre > 0.f ? 1.f : d.slope);   // d loss / d pre_e: the same scalar feeds s_src[j] and s_dst[i]
+      gss += ge;
+      if (gs_dst != nullptr && writer) {
+        // merged backward: grad s_dst[i, h] += ge by a reduction in the L2 (one scalar per head and edge; [N, H] stays L2-resident),
+        // instead of a second streaming pass over the forward CSR.  i rides in the gathered row behind the statistics.
+        const int32_t i = __float_as_int(lds1(row_addr + (uint32_t)id_off * 4));
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gs_dst + (int64_t)i * d.H + head), "f"(ge) : "memory");
+      }
     }
   }
   __device__ __forceinline__ void row_end(int32_t row, int32_t) {
@@ -343,10 +352,12 @@ struct GatBwdSrcState {
 template <int LPR>
 __global__ void __launch_bounds__(32) gat_bwd_src_kernel(const GatStream a, const GatDims d, const float* __restrict__ xcat,
                                                          int64_t xstride, float* __restrict__ gx, float* __restrict__ gs_src,
-                                                         float* __restrict__ part, int32_t pitch) {
+                                                         float* __restrict__ part, float* __restrict__ gs_dst, int32_t id_off,
+                                                         int32_t pitch) {
   extern __shared__ __align__(16) unsigned char ring_smem[];
   const int lane = threadIdx.x & 31, sub = lane & (LPR - 1);
   GatBwdSrcState st;
+  st.gs_dst = gs_dst; st.id_off = id_off;
   st.kcol = sub * 4; st.active = st.kcol < d.K; st.head = st.active ? st.kcol / d.C : 0;
   st.writer = st.active && (sub & (d.LH - 1)) == 0; st.sub = sub; st.gmask = group_mask<LPR>(lane);
   st.d = d; st.xcat = xcat; st.xstride = xstride; st.n_rows = a.n_rows; st.gx = gx; st.gs_src = gs_src; st.part = part;
@@ -740,8 +751,39 @@ extern "C" int gglb200_gat_bwd_src(const int32_t* rowptr_t, const int32_t* col_t
   const size_t rowbytes = (size_t)gcat_stride * 4;
   a.rowb = (uint32_t)rowbytes;
   float* part = (float*)workspace;
-  GGL_GAT_DISPATCH(gat_bwd_src_kernel, d, xcat, xcat_stride, gx, gs_src, part);
+  GGL_GAT_DISPATCH(gat_bwd_src_kernel, d, xcat, xcat_stride, gx, gs_src, part, (float*)nullptr, 0);
   GGL_LAUNCHED("gat_bwd_src");
+  if (a.has_long) {
+    gat_sum_finalize_kernel<<<sm_count() * 2, 256, 0, stream>>>(plan_t, part, d.K + H, d.W, gx, d.K, d.K, gs_src, H, a.ws_chunks);
+    GGL_LAUNCHED("gat_sum_finalize");
+  }
+  return GGL_OK;
+}
+
+// The whole backward in ONE streaming pass over the transposed CSR: as gglb200_gat_bwd_src, and every edge also adds its
+// d loss / d pre_e to grad s_dst[i, h] with a reduction in the L2 (red.global.add.f32; gs_dst [N, H] is zero-filled here).  gcat rows
+// carry the destination id behind the statistics: [gout (K) | {s_dst, m, 1/s, D} x H | int32 row id, 0, 0, 0].  grad s_dst is summed
+// in arrival order (rounding differs run to run in the last bits); grad x and grad s_src are those of the two-pass form.
+extern "C" int gglb200_gat_bwd(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* plan_t, const float* gcat,
+                               int64_t gcat_stride, const float* xcat, int64_t xcat_stride, float slope, float* gx, float* gs_src,
+                               float* gs_dst, int64_t n_rows, int64_t E, int32_t H, int32_t C, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_rows == 0) return GGL_OK;
+  GatStream a; GatDims d; int lpr;
+  int st = gat_setup("gat_bwd", rowptr_t, col_t, plan_t, n_rows, E, H, C, H * C + H, workspace, workspace_bytes, &a, &d, &lpr);
+  if (st) return st;
+  GGL_REQUIRE(gcat && xcat && gx && gs_src && gs_dst, GGL_EINVAL, "gat_bwd: NULL pointer");
+  GGL_REQUIRE(gcat_stride == d.K + 4 * H + 4 && xcat_stride % 4 == 0 && ((uintptr_t)gcat | (uintptr_t)xcat | (uintptr_t)gx) % 16 == 0,
+              GGL_EINVAL, "gat_bwd: gcat rows must be [gout | {s_dst,m,1/s,D} x H | row id, 0, 0, 0], 16-byte aligned");
+  GGL_CUDA(cudaMemsetAsync(gs_dst, 0, (size_t)n_rows * H * sizeof(float), stream));
+  d.slope = slope;
+  a.src = gcat; a.src_stride = gcat_stride;
+  const size_t rowbytes = (size_t)gcat_stride * 4;
+  a.rowb = (uint32_t)rowbytes;
+  float* part = (float*)workspace;
+  GGL_GAT_DISPATCH(gat_bwd_src_kernel, d, xcat, xcat_stride, gx, gs_src, part, gs_dst, (int32_t)(d.K + 4 * H));
+  GGL_LAUNCHED("gat_bwd_merged");
   if (a.has_long) {
     gat_sum_finalize_kernel<<<sm_count() * 2, 256, 0, stream>>>(plan_t, part, d.K + H, d.W, gx, d.K, d.K, gs_src, H, a.ws_chunks);
     GGL_LAUNCHED("gat_sum_finalize");

@@ -738,6 +738,11 @@ class _EdgeSoftmax(torch.autograd.Function):
         return gl, None, None
 
 
+# fused GAT backward: 'merged' = one streaming pass over the transposed CSR, grad s_dst by L2 reductions (arrival-order sums);
+# 'two_pass' = the deterministic form (second pass over the forward CSR).  torch.use_deterministic_algorithms(True) forces two_pass.
+_GAT_BWD = os.environ.get('GGLB200_GAT_BWD', 'merged')
+
+
 def gat_fusable(H, C):
     lh = C // 4
     return C % 4 == 0 and lh >= 1 and (lh & (lh - 1)) == 0 and H * C <= 128
@@ -794,13 +799,23 @@ class _GatAggregate(torch.autograd.Function):
         gout = grad_out.contiguous().view(N, K).float()
         with torch.cuda.device(dev):
             D = (out * gout).view(N, H, C).sum(-1)                           # row term of the softmax Jacobian, per node
-            gcat = torch.empty((N, K + 4 * H), dtype=torch.float32, device=dev)
+            merged = _GAT_BWD == 'merged' and not torch.are_deterministic_algorithms_enabled()
+            W = K + 4 * H + (4 if merged else 0)
+            gcat = torch.empty((N, W), dtype=torch.float32, device=dev)
             gcat[:, :K] = gout
-            gcat[:, K:] = torch.stack([sd, m, 1.0 / s, D], dim=2).view(N, 4 * H)
+            gcat[:, K:K + 4 * H] = torch.stack([sd, m, 1.0 / s, D], dim=2).view(N, 4 * H)
             gx = torch.empty((N, K), dtype=torch.float32, device=dev)
             gs_src = torch.empty((N, H), dtype=torch.float32, device=dev)
             gs_dst = torch.empty((N, H), dtype=torch.float32, device=dev)
             ws, nb = _GatAggregate._ws(g.bwd, H, C, dev)
+            if merged:
+                # ONE pass: every edge adds its d loss / d pre to grad s_dst[i] with an L2 reduction; the destination id rides in the row
+                gcat[:, K + 4 * H:] = 0
+                gcat[:, K + 4 * H] = torch.arange(N, dtype=torch.int32, device=dev).view(torch.float32)
+                _lib.check(lib.gglb200_gat_bwd(_ptr(g.bwd.rowptr), _ptr(g.bwd.col), _ptr(g.bwd.plan), _ptr(gcat), W, _ptr(xcat), K + Hp,
+                                               ctx.slope, _ptr(gx), _ptr(gs_src), _ptr(gs_dst), N, g.E, H, C, _ptr(ws), nb, _stream(dev)),
+                           'gat_bwd')
+                return gx.view(N, H, C), gs_src, gs_dst, None, None
             _lib.check(lib.gglb200_gat_bwd_src(_ptr(g.bwd.rowptr), _ptr(g.bwd.col), _ptr(g.bwd.plan), _ptr(gcat), K + 4 * H, _ptr(xcat),
                                                K + Hp, ctx.slope, _ptr(gx), _ptr(gs_src), N, g.E, H, C, _ptr(ws), nb, _stream(dev)),
                        'gat_bwd_src')

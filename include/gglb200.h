@@ -347,6 +347,13 @@ GGL_API int gglb200_gat_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, c
                         int64_t gcat_stride, const float* xcat, int64_t xcat_stride, float slope, float* gx,
                         float* gs_src, int64_t n_rows, int64_t E, int32_t H, int32_t C, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* bwd     the whole backward in ONE pass over the transposed CSR: gglb200_gat_bwd_src plus grad s_dst accumulated by L2 reductions
+ *         (red.global.add.f32 per head and edge; gs_dst [N,H] zero-filled by the callee, summed in arrival order).  gcat rows
+ *         are [gout | {s_dst, m, 1/s, D} x H | int32 row id, 0, 0, 0] (stride H*C + 4H + 4). */
+GGL_API int gglb200_gat_bwd(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* plan_t, const float* gcat,
+                    int64_t gcat_stride, const float* xcat, int64_t xcat_stride, float slope, float* gx, float* gs_src,
+                    float* gs_dst, int64_t n_rows, int64_t E, int32_t H, int32_t C, void* workspace, size_t workspace_bytes,
+                    void* stream);
 GGL_API int gglb200_gat_bwd_dst(const int32_t* rowptr, const int32_t* col, const int32_t* plan, const float* xcat,
                         int64_t xcat_stride, const float* gcat, int64_t gcat_stride, float slope, float* gs_dst,
                         int64_t n_rows, int64_t E, int32_t H, int32_t C, void* workspace, size_t workspace_bytes,

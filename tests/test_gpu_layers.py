@@ -238,14 +238,19 @@ def test_gat_aggregate_fused_vs_composed(H, C, hub):
     alpha = ex / (den[dst] + 1e-16)
     ref = torch.zeros(N, H, C, dtype=torch.float64).index_add_(0, dst, alpha.unsqueeze(-1) * xd[src])
     ref.backward(gout.double())
-    xg, sg, dg = (t.to(DEV).requires_grad_(True) for t in (x, ss, sd))
-    out = mpops.gat_aggregate(ei.to(DEV), xg, sg, dg, 0.2)
-    out.backward(gout.to(DEV))
-    assert rel(out, ref) < 2e-5
-    assert float(out[:40].abs().max()) == 0.0                # empty rows
-    assert rel(xg.grad, xd.grad) < 5e-5
-    assert rel(sg.grad, ssd.grad) < 1e-4
-    assert rel(dg.grad, sdd.grad) < 1e-4
+    for mode in ('merged', 'two_pass'):                      # one-pass backward (grad s_dst by L2 reductions) and the deterministic form
+        old_mode, mpops._GAT_BWD = mpops._GAT_BWD, mode
+        try:
+            xg, sg, dg = (t.to(DEV).requires_grad_(True) for t in (x, ss, sd))
+            out = mpops.gat_aggregate(ei.to(DEV), xg, sg, dg, 0.2)
+            out.backward(gout.to(DEV))
+        finally:
+            mpops._GAT_BWD = old_mode
+        assert rel(out, ref) < 2e-5
+        assert float(out[:40].abs().max()) == 0.0                # empty rows
+        assert rel(xg.grad, xd.grad) < 5e-5, mode
+        assert rel(sg.grad, ssd.grad) < 1e-4, mode
+        assert rel(dg.grad, sdd.grad) < 1e-4, mode
     # and against the unfused GPU ops
     a2 = mpops.segment_softmax(torch.nn.functional.leaky_relu(ss.to(DEV)[ei[0].to(DEV)] + sd.to(DEV)[ei[1].to(DEV)], 0.2), ei[1].to(DEV), N)
     assert rel(out, mpops.bspmm(ei.to(DEV), a2, x.to(DEV))) < 2e-5
