@@ -34,5 +34,25 @@ for H, C in ((8, 8), (4, 16), (1, 64), (2, 4), (4, 25), (3, 5)):
         ss = torch.randn(N, H, generator=g).to(dev).requires_grad_(True)
         sd = torch.randn(N, H, generator=g).to(dev).requires_grad_(True)
         mpops.gat_aggregate(ei, x3, ss, sd, 0.2).square().sum().backward()
+# round-2 kernels: spanning lanes (C % 4 != 0), edge-id max, bipartite rows, sort-free segment reduce, tcgen05 GEMM, sampler, merged GAT backward
+from gammagl_b200 import sampler  # noqa: E402
+for H, C in ((4, 25), (3, 12)):
+    x3 = torch.randn(N, H, C, generator=g).to(dev).requires_grad_(True)
+    wh = torch.rand(E, H, generator=g).to(dev).requires_grad_(True)
+    mpops.bspmm(ei, wh, x3).sum().backward()
+xb = torch.randn(N, 20, generator=g).to(dev).requires_grad_(True)
+mpops.gspmm_max_edge(ei, w, xb).sum().backward()
+eib = torch.stack([ei[0], ei[1] % 300])
+mpops.gspmm(eib, w, xb, 'mean', num_dst=300).sum().backward()
+for K in (1, 2, 4, 8, 33):
+    m = torch.randn(E, K, generator=g).to(dev).requires_grad_(True)
+    for code in (0, 1, 2):
+        mpops.segment_reduce_oneshot(m.detach(), ei[1], N, code)
+a = torch.randn(300, 100, generator=g).to(dev)
+wl = torch.randn(100, 192, generator=g).to(dev)
+mpops.linear_tc(a, wl, torch.randn(192, generator=g).to(dev), True)
+ns = sampler.NeighborSampler(ei, [5, 3], num_nodes=N, seed=1)
+ns.sample(torch.arange(50))
+sampler.neighbor_sample(ns.rowptr, ns.col, torch.arange(20, device=dev), [4, -1], directed=False, seed=2)
 torch.cuda.synchronize()
 print('sanitize cases done')
