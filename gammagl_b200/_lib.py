@@ -59,6 +59,8 @@ SIGNATURES = {
     'gglb200_gat_bwd_src': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _c.c_float, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _sz, _vp]),
     'gglb200_gat_bwd': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _c.c_float, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _sz, _vp]),
     'gglb200_gat_bwd_dst': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _c.c_float, _vp, _i64, _i64, _i32, _i32, _vp, _sz, _vp]),
+    'gglb200_edge_softmax_stats_oneshot': (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
+    'gglb200_edge_softmax_dot_oneshot': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
     'gglb200_edge_softmax_workspace_bytes': (_sz, [_i64, _i32, _i64]),
     'gglb200_edge_softmax_fwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _sz, _vp]),
     'gglb200_edge_softmax_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _sz, _vp]),

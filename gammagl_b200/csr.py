@@ -204,7 +204,26 @@ def note_sighting(segment_ids, num_segments):
     return box[0]
 
 
+_validated = _Lru(64)
+
+
+def validate_ids(ids, n):
+    """Raise IndexError unless every id lies in [0, n).  One min/max pass + host sync per ids tensor (cached by tensor identity like
+    the CSRs): the sort-free kernels skip out-of-range ids instead of dereferencing them, this makes the error loud."""
+    if ids.numel() == 0:
+        return True
+
+    def check():
+        mn, mx = torch.aminmax(ids)
+        mn, mx = int(mn.item()), int(mx.item())
+        if mn < 0 or mx >= int(n):
+            raise IndexError('index out of range: ids span [%d, %d], expected [0, %d)' % (mn, mx, int(n)))
+        return True
+    return _validated.get(ids, int(n), check)
+
+
 def clear_caches():
     _graphs.clear()
     _segments.clear()
     _sightings.clear()
+    _validated.clear()

@@ -358,7 +358,8 @@ static int softmax_args(const char* who, const int32_t* rowptr, const int32_t* p
                         int64_t n_rows, int64_t E, int32_t H, void* ws, size_t ws_bytes, float** m, float** s, void** rest,
                         size_t* rest_bytes) {
   GGL_REQUIRE(n_rows >= 0 && E >= 0 && H >= 1, GGL_EINVAL, "%s: bad sizes", who);
-  GGL_REQUIRE(rowptr && perm && plan && ids, GGL_EINVAL, "%s: NULL pointer", who);
+  GGL_REQUIRE(ids != nullptr && ((rowptr && perm && plan) || (!rowptr && !perm && !plan)), GGL_EINVAL,
+              "%s: ids required; rowptr / perm / plan all set (CSR form) or all NULL (sort-free form)", who);
   const size_t stat = (((size_t)n_rows * H * 4) + 255) & ~(size_t)255;
   GGL_REQUIRE(ws != nullptr && ws_bytes >= 2 * stat, GGL_EWORKSPACE, "%s: workspace %zu < %zu", who, ws_bytes, 2 * stat);
   *m = (float*)ws;
@@ -378,6 +379,21 @@ extern "C" int gglb200_edge_softmax_fwd(const int32_t* rowptr, const int32_t* pe
   float *m, *s; void* rest; size_t rest_bytes;
   int st = softmax_args("edge_softmax_fwd", rowptr, perm, plan, ids, n_rows, E, H, workspace, workspace_bytes, &m, &s, &rest, &rest_bytes);
   if (st) return st;
+  if (rowptr == nullptr) {
+    // sort-free form (csrc/oneshot.cu): exact maxima by red.max on ordered keys, denominators by vector reductions, then the same
+    // element-wise normalisation; sums are in arrival order (rounding only)
+    const bool v4 = H % 4 == 0 && (((uintptr_t)logit | (uintptr_t)alpha) % 16 == 0);
+    st = gglb200_edge_softmax_stats_oneshot(ids, logit, m, s, v4 ? nullptr : alpha, n_rows, E, H, stream_);
+    if (st) return st;
+    if (v4) {
+      softmax_norm4_kernel<<<ew_grid(E * H / 4), 256, 0, stream>>>((const float4*)logit, m, s, ids, (float4*)alpha, E * (H / 4), H / 4);
+      GGL_LAUNCHED("softmax_norm4");
+    } else {
+      softmax_div_kernel<<<ew_grid(E * H), 256, 0, stream>>>(alpha, s, ids, E * H, H);
+      GGL_LAUNCHED("softmax_div");
+    }
+    return GGL_OK;
+  }
   if (softmax_fused_enabled() && H % 4 == 0 && H <= 128 && (((uintptr_t)logit | (uintptr_t)alpha) % 16 == 0)) {
     // two passes: online (max, denominator) per segment over the bulk-copy ring, then one element-wise normalisation
     st = softmax_stats(rowptr, perm, plan, logit, m, s, n_rows, E, H, rest, rest_bytes, stream);
@@ -406,6 +422,19 @@ extern "C" int gglb200_edge_softmax_bwd(const int32_t* rowptr, const int32_t* pe
   float *dot, *unused; void* rest; size_t rest_bytes;
   int st = softmax_args("edge_softmax_bwd", rowptr, perm, plan, ids, n_rows, E, H, workspace, workspace_bytes, &dot, &unused, &rest, &rest_bytes);
   if (st) return st;
+  if (rowptr == nullptr) {   // sort-free form
+    st = gglb200_edge_softmax_dot_oneshot(ids, alpha, galpha, dot, n_rows, E, H, stream_);
+    if (st) return st;
+    if (H % 4 == 0 && (((uintptr_t)alpha | (uintptr_t)galpha | (uintptr_t)glogit) % 16 == 0)) {
+      softmax_bwd4_kernel<<<ew_grid(E * H / 4), 256, 0, stream>>>((const float4*)alpha, (const float4*)galpha, dot, ids, (float4*)glogit,
+                                                                   E * (H / 4), H / 4);
+      GGL_LAUNCHED("softmax_bwd4");
+    } else {
+      softmax_bwd_kernel<<<ew_grid(E * H), 256, 0, stream>>>(alpha, galpha, dot, ids, glogit, E * H, H);
+      GGL_LAUNCHED("softmax_bwd");
+    }
+    return GGL_OK;
+  }
   if (softmax_fused_enabled() && H % 4 == 0 && H <= 128 && (((uintptr_t)alpha | (uintptr_t)galpha | (uintptr_t)glogit) % 16 == 0)) {
     // two passes: per-segment dot over the ring (both rows gathered per edge), then one element-wise pass
     st = softmax_dot(rowptr, perm, plan, alpha, galpha, dot, n_rows, E, H, rest, rest_bytes, stream);

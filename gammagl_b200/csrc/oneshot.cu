@@ -144,6 +144,74 @@ __global__ void __launch_bounds__(256) oneshot_max_decode_kernel(const unsigned 
   }
 }
 
+// ---- sort-free edge softmax (gammagl/utils/softmax.py:29-35) -------------------------------------------------------------------
+// The CSR form gathers 4H-byte logit rows through `perm` (request-bound: 5.5 ms at 1.15e8 edges, H = 8).  Here every pass streams
+// [E, H] in its original order: max by red.global.max.u32 on order-preserving keys, then sum(exp(x - m)) and the backward's
+// sum(alpha * galpha) by vector reductions; the element-wise passes are the existing ones (gat.cu).  No CSR, no sort.
+__global__ void __launch_bounds__(256) softmax_max_kernel(const float* __restrict__ x, const int64_t* __restrict__ ids, uint32_t* __restrict__ mkey,
+                                                          int64_t total, int32_t H, int64_t N) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; t < total; t += stride) {
+    const int64_t e = t / H;
+    const int64_t id = __ldg(ids + e);
+    const float v = __ldcs(x + t);
+    if (id < 0 || id >= N || v != v) continue;
+    asm volatile("red.global.max.u32 [%0], %1;" ::"l"(mkey + id * H + (t - e * H)), "r"(ordered_bits(v)) : "memory");
+  }
+}
+// keys -> floats in place (untouched keys = segments without edges: 0, never read by an edge)
+__global__ void __launch_bounds__(256) softmax_decode_kernel(uint32_t* __restrict__ mkey, int64_t total) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; t < total; t += stride) {
+    const uint32_t k = mkey[t];
+    const uint32_t b = k == 0u ? 0u : (k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+    mkey[t] = b;
+  }
+}
+// s[ids[e], h] += exp(x[e,h] - m[ids[e],h]); p written to alpha when alpha != NULL (the H % 4 != 0 composition divides it in place)
+template <int VEC>
+__global__ void __launch_bounds__(256) softmax_sum_kernel(const float* __restrict__ x, const float* __restrict__ m, const int64_t* __restrict__ ids,
+                                                          float* __restrict__ ssum, float* __restrict__ p_out, int64_t totalv, int32_t HV, int64_t N) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; t < totalv; t += stride) {
+    const int64_t e = t / HV;
+    const int64_t id = __ldg(ids + e);
+    if (id < 0 || id >= N) continue;
+    const int64_t o = (id * HV + (t - e * HV)) * VEC;
+    if constexpr (VEC == 4) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + t);
+      const float4 mm = __ldg(reinterpret_cast<const float4*>(m + o));
+      red_add4(ssum + o, expf(v.x - mm.x), expf(v.y - mm.y), expf(v.z - mm.z), expf(v.w - mm.w));
+    } else {
+      const float pv = expf(__ldcs(x + t) - __ldg(m + o));
+      if (p_out) p_out[t] = pv;
+      red_add(ssum + o, pv);
+    }
+  }
+}
+// dot[ids[e], h] += alpha[e,h] * galpha[e,h]
+template <int VEC>
+__global__ void __launch_bounds__(256) softmax_dotsum_kernel(const float* __restrict__ a, const float* __restrict__ g, const int64_t* __restrict__ ids,
+                                                             float* __restrict__ dot, int64_t totalv, int32_t HV, int64_t N) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; t < totalv; t += stride) {
+    const int64_t e = t / HV;
+    const int64_t id = __ldg(ids + e);
+    if (id < 0 || id >= N) continue;
+    const int64_t o = (id * HV + (t - e * HV)) * VEC;
+    if constexpr (VEC == 4) {
+      const float4 av = __ldcs(reinterpret_cast<const float4*>(a) + t), gv = __ldcs(reinterpret_cast<const float4*>(g) + t);
+      red_add4(dot + o, av.x * gv.x, av.y * gv.y, av.z * gv.z, av.w * gv.w);
+    } else {
+      red_add(dot + o, __ldcs(a + t) * __ldcs(g + t));
+    }
+  }
+}
+
 static int ew_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -253,5 +321,43 @@ extern "C" int gglb200_segment_reduce(int reduce, const void* x_, const int64_t*
     oneshot_max_decode_kernel<<<ew_grid(N * K), 256, 0, stream>>>(keys, x, out, arg, N * K, (int32_t)K, arg_empty);
     GGL_LAUNCHED("oneshot_max_decode");
   }
+  return GGL_OK;
+}
+
+// statistics of the sort-free edge softmax: stat_m[N,H] (exact segment maxima, 0 for segments without edges) and stat_s[N,H] =
+// sum exp(x - m); `p_or_null` receives exp(x - m) per edge when H % 4 != 0 (the caller divides it in place).
+extern "C" int gglb200_edge_softmax_stats_oneshot(const int64_t* ids, const float* logit, float* stat_m, float* stat_s, float* p_or_null,
+                                                  int64_t n_rows, int64_t E, int32_t H, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(n_rows >= 0 && E >= 0 && H >= 1, GGL_EINVAL, "edge_softmax_stats_oneshot: bad sizes");
+  if (n_rows == 0 || E == 0) return GGL_OK;
+  GGL_REQUIRE(ids && logit && stat_m && stat_s, GGL_EINVAL, "edge_softmax_stats_oneshot: NULL pointer");
+  GGL_CUDA(cudaMemsetAsync(stat_m, 0, (size_t)n_rows * H * 4, stream));
+  GGL_CUDA(cudaMemsetAsync(stat_s, 0, (size_t)n_rows * H * 4, stream));
+  softmax_max_kernel<<<ew_grid(E * H), 256, 0, stream>>>(logit, ids, (uint32_t*)stat_m, E * H, H, n_rows);
+  GGL_LAUNCHED("softmax_max");
+  softmax_decode_kernel<<<ew_grid(n_rows * H), 256, 0, stream>>>((uint32_t*)stat_m, n_rows * H);
+  GGL_LAUNCHED("softmax_decode");
+  if (H % 4 == 0 && p_or_null == nullptr && (((uintptr_t)logit | (uintptr_t)stat_m | (uintptr_t)stat_s) & 15) == 0)
+    softmax_sum_kernel<4><<<ew_grid(E * (H / 4)), 256, 0, stream>>>(logit, stat_m, ids, stat_s, nullptr, E * (H / 4), H / 4, n_rows);
+  else
+    softmax_sum_kernel<1><<<ew_grid(E * H), 256, 0, stream>>>(logit, stat_m, ids, stat_s, p_or_null, E * H, H, n_rows);
+  GGL_LAUNCHED("softmax_sum");
+  return GGL_OK;
+}
+
+// dot[N,H] = segment sum of alpha * galpha (the row term of the softmax Jacobian), sort-free
+extern "C" int gglb200_edge_softmax_dot_oneshot(const int64_t* ids, const float* alpha, const float* galpha, float* dot, int64_t n_rows,
+                                                int64_t E, int32_t H, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GGL_REQUIRE(n_rows >= 0 && E >= 0 && H >= 1, GGL_EINVAL, "edge_softmax_dot_oneshot: bad sizes");
+  if (n_rows == 0 || E == 0) return GGL_OK;
+  GGL_REQUIRE(ids && alpha && galpha && dot, GGL_EINVAL, "edge_softmax_dot_oneshot: NULL pointer");
+  GGL_CUDA(cudaMemsetAsync(dot, 0, (size_t)n_rows * H * 4, stream));
+  if (H % 4 == 0 && (((uintptr_t)alpha | (uintptr_t)galpha | (uintptr_t)dot) & 15) == 0)
+    softmax_dotsum_kernel<4><<<ew_grid(E * (H / 4)), 256, 0, stream>>>(alpha, galpha, ids, dot, E * (H / 4), H / 4, n_rows);
+  else
+    softmax_dotsum_kernel<1><<<ew_grid(E * H), 256, 0, stream>>>(alpha, galpha, ids, dot, E * H, H, n_rows);
+  GGL_LAUNCHED("softmax_dotsum");
   return GGL_OK;
 }

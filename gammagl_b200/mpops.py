@@ -23,7 +23,7 @@ import os
 import torch
 
 from . import _lib
-from .csr import _ptr, _stream, graph_of, note_sighting, require_cuda, segment_csr_if_cached, segment_csr_of
+from .csr import _ptr, _stream, graph_of, note_sighting, require_cuda, segment_csr_if_cached, segment_csr_of, validate_ids
 
 use_ext = True  # mirrors the module flag of the reference (torch.py:2-7); always the native path here
 PROFILE = None  # bench.py sets this to a list: spmm_csr then appends (n_rows, start_event, end_event) per launch
@@ -687,10 +687,25 @@ def bspmm(index, weight=None, x=None, reduce='sum'):
 # ------------------------------------------------------------------------------------------------
 # fused edge softmax (gammagl/utils/softmax.py:10-36)
 # ------------------------------------------------------------------------------------------------
+# segment_softmax: 'oneshot' = sort-free streaming passes with L2 reductions (no CSR; sums in arrival order), 'csr' = statistics over
+# the segment CSR (serial-order sums).  GGLB200_SOFTMAX_PATH = auto (default: oneshot, csr under torch.use_deterministic_algorithms)
+# | oneshot | csr.
+_SOFTMAX_PATH = os.environ.get('GGLB200_SOFTMAX_PATH', 'auto')
+
+
+def _softmax_oneshot():
+    if _SOFTMAX_PATH == 'csr':
+        return False
+    if _SOFTMAX_PATH == 'oneshot':
+        return True
+    return not torch.are_deterministic_algorithms_enabled()
+
+
 class _EdgeSoftmax(torch.autograd.Function):
     @staticmethod
-    def _workspace(csr, H, dev):
-        need = _lib.load().gglb200_edge_softmax_workspace_bytes(csr.n_rows, H, csr.n_chunks if csr.has_long else 0)
+    def _workspace(csr, n_rows, H, dev):
+        n_chunks = csr.n_chunks if (csr is not None and csr.has_long) else 0
+        need = _lib.load().gglb200_edge_softmax_workspace_bytes(n_rows, H, n_chunks)
         return torch.empty(need, dtype=torch.uint8, device=dev), need
 
     @staticmethod
@@ -705,24 +720,31 @@ class _EdgeSoftmax(torch.autograd.Function):
         H = data.numel() // max(E, 1)
         alpha = torch.empty_like(data)
         ctx.shape = tuple(data.shape)
+        ctx.n_rows = int(num_segments)
         if E == 0:
-            ctx.csr = None
+            ctx.empty = True
             return alpha
-        csr = segment_csr_of(segment_ids, int(num_segments))
+        ctx.empty = False
         ids = segment_ids if segment_ids.dtype == torch.int64 and segment_ids.is_contiguous() else segment_ids.to(torch.int64).contiguous()
+        if _softmax_oneshot():
+            validate_ids(segment_ids, num_segments)
+            csr = None
+        else:
+            csr = segment_csr_of(segment_ids, int(num_segments))
         dev = data.device
         with torch.cuda.device(dev):
             _lib.tune_device(dev.index)
-            ws, nb = _EdgeSoftmax._workspace(csr, H, dev)
-            _lib.check(lib.gglb200_edge_softmax_fwd(_ptr(csr.rowptr), _ptr(csr.perm), _ptr(csr.plan), _ptr(ids), _ptr(data),
-                                                    _ptr(alpha), csr.n_rows, E, H, _ptr(ws), nb, _stream(dev)), 'edge_softmax_fwd')
+            ws, nb = _EdgeSoftmax._workspace(csr, ctx.n_rows, H, dev)
+            _lib.check(lib.gglb200_edge_softmax_fwd(_ptr(csr.rowptr) if csr else None, _ptr(csr.perm) if csr else None,
+                                                    _ptr(csr.plan) if csr else None, _ptr(ids), _ptr(data), _ptr(alpha), ctx.n_rows, E, H,
+                                                    _ptr(ws), nb, _stream(dev)), 'edge_softmax_fwd')
         ctx.csr, ctx.H, ctx.ids = csr, H, ids
         ctx.save_for_backward(alpha)
         return alpha
 
     @staticmethod
     def backward(ctx, galpha):
-        if ctx.csr is None:
+        if ctx.empty:
             return torch.zeros(ctx.shape, dtype=galpha.dtype, device=galpha.device), None, None
         lib = _lib.load()
         (alpha,) = ctx.saved_tensors
@@ -730,11 +752,12 @@ class _EdgeSoftmax(torch.autograd.Function):
         gl = torch.empty_like(alpha)
         dev = alpha.device
         csr = ctx.csr
+        E = alpha.shape[0]
         with torch.cuda.device(dev):
-            ws, nb = _EdgeSoftmax._workspace(csr, ctx.H, dev)
-            _lib.check(lib.gglb200_edge_softmax_bwd(_ptr(csr.rowptr), _ptr(csr.perm), _ptr(csr.plan), _ptr(ctx.ids), _ptr(alpha),
-                                                    _ptr(galpha), _ptr(gl), csr.n_rows, csr.E, ctx.H, _ptr(ws), nb, _stream(dev)),
-                       'edge_softmax_bwd')
+            ws, nb = _EdgeSoftmax._workspace(csr, ctx.n_rows, ctx.H, dev)
+            _lib.check(lib.gglb200_edge_softmax_bwd(_ptr(csr.rowptr) if csr else None, _ptr(csr.perm) if csr else None,
+                                                    _ptr(csr.plan) if csr else None, _ptr(ctx.ids), _ptr(alpha), _ptr(galpha), _ptr(gl),
+                                                    ctx.n_rows, E, ctx.H, _ptr(ws), nb, _stream(dev)), 'edge_softmax_bwd')
         return gl, None, None
 
 

@@ -320,6 +320,14 @@ GGL_API int gglb200_bspmm_bwd_w(const int32_t* rowptr, const int32_t* col, const
  * workspace: gglb200_edge_softmax_workspace_bytes(n_rows, H, n_chunks) with n_chunks = plan[0] (0 if unknown and
  * the graph has no row above GGLB200_LONG_ROW edges; E / GGLB200_LONG_CHUNK + E / GGLB200_LONG_ROW + 2 is always safe).
  * ------------------------------------------------------------------------------------------- */
+/* Sort-free form: pass rowptr = perm = plan = NULL (workspace = gglb200_edge_softmax_workspace_bytes(n_rows, H, 0)).  Every pass
+ * streams [E,H] in its original order -- no CSR, no sort, no permuted gather: exact segment maxima by red.global.max.u32 on
+ * order-preserving keys, denominators / Jacobian row terms by vector reductions (arrival-order sums), then the same element-wise
+ * passes.  The two building blocks are exported as well (stat_m / stat_s / dot [n_rows,H] fp32, written fully). */
+GGL_API int gglb200_edge_softmax_stats_oneshot(const int64_t* ids, const float* logit, float* stat_m, float* stat_s, float* p_or_null,
+                                       int64_t n_rows, int64_t E, int32_t H, void* stream);
+GGL_API int gglb200_edge_softmax_dot_oneshot(const int64_t* ids, const float* alpha, const float* galpha, float* dot, int64_t n_rows,
+                                     int64_t E, int32_t H, void* stream);
 GGL_API size_t gglb200_edge_softmax_workspace_bytes(int64_t n_rows, int32_t H, int64_t n_chunks);
 GGL_API int gglb200_edge_softmax_fwd(const int32_t* rowptr, const int32_t* perm, const int32_t* plan, const int64_t* ids,
                              const float* logit, float* alpha, int64_t n_rows, int64_t E, int32_t H,

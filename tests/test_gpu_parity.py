@@ -269,12 +269,17 @@ def test_bspmm_vs_oracle(mp, N, E, H, C, hub):
     assert rel_err(ww.grad.cpu().numpy(), gw_ref) < 1e-5
 
 
+@pytest.mark.parametrize('path', ['csr', 'oneshot'])
 @pytest.mark.parametrize('H', [1, 4, 8, 13])
-def test_segment_softmax_vs_oracle(mp, H):
+def test_segment_softmax_vs_oracle(mp, H, path, monkeypatch):
+    """Both forms of the edge softmax: statistics over the segment CSR (serial-order sums) and the sort-free streaming passes."""
+    monkeypatch.setattr(mp, '_SOFTMAX_PATH', path)
     N, E = 1200, 30000
     index = make_graph(N, E, seed=H, hub=2000)
     g = torch.Generator().manual_seed(17)
     logit = torch.randn(E, H, generator=g) * 3
+    logit[:200] = 9000.0 + torch.randn(200, H, generator=g)          # huge, negative and constant logits: the exact maximum matters
+    logit[200:400] = -7000.0
     ref = O.segment_softmax(logit.numpy(), index[1].numpy(), N)
     ll = logit.to(DEV).requires_grad_(True)
     got = mp.segment_softmax(ll, index[1].to(DEV), N)

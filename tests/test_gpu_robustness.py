@@ -47,6 +47,14 @@ def test_out_of_range_ids_raise(mp):
     e3[1, 5] = N                                   # bad destination id
     with pytest.raises(IndexError):
         mp.gspmm(e3, w, xs, 'sum')
+    lg = torch.randn(E, 4, generator=g).to(DEV)
+    for path in ('csr', 'oneshot'):                # segment_softmax: the CSR build resp. the id validation of the sort-free form
+        old_path, mp._SOFTMAX_PATH = mp._SOFTMAX_PATH, path
+        try:
+            with pytest.raises(IndexError):
+                mp.segment_softmax(lg, bad, N)
+        finally:
+            mp._SOFTMAX_PATH = old_path
     with pytest.raises(IndexError):
         utils.sort_edge_index(e2, num_nodes=N)
     with pytest.raises(IndexError):
