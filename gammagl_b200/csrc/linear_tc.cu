@@ -74,17 +74,28 @@ __global__ void __launch_bounds__(256, 1) linear_tf32x3_kernel(const float* __re
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // ---- A tile -> A_hi / A_lo (canonical layout).  lane <-> row inside a 32-row band, warp strides over (band, K chunk) ----
-  for (int item = warp; item < 4 * KC; item += 8) {
-    const int band = item & 3, kc = item >> 2;
-    const int r = band * 32 + lane;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row0 + r < M && kc * 4 < K) v = __ldg(reinterpret_cast<const float4*>(A + (row0 + r) * K + kc * 4));
-    float4 h, l;
-    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-    const uint32_t off = (uint32_t)kc * (kBM * 16) + (uint32_t)r * 16;
-    *reinterpret_cast<float4*>(a_hi + off) = h;
-    *reinterpret_cast<float4*>(a_lo + off) = l;
+  // ---- A tile -> A_hi / A_lo (canonical layout).  lane <-> row inside a 32-row band, a warp owns KC / 2 (band, K chunk) items:
+  //      all of its 16-byte loads are issued before the first is consumed (the tile load is one DRAM latency, not KC / 2)
+  {
+    constexpr int AI = KC / 2;
+    float4 va[AI];
+#pragma unroll
+    for (int i = 0; i < AI; ++i) {
+      const int item = warp + 8 * i, band = item & 3, kc = item >> 2;
+      const int r = band * 32 + lane;
+      va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + r < M && kc * 4 < K) va[i] = __ldg(reinterpret_cast<const float4*>(A + (row0 + r) * K + kc * 4));
+    }
+#pragma unroll
+    for (int i = 0; i < AI; ++i) {
+      const int item = warp + 8 * i, band = item & 3, kc = item >> 2;
+      const int r = band * 32 + lane;
+      float4 h, l;
+      split_tf32(va[i].x, h.x, l.x); split_tf32(va[i].y, h.y, l.y); split_tf32(va[i].z, h.z, l.z); split_tf32(va[i].w, h.w, l.w);
+      const uint32_t off = (uint32_t)kc * (kBM * 16) + (uint32_t)r * 16;
+      *reinterpret_cast<float4*>(a_hi + off) = h;
+      *reinterpret_cast<float4*>(a_lo + off) = l;
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -96,7 +107,37 @@ __global__ void __launch_bounds__(256, 1) linear_tf32x3_kernel(const float* __re
   const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(a_hi), a_lo_s = (uint32_t)__cvta_generic_to_shared(a_lo);
   const uint32_t b_hi_s = (uint32_t)__cvta_generic_to_shared(b_hi), b_lo_s = (uint32_t)__cvta_generic_to_shared(b_lo);
 
+  // W[:, n0 : n0 + 64] of a chunk, transposed to [n, k]: a thread owns WI (n, K chunk) items = 4 coalesced loads each.  The values
+  // of chunk c + 1 are fetched into registers while the MMAs of chunk c run (W is L2-resident; only the smem tile is single).
+  constexpr int WI = (kNC * KC + 255) / 256;
+  float wv[WI][4];
+  auto load_w = [&](int n0) {
+#pragma unroll
+    for (int i = 0; i < WI; ++i) {
+      const int item = tid + 256 * i, n = item & (kNC - 1), kc = item / kNC;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = kc * 4 + j;
+        wv[i][j] = (item < kNC * KC && k < K && n0 + n < N) ? __ldg(W + (int64_t)k * N + n0 + n) : 0.f;
+      }
+    }
+  };
+  auto store_w = [&]() {
+#pragma unroll
+    for (int i = 0; i < WI; ++i) {
+      const int item = tid + 256 * i, n = item & (kNC - 1), kc = item / kNC;
+      if (item < kNC * KC) {
+        float4 h, l;
+        split_tf32(wv[i][0], h.x, l.x); split_tf32(wv[i][1], h.y, l.y); split_tf32(wv[i][2], h.z, l.z); split_tf32(wv[i][3], h.w, l.w);
+        const uint32_t off = (uint32_t)kc * (kNC * 16) + (uint32_t)n * 16;
+        *reinterpret_cast<float4*>(b_hi + off) = h;
+        *reinterpret_cast<float4*>(b_lo + off) = l;
+      }
+    }
+  };
+
   const int n_chunks = (N + kNC - 1) / kNC;
+  load_w(0);
   for (int c = 0; c < n_chunks; ++c) {
     const int n0 = c * kNC;
     if (c > 0) {   // the previous chunk's MMAs have read W_hi / W_lo: wait for them before overwriting
@@ -104,21 +145,7 @@ __global__ void __launch_bounds__(256, 1) linear_tf32x3_kernel(const float* __re
       asm volatile("{\n\t.reg .pred p;\n\tLW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LD;\n\tbra LW;\n\tLD:\n\t}"
                    ::"r"(bar), "r"(parity) : "memory");
     }
-    // ---- W[:, n0 : n0 + 64] -> W_hi / W_lo transposed to [n, k]: a thread owns (n, K chunk): 4 coalesced loads, one 16-byte store ----
-    for (int item = tid; item < kNC * KC; item += 256) {
-      const int n = item & (kNC - 1), kc = item / kNC;
-      float v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = kc * 4 + i;
-        v[i] = (k < K && n0 + n < N) ? __ldg(W + (int64_t)k * N + n0 + n) : 0.f;
-      }
-      float4 h, l;
-      split_tf32(v[0], h.x, l.x); split_tf32(v[1], h.y, l.y); split_tf32(v[2], h.z, l.z); split_tf32(v[3], h.w, l.w);
-      const uint32_t off = (uint32_t)kc * (kNC * 16) + (uint32_t)n * 16;
-      *reinterpret_cast<float4*>(b_hi + off) = h;
-      *reinterpret_cast<float4*>(b_lo + off) = l;
-    }
+    store_w();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     __syncthreads();
     if (tid == 0) {
@@ -137,6 +164,7 @@ __global__ void __launch_bounds__(256, 1) linear_tf32x3_kernel(const float* __re
       // arrives on the mbarrier when every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
+    if (c + 1 < n_chunks) load_w(n0 + kNC);   // in flight while the tensor core works on chunk c
   }
   {
     const uint32_t parity = (uint32_t)(n_chunks - 1) & 1u;
