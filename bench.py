@@ -161,13 +161,14 @@ class ClockSampler:
 def ncu_traffic(workload, graph):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture of
     this workload (profiles/ncu_<round>_spmm_ring_<graph>_raw.csv).  The capture is only trusted when its stamp
-    (<csv>.stamp.json, written by tools/capture_round.sh next to the CSV) carries the digest of the kernel sources this
-    library was built from (gammagl_b200.build._digest()); otherwise traffic is None and the reason is returned."""
+    (<csv>.stamp.json, written by tools/capture_round.sh next to the CSV) carries the digest of the sources the captured kernel
+    is compiled from (gammagl_b200.build.kernel_digest(): spmm_impl.cuh, common.cuh, spmm_f32.cu, the header's tuning constants,
+    the compiler flags); otherwise traffic is None and the reason is returned."""
     if workload != 'c3':
         return None, 'no capture for this workload'
     import glob
     from gammagl_b200 import build as _b
-    want = _b._digest()
+    want = _b.kernel_digest()
     cands = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'ncu_r*_spmm_ring_%s_raw.csv' % graph)), reverse=True)
     why = 'no capture under profiles/'
     for path in cands:
@@ -177,7 +178,7 @@ def ncu_traffic(workload, graph):
         except Exception:
             why = 'capture %s has no stamp' % os.path.basename(path)
             continue
-        if st.get('source_digest') != want:
+        if st.get('kernel_digest') != want:
             why = 'stale: %s was captured from other kernel sources' % os.path.basename(path)
             continue
         try:
@@ -938,7 +939,10 @@ def run_b200(args):
     if world == 1 and not args.no_configs and args.workload == 'c3' and args.dtype == 'f32':
         configs = run_configs(torch, dev, args, peak)
         if 'c3_uniform' in configs:
+            ut, usrc = ncu_traffic('c3', 'uniform') if args.scale == 1.0 else (None, None)
             roofline['uniform_graph'] = {'kernel_ms': configs['c3_uniform']['kernel_ms'], 'frac': configs['c3_uniform']['kernel_frac'],
+                                         'traffic': ut, 'traffic_source': usrc,
+                                         'dram_frac': (ut / (configs['c3_uniform']['kernel_ms'] * 1e-3) / 1e9 / peak) if ut else None,
                                          'note': 'same kernel and algorithmic bytes on a uniform random graph (no hub rows for the L2 '
                                                  'to serve): the HBM-bound reading of the roofline; the RMAT frac above exceeds 1 '
                                                  'because the gather model charges L2 hits on hub rows to HBM'}

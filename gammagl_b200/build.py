@@ -40,6 +40,21 @@ def _digest():
     return h.hexdigest()
 
 
+def kernel_digest(files=('spmm_impl.cuh', 'common.cuh', 'spmm_f32.cu')):
+    """Digest of the sources ONE kernel family is compiled from (default: spmm_ring_kernel<float, ...>) plus the tuning constants of
+    the public header and the compiler flags.  An ncu capture stamped with it (tools/capture_round.sh) stays valid while exactly
+    these sources are unchanged; bench.py refuses a capture whose stamp differs (roofline.traffic)."""
+    h = hashlib.sha256()
+    for f in files:
+        h.update(f.encode())
+        h.update(open(os.path.join(CSRC, f), 'rb').read())
+    for line in open(os.path.join(ROOT, 'include', 'gglb200.h')):
+        if line.startswith('#define GGLB200_') and 'ABI_VERSION' not in line:
+            h.update(line.encode())
+    h.update(' '.join(ARCH + CFLAGS).encode())
+    return h.hexdigest()
+
+
 def up_to_date():
     return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == _digest()
 

@@ -18,7 +18,7 @@ for g in rmat uniform; do
   ncu -i $O/prof_ring_$g.ncu-rep --page raw --csv > $O/ncu_${R}_spmm_ring_${g}_raw.csv 2>/dev/null
   ncu -i $O/prof_ring_$g.ncu-rep --page details --csv > $O/ncu_${R}_spmm_ring_${g}_details.csv 2>/dev/null
   # stamp: bench.py only trusts a capture taken from the kernel sources it was built from (roofline.traffic)
-  python -c "import json,hashlib;from gammagl_b200 import build as b;print(json.dumps({'source_digest':b._digest(),'lib_sha256':hashlib.sha256(open(b.LIB,'rb').read()).hexdigest(),'round':'$R','graph':'$g'}))" > $O/ncu_${R}_spmm_ring_${g}_raw.csv.stamp.json
+  python -c "import json,hashlib;from gammagl_b200 import build as b;print(json.dumps({'kernel_digest':b.kernel_digest(),'source_digest':b._digest(),'lib_sha256':hashlib.sha256(open(b.LIB,'rb').read()).hexdigest(),'round':'$R','graph':'$g'}))" > $O/ncu_${R}_spmm_ring_${g}_raw.csv.stamp.json
   rm -f $O/prof_ring_$g.ncu-rep
 done
 # tcgen05 GEMM and the one-pass GAT backward: one full capture each (tensor-pipe / L2 reduction evidence)
