@@ -217,6 +217,8 @@ class _SegmentReduce(torch.autograd.Function):
                     _lib.check(lib.gglb200_scale_rows_by_count(_ptr(g), _ptr(rowptr), _ptr(gs), ctx.N, K, _stream(dev)),
                                'scale_rows_by_count')
                     g, reduce = gs, _lib.GGL_SUM
+                if c is not None:
+                    c.use_on_current_stream()
                 if c is not None and (_SEG_BWD == 'expand' or (_SEG_BWD == 'auto' and g.numel() * g.element_size() > _SEG_BWD_L2_BYTES)):
                     _lib.check(lib.gglb200_segment_expand_bwd(reduce, _ptr(g), _ptr(c.rowptr), _ptr(c.perm), _ptr(c.plan),
                                                               _ptr(gx), E, ctx.N, K, _dtype_code(g), _stream(dev)),
@@ -436,6 +438,7 @@ class _BSpMM(torch.autograd.Function):
                 if x.dtype != torch.float32 or grad.dtype != torch.float32:
                     raise _lib.GglError('bspmm weight gradient is float32 only')
                 gw = torch.empty((g.E, H), dtype=torch.float32, device=dev)
+                g.fwd.use_on_current_stream()
                 _lib.check(lib.gglb200_bspmm_bwd_w(_ptr(g.fwd.rowptr), _ptr(g.fwd.col), _ptr(g.fwd.perm), _ptr(g.fwd.plan),
                                                    _ptr(x), _ptr(grad), _ptr(gw), N, g.E, H, C, _stream(dev)), 'bspmm_bwd_w')
         return None, gw, gx
@@ -731,6 +734,7 @@ class _EdgeSoftmax(torch.autograd.Function):
             csr = None
         else:
             csr = segment_csr_of(segment_ids, int(num_segments))
+            csr.use_on_current_stream()
         dev = data.device
         with torch.cuda.device(dev):
             _lib.tune_device(dev.index)
@@ -803,6 +807,7 @@ class _GatAggregate(torch.autograd.Function):
             out = torch.empty((N, K), dtype=torch.float32, device=dev)
             m = torch.empty((N, H), dtype=torch.float32, device=dev)
             s = torch.empty((N, H), dtype=torch.float32, device=dev)
+            g.fwd.use_on_current_stream()
             ws, nb = _GatAggregate._ws(g.fwd, H, C, dev)
             _lib.check(lib.gglb200_gat_fwd(_ptr(g.fwd.rowptr), _ptr(g.fwd.col), _ptr(g.fwd.plan), _ptr(xcat), K + Hp, _ptr(sd),
                                            float(slope), _ptr(out), _ptr(m), _ptr(s), N, g.E, H, C, _ptr(ws), nb, _stream(dev)),
@@ -830,6 +835,8 @@ class _GatAggregate(torch.autograd.Function):
             gx = torch.empty((N, K), dtype=torch.float32, device=dev)
             gs_src = torch.empty((N, H), dtype=torch.float32, device=dev)
             gs_dst = torch.empty((N, H), dtype=torch.float32, device=dev)
+            g.bwd.use_on_current_stream()
+            g.fwd.use_on_current_stream()
             ws, nb = _GatAggregate._ws(g.bwd, H, C, dev)
             if merged:
                 # ONE pass: every edge adds its d loss / d pre to grad s_dst[i] with an L2 reduction; the destination id rides in the row
