@@ -690,18 +690,23 @@ def bspmm(index, weight=None, x=None, reduce='sum'):
 # ------------------------------------------------------------------------------------------------
 # fused edge softmax (gammagl/utils/softmax.py:10-36)
 # ------------------------------------------------------------------------------------------------
-# segment_softmax: 'oneshot' = sort-free streaming passes with L2 reductions (no CSR; sums in arrival order), 'csr' = statistics over
-# the segment CSR (serial-order sums).  GGLB200_SOFTMAX_PATH = auto (default: oneshot, csr under torch.use_deterministic_algorithms)
-# | oneshot | csr.
+# segment_softmax has two forms of its segment statistics:
+#   csr      one pass over the segment CSR (rows gathered through perm): serial-order sums, long rows combined chunk-wise -- the
+#            denominators of 10^6-edge hub segments stay within 1e-6 of exact; deterministic
+#   oneshot  sort-free streaming passes with L2 reductions (csrc/oneshot.cu): no CSR, 1.3x / 1.7x faster (C4: 7.8 -> 6.0 ms forward,
+#            11.0 -> 6.3 ms backward), sums in arrival order -- the accuracy of the reference's own serial fp32 loop (|sum alpha - 1|
+#            up to ~5e-5 on a 2 * 10^6-edge hub), not better
+# GGLB200_SOFTMAX_PATH = auto (default: forward csr -- alpha is a model output --, backward's Jacobian row term oneshot; everything
+# csr under torch.use_deterministic_algorithms) | oneshot | csr.
 _SOFTMAX_PATH = os.environ.get('GGLB200_SOFTMAX_PATH', 'auto')
 
 
-def _softmax_oneshot():
+def _softmax_oneshot(backward):
     if _SOFTMAX_PATH == 'csr':
         return False
     if _SOFTMAX_PATH == 'oneshot':
         return True
-    return not torch.are_deterministic_algorithms_enabled()
+    return backward and not torch.are_deterministic_algorithms_enabled()
 
 
 class _EdgeSoftmax(torch.autograd.Function):
@@ -729,7 +734,7 @@ class _EdgeSoftmax(torch.autograd.Function):
             return alpha
         ctx.empty = False
         ids = segment_ids if segment_ids.dtype == torch.int64 and segment_ids.is_contiguous() else segment_ids.to(torch.int64).contiguous()
-        if _softmax_oneshot():
+        if _softmax_oneshot(False):
             validate_ids(segment_ids, num_segments)
             csr = None
         else:
@@ -755,7 +760,9 @@ class _EdgeSoftmax(torch.autograd.Function):
         galpha = galpha.contiguous()
         gl = torch.empty_like(alpha)
         dev = alpha.device
-        csr = ctx.csr
+        csr = None if _softmax_oneshot(True) else ctx.csr
+        if csr is None and not _softmax_oneshot(True):      # forward ran sort-free, backward asked for the CSR form
+            csr = segment_csr_of(ctx.ids, ctx.n_rows)
         E = alpha.shape[0]
         with torch.cuda.device(dev):
             ws, nb = _EdgeSoftmax._workspace(csr, ctx.n_rows, ctx.H, dev)
