@@ -329,7 +329,10 @@ class PeerGraph:
         return out
 
     def degree_norms(self, power=-0.5):
-        """(deg_out^power, deg_in^power) of the owned nodes (0 for isolated ones), from the two local CSRs."""
+        """(deg_out^power, deg_in^power) of the owned nodes (0 for isolated ones), from the two local CSRs (computed once per power)."""
+        hit = self._norms.get(power) if hasattr(self, '_norms') else None
+        if hit is not None:
+            return hit
         from . import _lib
         from .csr import _ptr, _stream
         lib = _lib.load()
@@ -338,6 +341,9 @@ class PeerGraph:
             nd = torch.empty(self.n_local, dtype=torch.float32, device=self.device)
             _lib.check(lib.gglb200_degree_power(_ptr(self.bwd.rowptr), _ptr(ns), self.n_local, power, _stream(self.device)), 'degree_power')
             _lib.check(lib.gglb200_degree_power(_ptr(self.fwd.rowptr), _ptr(nd), self.n_local, power, _stream(self.device)), 'degree_power')
+        if not hasattr(self, '_norms'):
+            self._norms = {}
+        self._norms[power] = (ns, nd)
         return ns, nd
 
 
