@@ -13,7 +13,7 @@
 // truncation of the lo parts are O(2^-21) relative: parity with the fp32 reference at 1e-5 is tested, plain TF32 (2^-11) would
 // not pass it.
 //
-// Layout / instructions (cta_group::1, one CTA per 128 output rows, 256 threads):
+// Layout / instructions (cta_group::1, one CTA per 128 output rows, 256 threads, two CTAs resident per SM):
 //   * operands in the canonical NO-SWIZZLE K-major layout of tcgen05 shared-memory descriptors: 8-row x 16-byte core matrices;
 //     element (r, k) of a [R, K] operand sits at  (k / 4) * R * 16  +  r * 16  +  (k % 4) * 4   (K-chunk stride LBO = 16 R,
 //     8-row-group stride SBO = 128).  Threads write A_hi/A_lo (lane <-> row: conflict-free 16-byte stores) and, per 64-column
@@ -48,10 +48,14 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   lo = v - hi;                                              // exact in fp32
 }
 
-template <int KC /* K chunks of 4 elements, even */>
-__global__ void __launch_bounds__(256, 1) linear_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ W,
+// KC = 16-byte K chunks per K PASS (even: one MMA K step = 2 chunks).  K is covered by k_passes passes of KC chunks each, every pass
+// re-staging its slice of A and W and accumulating into the same TMEM columns: the shared-memory tile of a CTA stays below half an
+// SM (KC = 14: 80 KB), so TWO CTAs are resident per SM and the loads / staging of one overlap the MMAs and the epilogue of the other.
+template <int KC>
+__global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ W,
                                                                const float* __restrict__ bias, const int relu, float* __restrict__ out,
-                                                               const int64_t M, const int32_t K, const int32_t N, const int32_t tmem_cols) {
+                                                               const int64_t M, const int32_t K, const int32_t N, const int32_t tmem_cols,
+                                                               const int32_t k_passes) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mma_bar;
   __shared__ uint32_t tmem_base_slot;
@@ -74,50 +78,46 @@ __global__ void __launch_bounds__(256, 1) linear_tf32x3_kernel(const float* __re
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // ---- A tile -> A_hi / A_lo (canonical layout).  lane <-> row inside a 32-row band, a warp owns KC / 2 (band, K chunk) items:
-  //      all of its 16-byte loads are issued before the first is consumed (the tile load is one DRAM latency, not KC / 2)
-  {
-    constexpr int AI = KC / 2;
-    float4 va[AI];
+
+  // ---- A slice of a K pass: lane <-> row inside a 32-row band, a warp owns AI (band, K chunk) items; all 16-byte loads of a slice are
+  //      issued before the first is consumed and one pass AHEAD of their use (the slice load is one DRAM latency, hidden behind MMAs)
+  constexpr int AI = (4 * KC + 7) / 8;
+  float4 va[AI];
+  auto load_a = [&](int kp) {
 #pragma unroll
     for (int i = 0; i < AI; ++i) {
       const int item = warp + 8 * i, band = item & 3, kc = item >> 2;
       const int r = band * 32 + lane;
+      const int k = (kp * KC + kc) * 4;
       va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < M && kc * 4 < K) va[i] = __ldg(reinterpret_cast<const float4*>(A + (row0 + r) * K + kc * 4));
+      if (item < 4 * KC && row0 + r < M && k < K) va[i] = __ldg(reinterpret_cast<const float4*>(A + (row0 + r) * K + k));
     }
+  };
+  auto store_a = [&]() {
 #pragma unroll
     for (int i = 0; i < AI; ++i) {
       const int item = warp + 8 * i, band = item & 3, kc = item >> 2;
       const int r = band * 32 + lane;
-      float4 h, l;
-      split_tf32(va[i].x, h.x, l.x); split_tf32(va[i].y, h.y, l.y); split_tf32(va[i].z, h.z, l.z); split_tf32(va[i].w, h.w, l.w);
-      const uint32_t off = (uint32_t)kc * (kBM * 16) + (uint32_t)r * 16;
-      *reinterpret_cast<float4*>(a_hi + off) = h;
-      *reinterpret_cast<float4*>(a_lo + off) = l;
+      if (item < 4 * KC) {
+        float4 h, l;
+        split_tf32(va[i].x, h.x, l.x); split_tf32(va[i].y, h.y, l.y); split_tf32(va[i].z, h.z, l.z); split_tf32(va[i].w, h.w, l.w);
+        const uint32_t off = (uint32_t)kc * (kBM * 16) + (uint32_t)r * 16;
+        *reinterpret_cast<float4*>(a_hi + off) = h;
+        *reinterpret_cast<float4*>(a_lo + off) = l;
+      }
     }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_base_slot;
-
-  // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-  const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(a_hi), a_lo_s = (uint32_t)__cvta_generic_to_shared(a_lo);
-  const uint32_t b_hi_s = (uint32_t)__cvta_generic_to_shared(b_hi), b_lo_s = (uint32_t)__cvta_generic_to_shared(b_lo);
-
-  // W[:, n0 : n0 + 64] of a chunk, transposed to [n, k]: a thread owns WI (n, K chunk) items = 4 coalesced loads each.  The values
-  // of chunk c + 1 are fetched into registers while the MMAs of chunk c run (W is L2-resident; only the smem tile is single).
+  };
+  // W[k slice, n0 : n0 + 64] of a chunk, transposed to [n, k]: a thread owns WI (n, K chunk) items = 4 coalesced loads each; the values
+  // of the NEXT chunk are fetched into registers while the MMAs of the current one run (W is L2-resident; the smem tile is single)
   constexpr int WI = (kNC * KC + 255) / 256;
   float wv[WI][4];
-  auto load_w = [&](int n0) {
+  auto load_w = [&](int kp, int n0) {
 #pragma unroll
     for (int i = 0; i < WI; ++i) {
       const int item = tid + 256 * i, n = item & (kNC - 1), kc = item / kNC;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int k = kc * 4 + j;
+        const int k = (kp * KC + kc) * 4 + j;
         wv[i][j] = (item < kNC * KC && k < K && n0 + n < N) ? __ldg(W + (int64_t)k * N + n0 + n) : 0.f;
       }
     }
@@ -135,42 +135,56 @@ __global__ void __launch_bounds__(256, 1) linear_tf32x3_kernel(const float* __re
       }
     }
   };
+  auto wait_commit = [&](int ci) {   // the ci-th tcgen05.commit (0-based) has arrived: every MMA issued before it has completed
+    const uint32_t parity = (uint32_t)ci & 1u;
+    asm volatile("{\n\t.reg .pred p;\n\tLW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LD;\n\tbra LW;\n\tLD:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+  };
+
+  load_a(0);
+  load_w(0, 0);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(a_hi), a_lo_s = (uint32_t)__cvta_generic_to_shared(a_lo);
+  const uint32_t b_hi_s = (uint32_t)__cvta_generic_to_shared(b_hi), b_lo_s = (uint32_t)__cvta_generic_to_shared(b_lo);
 
   const int n_chunks = (N + kNC - 1) / kNC;
-  load_w(0);
-  for (int c = 0; c < n_chunks; ++c) {
-    const int n0 = c * kNC;
-    if (c > 0) {   // the previous chunk's MMAs have read W_hi / W_lo: wait for them before overwriting
-      const uint32_t parity = (uint32_t)(c - 1) & 1u;
-      asm volatile("{\n\t.reg .pred p;\n\tLW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LD;\n\tbra LW;\n\tLD:\n\t}"
-                   ::"r"(bar), "r"(parity) : "memory");
-    }
-    store_w();
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d = tmem_base + (uint32_t)n0;
+  int ci = 0;   // commits issued so far
+  for (int kp = 0; kp < k_passes; ++kp) {
+    for (int c = 0; c < n_chunks; ++c, ++ci) {
+      const int n0 = c * kNC;
+      if (ci > 0) wait_commit(ci - 1);   // the MMAs that read the W tile (and, at a pass boundary, the A slice) have retired
+      if (c == 0) store_a();
+      store_w();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem_base + (uint32_t)n0;
 #pragma unroll 1
-      for (int ks = 0; ks < KC / 2; ++ks) {   // one MMA K step = 8 elements = 2 chunks
-        const uint64_t ah = umma_desc(a_hi_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
-        const uint64_t al = umma_desc(a_lo_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
-        const uint64_t bh = umma_desc(b_hi_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
-        const uint64_t bl = umma_desc(b_lo_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
-        umma_tf32(d, al, bh, IDESC, ks > 0 ? 1u : 0u);   // small terms first
-        umma_tf32(d, ah, bl, IDESC, 1u);
-        umma_tf32(d, ah, bh, IDESC, 1u);
+        for (int ks = 0; ks < KC / 2; ++ks) {   // one MMA K step = 8 elements = 2 chunks
+          const uint64_t ah = umma_desc(a_hi_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
+          const uint64_t al = umma_desc(a_lo_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
+          const uint64_t bh = umma_desc(b_hi_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
+          const uint64_t bl = umma_desc(b_lo_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
+          umma_tf32(d, al, bh, IDESC, (kp > 0 || ks > 0) ? 1u : 0u);   // small terms first
+          umma_tf32(d, ah, bl, IDESC, 1u);
+          umma_tf32(d, ah, bh, IDESC, 1u);
+        }
+        // arrives on the mbarrier when every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
       }
-      // arrives on the mbarrier when every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+      // prefetch for the next (pass, chunk) while the tensor core works
+      if (c + 1 < n_chunks) load_w(kp, n0 + kNC);
+      else if (kp + 1 < k_passes) { load_a(kp + 1); load_w(kp + 1, 0); }
     }
-    if (c + 1 < n_chunks) load_w(n0 + kNC);   // in flight while the tensor core works on chunk c
   }
-  {
-    const uint32_t parity = (uint32_t)(n_chunks - 1) & 1u;
-    asm volatile("{\n\t.reg .pred p;\n\tLW2:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LD2;\n\tbra LW2;\n\tLD2:\n\t}"
-                 ::"r"(bar), "r"(parity) : "memory");
-  }
+  wait_commit(ci - 1);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- epilogue: TMEM -> registers -> bias / ReLU -> global ----
@@ -219,25 +233,31 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
   GGL_REQUIRE(M >= 0 && K > 0 && N > 0, GGL_EINVAL, "linear: bad sizes M=%lld K=%lld N=%lld", (long long)M, (long long)K, (long long)N);
   if (M == 0) return GGL_OK;
   GGL_REQUIRE(A && W && out, GGL_EINVAL, "linear: NULL pointer");
-  GGL_REQUIRE(K % 4 == 0 && K <= 128, GGL_EUNSUPPORTED, "linear: K = %lld (supported: multiples of 4 up to 128)", (long long)K);
+  GGL_REQUIRE(K % 4 == 0 && K <= 256, GGL_EUNSUPPORTED, "linear: K = %lld (supported: multiples of 4 up to 256)", (long long)K);
   GGL_REQUIRE(N % 4 == 0 && N <= 256, GGL_EUNSUPPORTED, "linear: N = %lld (supported: multiples of 4 up to 256)", (long long)N);
   GGL_REQUIRE((((uintptr_t)A | (uintptr_t)out | (uintptr_t)bias) & 15) == 0, GGL_EUNSUPPORTED, "linear: 16-byte aligned A / out / bias");
   GGL_REQUIRE((M + kBM - 1) / kBM < INT32_MAX, GGL_ERANGE, "linear: M too large");
   const int n_chunks = (int)((N + kNC - 1) / kNC);
   int tmem_cols = 32;
   while (tmem_cols < n_chunks * kNC) tmem_cols <<= 1;
-  const int kc = (int)((K + 7) / 8) * 2;   // K chunks of 4, rounded up to whole MMA K steps (zero padded)
+  // K passes: the smallest number of passes whose slice (KC 16-byte chunks, even, <= 16) covers K; KC = 16 keeps two CTAs per SM
+  const int chunks = (int)((K + 3) / 4);
+  int k_passes = (chunks + 15) / 16;
+  int kc = (chunks + k_passes - 1) / k_passes;
+  kc = (kc + 1) & ~1;
   const unsigned grid = (unsigned)((M + kBM - 1) / kBM);
 #define GGL_LIN(KC_)                                                                                                        \
   do {                                                                                                                      \
     const size_t smem = (size_t)2 * KC_ * kBM * 16 + (size_t)2 * KC_ * kNC * 16;                                            \
     GGL_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    linear_tf32x3_kernel<KC_><<<grid, 256, smem, stream>>>(A, W, bias, relu, out, M, (int32_t)K, (int32_t)N, tmem_cols);    \
+    linear_tf32x3_kernel<KC_><<<grid, 256, smem, stream>>>(A, W, bias, relu, out, M, (int32_t)K, (int32_t)N, tmem_cols,     \
+                                                           k_passes);                                                       \
   } while (0)
-  if (kc <= 8) GGL_LIN(8);
-  else if (kc <= 16) GGL_LIN(16);
-  else if (kc <= 26) GGL_LIN(26);
-  else GGL_LIN(32);
+  if (kc <= 4) GGL_LIN(4);
+  else if (kc <= 8) GGL_LIN(8);
+  else if (kc <= 12) GGL_LIN(12);
+  else if (kc <= 14) GGL_LIN(14);
+  else GGL_LIN(16);
 #undef GGL_LIN
   GGL_LAUNCHED("linear_tf32x3");
   return GGL_OK;

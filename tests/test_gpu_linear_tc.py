@@ -15,7 +15,8 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize('M,K,N', [(1000, 100, 256), (333, 128, 64), (128, 4, 4), (5000, 36, 100), (129, 64, 192), (77, 8, 16),
-                                   (4096, 104, 128), (1, 100, 256)])
+                                   (4096, 104, 128), (1, 100, 256),
+                                   (700, 256, 64), (513, 200, 128), (300, 132, 256)])     # K > 128: three / four K passes
 @pytest.mark.parametrize('bias,relu', [(False, False), (True, True)])
 def test_linear_tc_matches_fp64(M, K, N, bias, relu):
     from gammagl_b200 import mpops
