@@ -5,8 +5,9 @@
 // This is the Linear of GCNConv / SAGEConv / GINConv (/root/reference/gammagl/layers/conv/gcn_conv.py:79, sage_conv.py:80,
 // gin_conv.py:57; tlx.layers.Linear = torch matmul on fp32 SIMT cores in the reference) applied to the aggregated rows when a
 // layer aggregates first (F_in < F_out: `GCNConv(aggregate_first)`), with the bias + ReLU epilogue of gcn_conv.py:104-106 fused.
-// A is the [N_nodes, F_in] output of the aggregation kernel, so F_in is small (100 / 128): the whole K extent of a 128-row tile
-// lives in shared memory at once and the kernel is bound by reading A and writing out, not by math.
+// A is the [N_nodes, F_in] output of the aggregation kernel, so F_in is small (100 / 128, up to 256 here): a 128-row tile is covered
+// in one to four K passes of at most 64 columns whose operands live in shared memory at once; the kernel is bound by reading A and
+// writing out, not by math.
 //
 // fp32 accuracy on TF32 tensor cores (3xTF32): a = a_hi + a_lo with a_hi = a truncated to TF32 (top 19 bits) and a_lo = a - a_hi
 // (exact), likewise w; D = a_hi.w_hi + a_hi.w_lo + a_lo.w_hi in the fp32 TMEM accumulator.  The dropped a_lo.w_lo term and the
