@@ -105,15 +105,31 @@ def check(status, what=''):
 _tuned_devices = set()
 
 
+_previous_l2_fetch = {}
+
+
 def tune_device(device_index):
     """Once per device: 32-byte L2 fetch granularity for the random row gathers (env GGLB200_L2_FETCH=32|64|128,
-    0 leaves the driver default untouched).  Must be called with `device_index` current."""
+    0 leaves the driver default untouched).  Must be called with `device_index` current.
+    This is a device-wide limit, so it also applies to the host application's other kernels; measured on B200 at the C3 shape
+    (tools/bench_layer.py, profiles/bench_layer_r2.json): the fp32 cuBLAS GEMM next to the aggregation runs 2.95 / 2.97 / 2.97 ms at
+    32 / 64 / 128 bytes -- no penalty --, the aggregation 5.38 / 5.46 / 5.49 ms.  restore_device() puts the previous value back."""
     if device_index in _tuned_devices:
         return
     _tuned_devices.add(device_index)
     want = int(os.environ.get('GGLB200_L2_FETCH', '32'))
     if want:
-        check(load().gglb200_set_l2_fetch_granularity(want, None), 'set_l2_fetch_granularity')
+        prev = ctypes.c_int(0)
+        check(load().gglb200_set_l2_fetch_granularity(want, ctypes.byref(prev)), 'set_l2_fetch_granularity')
+        _previous_l2_fetch[device_index] = prev.value
+
+
+def restore_device(device_index):
+    """Undo tune_device() on the current device (the L2 fetch granularity the process found)."""
+    prev = _previous_l2_fetch.pop(device_index, None)
+    _tuned_devices.discard(device_index)
+    if prev in (32, 64, 128):
+        check(load().gglb200_set_l2_fetch_granularity(prev, None), 'set_l2_fetch_granularity')
 
 
 def launch_count():
