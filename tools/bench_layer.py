@@ -42,5 +42,35 @@ got = mpops.linear_tc(mpops.gcn_propagate(ei, x, 'both'), W, b, True)
 lib32 = torch.relu(mpops.gcn_propagate(ei, x, 'both') @ W + b)
 out['rel_err_linear_tc_vs_fp64'] = float((got.double() - ref).abs().max() / ref.abs().max())
 out['rel_err_cublas_fp32_vs_fp64'] = float((lib32.double() - ref).abs().max() / ref.abs().max())
+# ---- a whole model step: 2-layer GCN (100 -> 256 -> 47 classes, ReLU between), forward + backward, layers of gammagl_b200.layers ----
+from gammagl_b200.layers import GCNConv  # noqa: E402
+del ref, got, lib32, xw
+torch.cuda.empty_cache()
+y = torch.randint(0, 47, (N,), generator=g, device=dev)
+
+
+def build_model(aggregate_first):
+    torch.manual_seed(0)
+    l1 = GCNConv(F, H, aggregate_first=aggregate_first, fused_activation='relu').to(dev)
+    l2 = GCNConv(H, 47).to(dev)
+    return l1, l2
+
+
+def model_step(layers):
+    l1, l2 = layers
+    for l in layers:
+        l.zero_grad(set_to_none=True)
+    logits = l2(l1(x, ei), ei)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    return loss
+
+
+ma, mb = build_model(False), build_model(True)
+la, lb = float(model_step(ma)), float(model_step(mb))
+out['gcn2_transform_first_fwd_bwd_ms'] = timeit(lambda: model_step(ma), reps=5, warm=2)
+out['gcn2_aggregate_first_linear_tc_fwd_bwd_ms'] = timeit(lambda: model_step(mb), reps=5, warm=2)
+out['gcn2_loss_transform_first'], out['gcn2_loss_aggregate_first'] = la, lb
+out['gcn2_note'] = 'GCN 100 -> 256 -> 47 on the C3 graph, cross-entropy, forward + backward (no optimizer); layer 1 aggregate-first runs the tcgen05 Linear'
 out['shape'] = {'N': N, 'E': E, 'F_in': F, 'F_out': H}
 print(json.dumps(out))
