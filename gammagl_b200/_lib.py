@@ -41,7 +41,8 @@ SIGNATURES = {
     'gglb200_spmm_max_edge_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     'gglb200_segment_reduce_workspace_bytes': (_sz, [_int, _i64, _i64]),
     'gglb200_segment_reduce': (_int, [_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _int, _vp, _sz, _vp]),
-    'gglb200_linear_tf32x3': (_int, [_vp, _vp, _vp, _int, _vp, _i64, _i64, _i64, _vp]),
+    'gglb200_linear_workspace_bytes': (_sz, [_i64, _i64]),
+    'gglb200_linear_tf32x3': (_int, [_vp, _vp, _vp, _int, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     'gglb200_sample_workspace_bytes': (_sz, [_i64]),
     'gglb200_sample_count': (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
     'gglb200_sample_pick': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _c.c_uint64, _vp, _vp, _vp, _vp]),

@@ -49,26 +49,60 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   lo = v - hi;                                              // exact in fp32
 }
 
-// KC = 16-byte K chunks per K PASS (even: one MMA K step = 2 chunks).  K is covered by k_passes passes of KC chunks each, every pass
-// re-staging its slice of A and W and accumulating into the same TMEM columns: the shared-memory tile of a CTA stays below half an
-// SM (KC = 14: 80 KB), so TWO CTAs are resident per SM and the loads / staging of one overlap the MMAs and the epilogue of the other.
+// W prepared for the tensor core: for every (K pass, 64-column chunk) one contiguous block [W_hi tile | W_lo tile] in the canonical
+// no-swizzle K-major layout (element (n, kc, j) of a tile at kc * 64 * 16 + n * 16 + j * 4), zero padded.  The GEMM kernel then fetches
+// a block with ONE bulk async copy straight into shared memory -- no register staging, no split arithmetic per tile.
 template <int KC>
-__global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ W,
+__global__ void __launch_bounds__(256) linear_prep_w_kernel(const float* __restrict__ W, float* __restrict__ wc, int32_t K, int32_t N,
+                                                            int32_t k_passes, int32_t n_chunks) {
+  const int64_t total = (int64_t)k_passes * n_chunks * KC * kNC;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(t % kNC);
+    const int kc = (int)((t / kNC) % KC);
+    const int64_t blk = t / ((int64_t)kNC * KC);          // kp * n_chunks + c
+    const int c = (int)(blk % n_chunks), kp = (int)(blk / n_chunks);
+    float4 h, l;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = (kp * KC + kc) * 4 + j, col = c * kNC + n;
+      v[j] = (k < K && col < N) ? __ldg(W + (int64_t)k * N + col) : 0.f;
+    }
+    split_tf32(v[0], h.x, l.x); split_tf32(v[1], h.y, l.y); split_tf32(v[2], h.z, l.z); split_tf32(v[3], h.w, l.w);
+    float* base = wc + blk * (2 * KC * kNC * 4);
+    *reinterpret_cast<float4*>(base + (kc * kNC + n) * 4) = h;
+    *reinterpret_cast<float4*>(base + KC * kNC * 4 + (kc * kNC + n) * 4) = l;
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tLW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LD;\n\tbra LW;\n\tLD:\n\t}"
+               ::"r"(bar), "r"(parity) : "memory");
+}
+
+// KC = 16-byte K chunks per K PASS (even, <= 14: one MMA K step = 2 chunks).  K is covered by k_passes passes, each re-staging its slice
+// of A and accumulating into the same TMEM columns; with KC <= 14 a CTA needs 112 KB of shared memory (A_hi | A_lo | two W blocks), so
+// TWO CTAs are resident per SM.  Roles: all threads stage the A slice (fp32 -> hi / lo, one pass ahead in registers); thread 32 is the
+// W producer (one bulk async copy per (pass, chunk) into a 2-deep ring, mbarrier `full`); thread 0 issues the MMAs and commits them
+// to mbarrier `done` (ring slot free / accumulator ready); 8 warps run the epilogue.
+template <int KC>
+__global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ wc,
                                                                const float* __restrict__ bias, const int relu, float* __restrict__ out,
                                                                const int64_t M, const int32_t K, const int32_t N, const int32_t tmem_cols,
                                                                const int32_t k_passes) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long mma_bar;
+  __shared__ __align__(8) unsigned long long bars[4];   // full[0..1], done[0..1]
   __shared__ uint32_t tmem_base_slot;
   constexpr uint32_t A_BYTES = KC * kBM * 16;   // one of A_hi / A_lo
-  constexpr uint32_t B_BYTES = KC * kNC * 16;   // one of W_hi / W_lo for a 64-column chunk
+  constexpr uint32_t B_BYTES = KC * kNC * 16;   // one of W_hi / W_lo of a block
   unsigned char* a_hi = smem;
   unsigned char* a_lo = smem + A_BYTES;
-  unsigned char* b_hi = smem + 2 * A_BYTES;
-  unsigned char* b_lo = smem + 2 * A_BYTES + B_BYTES;
+  unsigned char* b_ring = smem + 2 * A_BYTES;   // slot s at b_ring + s * 2 * B_BYTES: [W_hi | W_lo]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * kBM;
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mma_bar);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+  const int n_chunks = (N + kNC - 1) / kNC;
+  const int total = k_passes * n_chunks;
 
   if (warp == 0) {   // TMEM allocation by one full warp; the address lands in shared memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_base_slot)),
@@ -76,12 +110,11 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
 
-  // ---- A slice of a K pass: lane <-> row inside a 32-row band, a warp owns AI (band, K chunk) items; all 16-byte loads of a slice are
-  //      issued before the first is consumed and one pass AHEAD of their use (the slice load is one DRAM latency, hidden behind MMAs)
   constexpr int AI = (4 * KC + 7) / 8;
   float4 va[AI];
   auto load_a = [&](int kp) {
@@ -108,84 +141,72 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
       }
     }
   };
-  // W[k slice, n0 : n0 + 64] of a chunk, transposed to [n, k]: a thread owns WI (n, K chunk) items = 4 coalesced loads each; the values
-  // of the NEXT chunk are fetched into registers while the MMAs of the current one run (W is L2-resident; the smem tile is single)
-  constexpr int WI = (kNC * KC + 255) / 256;
-  float wv[WI][4];
-  auto load_w = [&](int kp, int n0) {
-#pragma unroll
-    for (int i = 0; i < WI; ++i) {
-      const int item = tid + 256 * i, n = item & (kNC - 1), kc = item / kNC;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = (kp * KC + kc) * 4 + j;
-        wv[i][j] = (item < kNC * KC && k < K && n0 + n < N) ? __ldg(W + (int64_t)k * N + n0 + n) : 0.f;
-      }
-    }
-  };
-  auto store_w = [&]() {
-#pragma unroll
-    for (int i = 0; i < WI; ++i) {
-      const int item = tid + 256 * i, n = item & (kNC - 1), kc = item / kNC;
-      if (item < kNC * KC) {
-        float4 h, l;
-        split_tf32(wv[i][0], h.x, l.x); split_tf32(wv[i][1], h.y, l.y); split_tf32(wv[i][2], h.z, l.z); split_tf32(wv[i][3], h.w, l.w);
-        const uint32_t off = (uint32_t)kc * (kNC * 16) + (uint32_t)n * 16;
-        *reinterpret_cast<float4*>(b_hi + off) = h;
-        *reinterpret_cast<float4*>(b_lo + off) = l;
-      }
-    }
-  };
-  auto wait_commit = [&](int ci) {   // the ci-th tcgen05.commit (0-based) has arrived: every MMA issued before it has completed
-    const uint32_t parity = (uint32_t)ci & 1u;
-    asm volatile("{\n\t.reg .pred p;\n\tLW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LD;\n\tbra LW;\n\tLD:\n\t}"
-                 ::"r"(bar), "r"(parity) : "memory");
+  // producer: block i -> ring slot i & 1 (after the MMAs of block i - 2 have released it)
+  auto issue_copy = [&](int i) {
+    const uint32_t slot = (uint32_t)i & 1u, full = bar0 + 8 * slot, done = bar0 + 16 + 8 * slot;
+    if (i >= 2) mbar_wait_parity(done, (uint32_t)((i - 2) >> 1) & 1u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(2u * B_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(b_ring + slot * 2 * B_BYTES)), "l"(wc + (int64_t)i * (2 * B_BYTES / 4)),
+                   "r"(2u * B_BYTES), "r"(full) : "memory");
   };
 
   load_a(0);
-  load_w(0, 0);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  __syncthreads();   // barriers initialised, TMEM address published
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
+  if (tid == 32) {
+    issue_copy(0);
+    if (total > 1) issue_copy(1);
+  }
 
   // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
   const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(a_hi), a_lo_s = (uint32_t)__cvta_generic_to_shared(a_lo);
-  const uint32_t b_hi_s = (uint32_t)__cvta_generic_to_shared(b_hi), b_lo_s = (uint32_t)__cvta_generic_to_shared(b_lo);
+  const uint32_t b_ring_s = (uint32_t)__cvta_generic_to_shared(b_ring);
 
-  const int n_chunks = (N + kNC - 1) / kNC;
-  int ci = 0;   // commits issued so far
   for (int kp = 0; kp < k_passes; ++kp) {
-    for (int c = 0; c < n_chunks; ++c, ++ci) {
-      const int n0 = c * kNC;
-      if (ci > 0) wait_commit(ci - 1);   // the MMAs that read the W tile (and, at a pass boundary, the A slice) have retired
-      if (c == 0) store_a();
-      store_w();
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      __syncthreads();
-      if (tid == 0) {
+    if (kp > 0) {   // the MMAs of the previous pass have read the A slice: wait for its last commit before overwriting
+      const int il = kp * n_chunks - 1;
+      mbar_wait_parity(bar0 + 16 + 8 * ((uint32_t)il & 1u), (uint32_t)(il >> 1) & 1u);
+    }
+    store_a();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c = 0; c < n_chunks; ++c) {
+        const int i = kp * n_chunks + c;
+        const uint32_t slot = (uint32_t)i & 1u;
+        mbar_wait_parity(bar0 + 8 * slot, (uint32_t)(i >> 1) & 1u);          // W block i has landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + (uint32_t)n0;
+        const uint32_t d = tmem_base + (uint32_t)(c * kNC);
+        const uint32_t bh_s = b_ring_s + slot * 2 * B_BYTES, bl_s = bh_s + B_BYTES;
 #pragma unroll 1
         for (int ks = 0; ks < KC / 2; ++ks) {   // one MMA K step = 8 elements = 2 chunks
           const uint64_t ah = umma_desc(a_hi_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
           const uint64_t al = umma_desc(a_lo_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
-          const uint64_t bh = umma_desc(b_hi_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
-          const uint64_t bl = umma_desc(b_lo_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
+          const uint64_t bh = umma_desc(bh_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
+          const uint64_t bl = umma_desc(bl_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
           umma_tf32(d, al, bh, IDESC, (kp > 0 || ks > 0) ? 1u : 0u);   // small terms first
           umma_tf32(d, ah, bl, IDESC, 1u);
           umma_tf32(d, ah, bh, IDESC, 1u);
         }
-        // arrives on the mbarrier when every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+        // arrives on `done[slot]` when every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 16 + 8 * slot) : "memory");
       }
-      // prefetch for the next (pass, chunk) while the tensor core works
-      if (c + 1 < n_chunks) load_w(kp, n0 + kNC);
-      else if (kp + 1 < k_passes) { load_a(kp + 1); load_w(kp + 1, 0); }
+    } else if (tid == 32) {
+      for (int c = 0; c < n_chunks; ++c) {
+        const int i = kp * n_chunks + c + 2;
+        if (i < total) issue_copy(i);
+      }
     }
+    if (kp + 1 < k_passes) load_a(kp + 1);   // next slice in flight while the tensor core works on this one
   }
-  wait_commit(ci - 1);
+  // accumulator complete: the last commit on each ring slot has arrived
+  mbar_wait_parity(bar0 + 16 + 8 * ((uint32_t)(total - 1) & 1u), (uint32_t)((total - 1) >> 1) & 1u);
+  if (total > 1) mbar_wait_parity(bar0 + 16 + 8 * ((uint32_t)(total - 2) & 1u), (uint32_t)((total - 2) >> 1) & 1u);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- epilogue: TMEM -> registers -> bias / ReLU -> global ----
@@ -228,8 +249,26 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
 
 using namespace ggl;
 
+static void linear_plan(int64_t K, int* k_passes, int* kc) {
+  // K passes: slices of at most 14 sixteen-byte chunks (56 columns), even, as equal as possible -- 112 KB of shared memory per CTA
+  const int chunks = (int)((K + 3) / 4);
+  *k_passes = (chunks + 13) / 14;
+  int c = (chunks + *k_passes - 1) / *k_passes;
+  *kc = (c + 1) & ~1;
+}
+static int linear_kc_class(int kc) { return kc <= 4 ? 4 : (kc <= 8 ? 8 : (kc <= 12 ? 12 : 14)); }
+
+extern "C" size_t gglb200_linear_workspace_bytes(int64_t K, int64_t N) {
+  if (K <= 0 || N <= 0) return 0;
+  int k_passes, kc;
+  linear_plan(K, &k_passes, &kc);
+  const int KC = linear_kc_class(kc);
+  const int64_t n_chunks = (N + kNC - 1) / kNC;
+  return (size_t)k_passes * n_chunks * 2 * KC * kNC * 16 + 256;
+}
+
 extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float* bias, int relu, float* out, int64_t M, int64_t K,
-                                     int64_t N, void* stream_) {
+                                     int64_t N, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GGL_REQUIRE(M >= 0 && K > 0 && N > 0, GGL_EINVAL, "linear: bad sizes M=%lld K=%lld N=%lld", (long long)M, (long long)K, (long long)N);
   if (M == 0) return GGL_OK;
@@ -238,27 +277,32 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
   GGL_REQUIRE(N % 4 == 0 && N <= 256, GGL_EUNSUPPORTED, "linear: N = %lld (supported: multiples of 4 up to 256)", (long long)N);
   GGL_REQUIRE((((uintptr_t)A | (uintptr_t)out | (uintptr_t)bias) & 15) == 0, GGL_EUNSUPPORTED, "linear: 16-byte aligned A / out / bias");
   GGL_REQUIRE((M + kBM - 1) / kBM < INT32_MAX, GGL_ERANGE, "linear: M too large");
+  GGL_REQUIRE(workspace != nullptr && workspace_bytes >= gglb200_linear_workspace_bytes(K, N), GGL_EWORKSPACE,
+              "linear: workspace %zu < %zu", workspace_bytes, gglb200_linear_workspace_bytes(K, N));
   const int n_chunks = (int)((N + kNC - 1) / kNC);
   int tmem_cols = 32;
   while (tmem_cols < n_chunks * kNC) tmem_cols <<= 1;
-  // K passes: the smallest number of passes whose slice (KC 16-byte chunks, even, <= 16) covers K; KC = 16 keeps two CTAs per SM
-  const int chunks = (int)((K + 3) / 4);
-  int k_passes = (chunks + 15) / 16;
-  int kc = (chunks + k_passes - 1) / k_passes;
-  kc = (kc + 1) & ~1;
+  int k_passes, kc;
+  linear_plan(K, &k_passes, &kc);
+  float* wc = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   const unsigned grid = (unsigned)((M + kBM - 1) / kBM);
 #define GGL_LIN(KC_)                                                                                                        \
   do {                                                                                                                      \
-    const size_t smem = (size_t)2 * KC_ * kBM * 16 + (size_t)2 * KC_ * kNC * 16;                                            \
+    const int64_t items = (int64_t)k_passes * n_chunks * KC_ * kNC;                                                         \
+    linear_prep_w_kernel<KC_><<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(W, wc, (int32_t)K, (int32_t)N, k_passes,  \
+                                                                                   n_chunks);                               \
+    GGL_LAUNCHED("linear_prep_w");                                                                                          \
+    const size_t smem = (size_t)2 * KC_ * kBM * 16 + (size_t)4 * KC_ * kNC * 16;                                            \
     GGL_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    linear_tf32x3_kernel<KC_><<<grid, 256, smem, stream>>>(A, W, bias, relu, out, M, (int32_t)K, (int32_t)N, tmem_cols,     \
+    linear_tf32x3_kernel<KC_><<<grid, 256, smem, stream>>>(A, wc, bias, relu, out, M, (int32_t)K, (int32_t)N, tmem_cols,    \
                                                            k_passes);                                                       \
   } while (0)
-  if (kc <= 4) GGL_LIN(4);
-  else if (kc <= 8) GGL_LIN(8);
-  else if (kc <= 12) GGL_LIN(12);
-  else if (kc <= 14) GGL_LIN(14);
-  else GGL_LIN(16);
+  switch (linear_kc_class(kc)) {
+    case 4: GGL_LIN(4); break;
+    case 8: GGL_LIN(8); break;
+    case 12: GGL_LIN(12); break;
+    default: GGL_LIN(14); break;
+  }
 #undef GGL_LIN
   GGL_LAUNCHED("linear_tf32x3");
   return GGL_OK;

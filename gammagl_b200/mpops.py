@@ -624,8 +624,10 @@ class _LinearTC(torch.autograd.Function):
         bflat = None if bias is None else bias.detach().reshape(-1).to(torch.float32).contiguous()
         with torch.cuda.device(dev):
             out = torch.empty((M, N), dtype=torch.float32, device=dev)
-            _lib.check(lib.gglb200_linear_tf32x3(_ptr(a), _ptr(w), _ptr(bflat), int(bool(relu)), _ptr(out), M, K, N, _stream(dev)),
-                       'linear_tf32x3')
+            nb = lib.gglb200_linear_workspace_bytes(K, N)
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _lib.check(lib.gglb200_linear_tf32x3(_ptr(a), _ptr(w), _ptr(bflat), int(bool(relu)), _ptr(out), M, K, N, _ptr(ws), nb,
+                                                 _stream(dev)), 'linear_tf32x3')
         ctx.relu = bool(relu)
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.save_for_backward(a, w, out if relu else None)

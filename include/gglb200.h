@@ -245,8 +245,9 @@ GGL_API int gglb200_sample_pick(const int64_t* rowptr, const int64_t* col, const
  * operand splitting (3xTF32: a_hi.w_hi + a_hi.w_lo + a_lo.w_hi), ~1e-6 relative.  Other shapes: GGL_EUNSUPPORTED (the
  * host side then uses the library GEMM).
  * ------------------------------------------------------------------------------------------- */
+GGL_API size_t gglb200_linear_workspace_bytes(int64_t K, int64_t N);   /* W split into hi / lo tensor-core tiles, rebuilt per call */
 GGL_API int gglb200_linear_tf32x3(const float* A, const float* W, const float* bias, int relu, float* out, int64_t M, int64_t K,
-                          int64_t N, void* stream);
+                          int64_t N, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Sort-free unsorted segment reduce (the role of mpops/torch_ext/cuda/segment_{sum,mean,max}_cuda.cu -- scalar atomicAdd /
