@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
                                                                const int64_t M, const int32_t K, const int32_t N, const int32_t tmem_cols,
                                                                const int32_t k_passes) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long bars[4];   // full[0..1], done[0..1]
+  __shared__ __align__(8) unsigned long long bars[5];   // full[0..1], done[0..1], pass (all threads wait EVERY phase of it in order:
+                                                        // a parity wait is only meaningful to a thread that has seen the previous phase)
   __shared__ uint32_t tmem_base_slot;
   constexpr uint32_t A_BYTES = KC * kBM * 16;   // one of A_hi / A_lo
   constexpr uint32_t B_BYTES = KC * kNC * 16;   // one of W_hi / W_lo of a block
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
-    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i) : "memory");
+    for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -167,10 +168,8 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
   const uint32_t b_ring_s = (uint32_t)__cvta_generic_to_shared(b_ring);
 
   for (int kp = 0; kp < k_passes; ++kp) {
-    if (kp > 0) {   // the MMAs of the previous pass have read the A slice: wait for its last commit before overwriting
-      const int il = kp * n_chunks - 1;
-      mbar_wait_parity(bar0 + 16 + 8 * ((uint32_t)il & 1u), (uint32_t)(il >> 1) & 1u);
-    }
+    // the MMAs of the previous pass have read the A slice: wait for that pass's commit before overwriting
+    if (kp > 0) mbar_wait_parity(bar0 + 32, (uint32_t)(kp - 1) & 1u);
     store_a();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     __syncthreads();
@@ -196,6 +195,7 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
         // arrives on `done[slot]` when every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 16 + 8 * slot) : "memory");
       }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 32) : "memory");   // pass done
     } else if (tid == 32) {
       for (int c = 0; c < n_chunks; ++c) {
         const int i = kp * n_chunks + c + 2;
@@ -204,9 +204,8 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
     }
     if (kp + 1 < k_passes) load_a(kp + 1);   // next slice in flight while the tensor core works on this one
   }
-  // accumulator complete: the last commit on each ring slot has arrived
-  mbar_wait_parity(bar0 + 16 + 8 * ((uint32_t)(total - 1) & 1u), (uint32_t)((total - 1) >> 1) & 1u);
-  if (total > 1) mbar_wait_parity(bar0 + 16 + 8 * ((uint32_t)(total - 2) & 1u), (uint32_t)((total - 2) >> 1) & 1u);
+  // accumulator complete: the commit of the last pass has arrived
+  mbar_wait_parity(bar0 + 32, (uint32_t)(k_passes - 1) & 1u);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- epilogue: TMEM -> registers -> bias / ReLU -> global ----

@@ -20,6 +20,7 @@
 //          A second pass decodes: out = x[arg] (exact bits), arg = edge id, empty rows = lowest() / arg_empty.
 // ids outside [0, N) are skipped and counted in *n_bad (the host raises); nothing is clamped.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace ggl {
 
@@ -40,13 +41,12 @@ __device__ __forceinline__ uint32_t ordered_bits(float v) {
 
 // A group of LPR lanes owns one edge row of KV = K / VEC vector elements (LPR = next power of two >= min(KV, 32)); a warp
 // moves 32 / LPR edges per step, U steps in flight.
-template <int VEC, int LPR, int MODE /* 0 sum, 1 max */>
+template <int VEC, int LPR, int MODE /* 0 sum, 1 max */, int U = 4>
 __global__ void __launch_bounds__(256) oneshot_kernel(const float* __restrict__ x, const int64_t* __restrict__ ids, float* __restrict__ out,
                                                       unsigned long long* __restrict__ keys, uint32_t* __restrict__ cnt,
                                                       unsigned long long* __restrict__ n_bad, int64_t E, int32_t K, int64_t N,
                                                       int32_t rep_mask /* SUM: replicas - 1 (0 = none) */, int64_t rep_stride) {
   constexpr int GPW = 32 / LPR;
-  constexpr int U = 4;
   const int lane = threadIdx.x & 31, sub = lane & (LPR - 1), grp = lane / LPR;
   const int32_t KV = K / VEC;
   const int64_t span = (int64_t)gridDim.x * (blockDim.x >> 5) * (GPW * U);
@@ -218,6 +218,12 @@ static int ew_grid(int64_t n) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+static int oneshot_unroll() { return env_int("GGLB200_ONESHOT_UNROLL", 4); }
+
 template <int VEC, int MODE>
 static void launch_oneshot(const float* x, const int64_t* ids, float* out, unsigned long long* keys, uint32_t* cnt, unsigned long long* n_bad,
                            int64_t E, int32_t K, int64_t N, cudaStream_t stream, int32_t rep_mask = 0, int64_t rep_stride = 0) {
@@ -229,6 +235,10 @@ static void launch_oneshot(const float* x, const int64_t* ids, float* out, unsig
   const int64_t cap = (int64_t)sm_count() * 16;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
+  if (lpr == 1 && oneshot_unroll() == 8) {   // experiment knob (GGLB200_ONESHOT_UNROLL): 8 edges per lane in flight
+    oneshot_kernel<VEC, 1, MODE, 8><<<(int)grid, 256, 0, stream>>>(x, ids, out, keys, cnt, n_bad, E, K, N, rep_mask, rep_stride);
+    return;
+  }
   switch (lpr) {
     case 1: oneshot_kernel<VEC, 1, MODE><<<(int)grid, 256, 0, stream>>>(x, ids, out, keys, cnt, n_bad, E, K, N, rep_mask, rep_stride); break;
     case 2: oneshot_kernel<VEC, 2, MODE><<<(int)grid, 256, 0, stream>>>(x, ids, out, keys, cnt, n_bad, E, K, N, rep_mask, rep_stride); break;
@@ -247,13 +257,15 @@ constexpr int kReplicas = 8;                       // output replicas of narrow 
 constexpr size_t kReplicaBudget = 48u << 20;
 
 static int sum_replicas(int64_t N, int64_t K) {
-  return (K <= 4 && (size_t)N * (size_t)K * 4 * kReplicas <= kReplicaBudget) ? kReplicas : 1;
+  int r = ggl::env_int("GGLB200_ONESHOT_REPLICAS", kReplicas);   // power of two, at most kReplicas (the workspace is sized for that)
+  if (r < 1 || r > kReplicas || (r & (r - 1))) r = kReplicas;
+  return (K <= 4 && (size_t)N * (size_t)K * 4 * kReplicas <= kReplicaBudget) ? r : 1;
 }
 
 extern "C" size_t gglb200_segment_reduce_workspace_bytes(int reduce, int64_t N, int64_t K) {
   if (N <= 0 || K <= 0) return 0;
   if (reduce == GGL_MAX) return (size_t)N * (size_t)K * 8 + 256;
-  return sum_replicas(N, K) > 1 ? (size_t)N * (size_t)K * 4 * kReplicas + 256 : 0;
+  return (K <= 4 && (size_t)N * (size_t)K * 4 * kReplicas <= kReplicaBudget) ? (size_t)N * (size_t)K * 4 * kReplicas + 256 : 0;
 }
 
 extern "C" int gglb200_segment_reduce(int reduce, const void* x_, const int64_t* ids, void* out_, int64_t* arg, int64_t arg_empty,
