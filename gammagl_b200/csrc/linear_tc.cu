@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
                                                                const int64_t M, const int32_t K, const int32_t N, const int32_t tmem_cols,
                                                                const int32_t k_passes) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long bars[5];   // full[0..1], done[0..1], pass (all threads wait EVERY phase of it in order:
+  __shared__ __align__(16) float bias_s[256];            // bias (or zeros) for the epilogue: broadcast shared-memory reads
+  __shared__ __align__(8) unsigned long long bars[9];   // full[0..1], done[0..1], pass (all threads wait EVERY phase of it in order:
                                                         // a parity wait is only meaningful to a thread that has seen the previous phase)
   __shared__ uint32_t tmem_base_slot;
   constexpr uint32_t A_BYTES = KC * kBM * 16;   // one of A_hi / A_lo
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
-    for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i) : "memory");
+    for (int i = 0; i < 9; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
   };
 
   load_a(0);
+  bias_s[tid] = (bias != nullptr && tid < N) ? __ldg(bias + tid) : 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();   // barriers initialised, TMEM address published
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -194,8 +196,11 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
         }
         // arrives on `done[slot]` when every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 16 + 8 * slot) : "memory");
+        if (kp + 1 == k_passes)   // chunk c of the accumulator is final: its epilogue may start while the next chunks multiply
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 40 + 8 * c) : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 32) : "memory");   // pass done
+      if (kp + 1 < k_passes)   // pass done (the last pass is tracked per chunk; nothing may arrive after the acc[] commits)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 32) : "memory");
     } else if (tid == 32) {
       for (int c = 0; c < n_chunks; ++c) {
         const int i = kp * n_chunks + c + 2;
@@ -204,35 +209,48 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
     }
     if (kp + 1 < k_passes) load_a(kp + 1);   // next slice in flight while the tensor core works on this one
   }
-  // accumulator complete: the commit of the last pass has arrived
-  mbar_wait_parity(bar0 + 32, (uint32_t)(k_passes - 1) & 1u);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-  // ---- epilogue: TMEM -> registers -> bias / ReLU -> global ----
+  // ---- epilogue: TMEM -> registers -> bias / ReLU -> global.  Warp w reads TMEM lanes 32 (w % 4) .. (its rows) and the column half
+  // w / 4, 32 columns per tcgen05.ld; a lane holds 128 contiguous bytes of its output row and stores them as four 32-byte vectors
+  // (full sectors; 16-byte vectors when rows are not 32-byte aligned).  Chunk c is read as soon as ITS last MMAs have retired.
   {
     const int q = warp & 3, half = warp >> 2;
     const int64_t r = row0 + q * 32 + lane;
     const int n_cols = n_chunks * kNC;
     const int c_lo = half * (n_cols / 2), c_hi = c_lo + n_cols / 2;
-    for (int col = c_lo; col < c_hi; col += 16) {
-      uint32_t v[16];
+    const bool wide = ((N & 7) == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0);
+    for (int col = c_lo; col < c_hi; col += 32) {
+      mbar_wait_parity(bar0 + 40 + 8 * (uint32_t)(col / kNC), 0u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                     "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                   : "r"(taddr) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+          "%25,%26,%27,%28,%29,%30,%31}, [%32];\n\ttcgen05.wait::ld.sync.aligned;"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+            "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+            "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr) : "memory");
       if (r < M && col < N) {
+        float* orow = out + r * N + col;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
+        for (int j = 0; j < 32; j += 8) {
           if (col + j >= N) break;
-          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          if (bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + j));
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col + j), b1 = *reinterpret_cast<const float4*>(bias_s + col + j + 4);
+          float o[8] = {__uint_as_float(v[j]) + b0.x,     __uint_as_float(v[j + 1]) + b0.y, __uint_as_float(v[j + 2]) + b0.z,
+                        __uint_as_float(v[j + 3]) + b0.w, __uint_as_float(v[j + 4]) + b1.x, __uint_as_float(v[j + 5]) + b1.y,
+                        __uint_as_float(v[j + 6]) + b1.z, __uint_as_float(v[j + 7]) + b1.w};
+          if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
           }
-          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          __stcs(reinterpret_cast<float4*>(out + r * N + col + j), o);
+          if (wide) {
+            asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(orow + j), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
+                         "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+          } else {
+            __stcs(reinterpret_cast<float4*>(orow + j), make_float4(o[0], o[1], o[2], o[3]));
+            if (col + j + 4 < N) __stcs(reinterpret_cast<float4*>(orow + j + 4), make_float4(o[4], o[5], o[6], o[7]));
+          }
         }
       }
     }
