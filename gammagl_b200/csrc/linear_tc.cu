@@ -24,6 +24,7 @@
 //   * epilogue: 8 warps read the 128 x N fp32 accumulator with tcgen05.ld.32x32b.x16 (warp w: TMEM lanes 32 (w % 4) .., column
 //     half w / 4), add the bias, apply ReLU, and store 64-byte row pieces.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace ggl {
 
@@ -75,6 +76,12 @@ __global__ void __launch_bounds__(256) linear_prep_w_kernel(const float* __restr
   }
 }
 
+__device__ __forceinline__ bool elect_one() {   // one lane of a fully active warp
+  uint32_t leader;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+  return leader != 0;
+}
+
 __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
   asm volatile("{\n\t.reg .pred p;\n\tLW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LD;\n\tbra LW;\n\tLD:\n\t}"
                ::"r"(bar), "r"(parity) : "memory");
@@ -89,9 +96,8 @@ template <int KC>
 __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ wc,
                                                                const float* __restrict__ bias, const int relu, float* __restrict__ out,
                                                                const int64_t M, const int32_t K, const int32_t N, const int32_t tmem_cols,
-                                                               const int32_t k_passes) {
+                                                               const int32_t k_passes, const int32_t dbg) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(16) float bias_s[256];            // bias (or zeros) for the epilogue: broadcast shared-memory reads
   __shared__ __align__(8) unsigned long long bars[9];   // full[0..1], done[0..1], pass (all threads wait EVERY phase of it in order:
                                                         // a parity wait is only meaningful to a thread that has seen the previous phase)
   __shared__ uint32_t tmem_base_slot;
@@ -101,6 +107,7 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
   unsigned char* a_lo = smem + A_BYTES;
   unsigned char* b_ring = smem + 2 * A_BYTES;   // slot s at b_ring + s * 2 * B_BYTES: [W_hi | W_lo]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // the same value, provably warp-uniform: role branches stay convergent
   const int64_t row0 = (int64_t)blockIdx.x * kBM;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
   const int n_chunks = (N + kNC - 1) / kNC;
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
       const int r = band * 32 + lane;
       const int k = (kp * KC + kc) * 4;
       va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (item < 4 * KC && row0 + r < M && k < K) va[i] = __ldg(reinterpret_cast<const float4*>(A + (row0 + r) * K + k));
+      if (item < 4 * KC && row0 + r < M && k < K && !(dbg & 4)) va[i] = __ldg(reinterpret_cast<const float4*>(A + (row0 + r) * K + k));
     }
   };
   auto store_a = [&]() {
@@ -147,6 +154,10 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
   auto issue_copy = [&](int i) {
     const uint32_t slot = (uint32_t)i & 1u, full = bar0 + 8 * slot, done = bar0 + 16 + 8 * slot;
     if (i >= 2) mbar_wait_parity(done, (uint32_t)((i - 2) >> 1) & 1u);
+    if (dbg & 1) {   // experiment: no W traffic
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
+      return;
+    }
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(2u * B_BYTES) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"((uint32_t)__cvta_generic_to_shared(b_ring + slot * 2 * B_BYTES)), "l"(wc + (int64_t)i * (2 * B_BYTES / 4)),
@@ -154,14 +165,16 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
   };
 
   load_a(0);
-  bias_s[tid] = (bias != nullptr && tid < N) ? __ldg(bias + tid) : 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();   // barriers initialised, TMEM address published
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
-  if (tid == 32) {
-    issue_copy(0);
-    if (total > 1) issue_copy(1);
+  if (warp_u == 1) {
+    if (elect_one()) {
+      issue_copy(0);
+      if (total > 1) issue_copy(1);
+    }
+    __syncwarp();
   }
 
   // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
@@ -175,39 +188,46 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
     store_a();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (kp + 1 < k_passes) load_a(kp + 1);   // next slice in flight while the tensor core works on this one
+    if (warp_u == 0) {
+      // MMA role: the whole warp waits for the W block, ONE elected lane issues (operands stay in uniform registers: a lone
+      // `tid == 0` branch makes the compiler move five registers to the uniform file before every single MMA)
       for (int c = 0; c < n_chunks; ++c) {
         const int i = kp * n_chunks + c;
         const uint32_t slot = (uint32_t)i & 1u;
         mbar_wait_parity(bar0 + 8 * slot, (uint32_t)(i >> 1) & 1u);          // W block i has landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + (uint32_t)(c * kNC);
-        const uint32_t bh_s = b_ring_s + slot * 2 * B_BYTES, bl_s = bh_s + B_BYTES;
-#pragma unroll 1
-        for (int ks = 0; ks < KC / 2; ++ks) {   // one MMA K step = 8 elements = 2 chunks
-          const uint64_t ah = umma_desc(a_hi_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
-          const uint64_t al = umma_desc(a_lo_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
-          const uint64_t bh = umma_desc(bh_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
-          const uint64_t bl = umma_desc(bl_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
-          umma_tf32(d, al, bh, IDESC, (kp > 0 || ks > 0) ? 1u : 0u);   // small terms first
-          umma_tf32(d, ah, bl, IDESC, 1u);
-          umma_tf32(d, ah, bh, IDESC, 1u);
+        if (elect_one()) {
+          const uint32_t d = tmem_base + (uint32_t)(c * kNC);
+          const uint32_t bh_s = b_ring_s + slot * 2 * B_BYTES, bl_s = bh_s + B_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < KC / 2; ++ks) {   // one MMA K step = 8 elements = 2 chunks
+            const uint64_t ah = umma_desc(a_hi_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
+            const uint64_t al = umma_desc(a_lo_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
+            const uint64_t bh = umma_desc(bh_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
+            const uint64_t bl = umma_desc(bl_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
+            umma_tf32(d, al, bh, IDESC, (kp > 0 || ks > 0) ? 1u : 0u);   // small terms first
+            umma_tf32(d, ah, bl, IDESC, 1u);
+            umma_tf32(d, ah, bh, IDESC, 1u);
+          }
+          // arrives on `done[slot]` when every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 16 + 8 * slot) : "memory");
+          if (kp + 1 == k_passes)   // chunk c of the accumulator is final: its epilogue may start while the next chunks multiply
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 40 + 8 * c) : "memory");
+          if (c + 1 == n_chunks && kp + 1 < k_passes)   // pass done (the last pass is tracked per chunk: nothing may arrive after acc[])
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 32) : "memory");
         }
-        // arrives on `done[slot]` when every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 16 + 8 * slot) : "memory");
-        if (kp + 1 == k_passes)   // chunk c of the accumulator is final: its epilogue may start while the next chunks multiply
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 40 + 8 * c) : "memory");
+        __syncwarp();
       }
-      if (kp + 1 < k_passes)   // pass done (the last pass is tracked per chunk; nothing may arrive after the acc[] commits)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 32) : "memory");
-    } else if (tid == 32) {
-      for (int c = 0; c < n_chunks; ++c) {
-        const int i = kp * n_chunks + c + 2;
-        if (i < total) issue_copy(i);
+    } else if (warp_u == 1) {
+      if (elect_one()) {   // W producer
+        for (int c = 0; c < n_chunks; ++c) {
+          const int i = kp * n_chunks + c + 2;
+          if (i < total) issue_copy(i);
+        }
       }
+      __syncwarp();
     }
-    if (kp + 1 < k_passes) load_a(kp + 1);   // next slice in flight while the tensor core works on this one
   }
   // ---- epilogue: TMEM -> registers -> bias / ReLU -> global.  Warp w reads TMEM lanes 32 (w % 4) .. (its rows) and the column half
   // w / 4, 32 columns per tcgen05.ld; a lane holds 128 contiguous bytes of its output row and stores them as four 32-byte vectors
@@ -219,6 +239,12 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
     const int c_lo = half * (n_cols / 2), c_hi = c_lo + n_cols / 2;
     const bool wide = ((N & 7) == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0);
     for (int col = c_lo; col < c_hi; col += 32) {
+      // the bias of these 32 columns, requested BEFORE the waits below so its latency hides behind them (static shared memory is
+      // full: one more KB would cost the second resident CTA)
+      float4 bv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        bv[j] = (bias != nullptr && col + 4 * j < N) ? __ldg(reinterpret_cast<const float4*>(bias + col) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       mbar_wait_parity(bar0 + 40 + 8 * (uint32_t)(col / kNC), 0u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t v[32];
@@ -231,12 +257,12 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
             "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
             "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr) : "memory");
-      if (r < M && col < N) {
+      if (r < M && col < N && !(dbg & 2)) {
         float* orow = out + r * N + col;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           if (col + j >= N) break;
-          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col + j), b1 = *reinterpret_cast<const float4*>(bias_s + col + j + 4);
+          const float4 b0 = bv[j / 4], b1 = bv[j / 4 + 1];
           float o[8] = {__uint_as_float(v[j]) + b0.x,     __uint_as_float(v[j + 1]) + b0.y, __uint_as_float(v[j + 2]) + b0.z,
                         __uint_as_float(v[j + 3]) + b0.w, __uint_as_float(v[j + 4]) + b1.x, __uint_as_float(v[j + 5]) + b1.y,
                         __uint_as_float(v[j + 6]) + b1.z, __uint_as_float(v[j + 7]) + b1.w};
@@ -302,6 +328,8 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
   int k_passes, kc;
   linear_plan(K, &k_passes, &kc);
   float* wc = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  const char* dbg_env = getenv("GGLB200_LINEAR_DBG");   // timing experiments only (1: no W copies, 2: no stores, 4: no A loads)
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
   const unsigned grid = (unsigned)((M + kBM - 1) / kBM);
 #define GGL_LIN(KC_)                                                                                                        \
   do {                                                                                                                      \
@@ -312,7 +340,7 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
     const size_t smem = (size_t)2 * KC_ * kBM * 16 + (size_t)4 * KC_ * kNC * 16;                                            \
     GGL_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     linear_tf32x3_kernel<KC_><<<grid, 256, smem, stream>>>(A, wc, bias, relu, out, M, (int32_t)K, (int32_t)N, tmem_cols,    \
-                                                           k_passes);                                                       \
+                                                           k_passes, dbg);                                                       \
   } while (0)
   switch (linear_kc_class(kc)) {
     case 4: GGL_LIN(4); break;
