@@ -21,8 +21,8 @@
 //     chunk of the output, W_hi/W_lo transposed to [n, k];
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (UTCMMA; M = 128, N = 64, K = 8 per instruction), three per
 //     K step, accumulating into TMEM columns [n0, n0 + 64); tcgen05.commit arrives on an mbarrier when the chunk's MMAs retire;
-//   * epilogue: 8 warps read the 128 x N fp32 accumulator with tcgen05.ld.32x32b.x16 (warp w: TMEM lanes 32 (w % 4) .., column
-//     half w / 4), add the bias, apply ReLU, and store 64-byte row pieces.
+//   * epilogue: 8 warps read the 128 x N fp32 accumulator with tcgen05.ld.32x32b.x32 (warp w: TMEM lanes 32 (w % 4) .., column
+//     half w / 4), add the bias, apply ReLU, and store 32-byte vectors (a lane owns 128 contiguous bytes of its row).
 #include "common.cuh"
 #include <cstdlib>
 
@@ -88,10 +88,16 @@ __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) 
 }
 
 // KC = 16-byte K chunks per K PASS (even, <= 14: one MMA K step = 2 chunks).  K is covered by k_passes passes, each re-staging its slice
-// of A and accumulating into the same TMEM columns; with KC <= 14 a CTA needs 112 KB of shared memory (A_hi | A_lo | two W blocks), so
-// TWO CTAs are resident per SM.  Roles: all threads stage the A slice (fp32 -> hi / lo, one pass ahead in registers); thread 32 is the
-// W producer (one bulk async copy per (pass, chunk) into a 2-deep ring, mbarrier `full`); thread 0 issues the MMAs and commits them
-// to mbarrier `done` (ring slot free / accumulator ready); 8 warps run the epilogue.
+// of A and accumulating into the same TMEM columns; with KC <= 14 a CTA needs 112 KB of dynamic + 128 B of static shared memory
+// (A_hi | A_lo | two W blocks), so TWO CTAs are resident per SM -- one more KB of static shared memory costs the second one.
+// Roles: all threads stage the A slice (fp32 -> hi / lo, one pass ahead in registers); warp 1 elects the W producer (one bulk async
+// copy per (pass, chunk) into a 2-deep ring, mbarrier `full`); warp 0 waits for the block and ONE elected lane issues its MMAs and
+// commits them to `done` (ring slot free), `pass` (A slice free) and `acc[c]` (accumulator chunk final); 8 warps run the epilogue,
+// chunk by chunk as the acc barriers arrive.  The role warps are selected by a warp index that went through __shfl_sync: the compiler
+// then knows the branch is warp-uniform, keeps the descriptors in uniform registers and issues the UTCHMMAs back to back; behind a plain
+// `tid == 0` test every MMA is wrapped in an ELECT loop with five R2UR moves and costs ~129 cycles (tools/probe_linear.py).
+// Every barrier is waited phase by phase, in order, by each thread that uses it: a parity wait means nothing to a thread that has not
+// seen the previous phase.
 template <int KC>
 __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ wc,
                                                                const float* __restrict__ bias, const int relu, float* __restrict__ out,
