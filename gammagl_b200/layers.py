@@ -199,8 +199,9 @@ class GCNConv(MessagePassing):
 
 
 class SAGEConv(MessagePassing):
-    def __init__(self, in_channels, out_channels, activation=None, aggr='mean', add_bias=True, fused=True):
+    def __init__(self, in_channels, out_channels, activation=None, aggr='mean', add_bias=True, fused=True, fold_norm=True):
         super().__init__(fused)
+        self.fold_norm = fold_norm
         if aggr not in ('mean', 'gcn', 'pool'):
             raise NotImplementedError("aggr '%s' (lstm) is outside the aggregation path" % aggr)
         self.aggr, self.act, self.in_feat = aggr, activation, in_channels
@@ -222,6 +223,12 @@ class SAGEConv(MessagePassing):
             src_feat = self.fc_neigh(src_feat)
             n = int(1 + edge[0].max().item())
             edge = add_self_loops(edge, n)
+            if (self.fused and self.fold_norm and n == num_nodes == int(src_feat.shape[0])
+                    and int(edge[1].max().item()) < n):
+                # the same sum with calc_gcn_norm's weights folded into two row scalings and the bias into the row write:
+                # no [E] weight vector, no w[perm] gather, no separate bias pass (mpops.gcn_propagate, norm of utils/norm.py)
+                out = mpops.gcn_propagate(edge, src_feat, 'both_src', bias=self.bias if self.add_bias else None)
+                return self.act(out) if self.act is not None else out
             weight = calc_gcn_norm(edge, n)
             out = self.propagate(src_feat, edge, edge_weight=weight, num_nodes=n, aggr='sum')
             out = out[:num_nodes]

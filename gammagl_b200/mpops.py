@@ -546,6 +546,10 @@ class _GcnPropagate(torch.autograd.Function):
         K = x2d.shape[1]
         with torch.cuda.device(dev):
             ns = nd = None
+            if norm == 'both_src':             # SAGEConv(aggr='gcn'): utils/norm.py:27-30 takes deg(src)^-1/2 on BOTH ends of an edge
+                ns = torch.empty(N, dtype=torch.float32, device=dev)
+                _lib.check(lib.gglb200_degree_power(_ptr(g.bwd.rowptr), _ptr(ns), N, -0.5, _stream(dev)), 'degree_power')
+                nd = ns
             if norm in ('both', 'left'):       # source side: out-degree (degree(src), gcn_conv.py:89)
                 ns = torch.empty(N, dtype=torch.float32, device=dev)
                 _lib.check(lib.gglb200_degree_power(_ptr(g.bwd.rowptr), _ptr(ns), N, -0.5 if norm == 'both' else -1.0, _stream(dev)), 'degree_power')
@@ -588,8 +592,9 @@ class _GcnPropagate(torch.autograd.Function):
 
 def gcn_propagate(edge_index, x, norm='both', bias=None, relu=False):
     """GCNConv's normalised propagate with unit edge weights (gcn_conv.py:78-104 after the Linear), weight-stream free.
-    `bias` ([K] or [1, K]) and `relu` fuse `out + bias` (gcn_conv.py:104-106) and the model's ReLU into the row write."""
-    if norm not in ('both', 'left', 'right', 'none'):
+    `bias` ([K] or [1, K]) and `relu` fuse `out + bias` (gcn_conv.py:104-106) and the model's ReLU into the row write.
+    norm='both_src' is calc_gcn_norm's weighting (utils/norm.py:27-30: deg(src)^-1/2 at both ends), what SAGEConv(aggr='gcn') uses."""
+    if norm not in ('both', 'left', 'right', 'none', 'both_src'):
         raise ValueError('Invalid norm value. Must be either "none", "both", "right" or "left".')
     return _GcnPropagate.apply(x, edge_index, norm, bias, relu)
 

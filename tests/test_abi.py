@@ -89,6 +89,22 @@ def test_new_entry_points_validate_without_gpu():
     assert lib.gglb200_segment_expand_bwd(0, None, None, None, None, None, 4, 4, 4, 99, None) == -2  # unknown dtype (GGL_EUNSUPPORTED)
 
 
+def test_round2_entry_points_validate_without_gpu():
+    """tcgen05 Linear / sort-free reduce / sampler: size queries are host arithmetic, argument errors return before any launch."""
+    lib = _lib.load()
+    # K = 100 -> 25 sixteen-byte chunks -> 2 passes of 14; N = 256 -> 4 chunks of 64 columns; [W_hi | W_lo] tile pairs + alignment slack
+    assert lib.gglb200_linear_workspace_bytes(100, 256) == 2 * 4 * 2 * 14 * 64 * 16 + 256
+    assert lib.gglb200_linear_workspace_bytes(8, 16) == 1 * 1 * 2 * 4 * 64 * 16 + 256
+    assert lib.gglb200_linear_workspace_bytes(0, 16) == 0
+    assert lib.gglb200_linear_tf32x3(None, None, None, 0, None, 0, 8, 8, None, 0, None) == 0        # M == 0: nothing to do
+    assert lib.gglb200_linear_tf32x3(None, None, None, 0, None, 4, 8, 8, None, 0, None) == -1       # NULL pointers
+    assert b'NULL' in lib.gglb200_last_error()
+    assert lib.gglb200_linear_tf32x3(None, None, None, 0, None, 4, 6, 8, None, 0, None) == -1       # checked before the shape: pointers
+    assert lib.gglb200_segment_reduce_workspace_bytes(_lib.GGL_MAX, 10, 4) == 10 * 4 * 8 + 256
+    assert lib.gglb200_segment_reduce_workspace_bytes(_lib.GGL_SUM, 10, 64) == 0                    # wide sums need no replicas
+    assert lib.gglb200_segment_reduce_workspace_bytes(_lib.GGL_SUM, 10, 1) == 10 * 4 * 8 + 256       # 8 replicas of narrow sums
+
+
 def test_utils_reject_cpu_tensors():
     import pytest
     import torch

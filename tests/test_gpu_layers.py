@@ -209,6 +209,50 @@ def test_gcn_propagate_folded_vs_oracle(norm):
     assert rel(ob.float(), torch.from_numpy(ref)) < 2e-2
 
 
+def test_sage_gcn_folded_vs_oracle_and_unfolded_layer():
+    """SAGEConv(aggr='gcn') with the normalisation of utils/norm.py:27-30 (deg(src)^-1/2 on BOTH ends) folded into two row scalings
+    (mpops.gcn_propagate(norm='both_src')): against the oracle's gspmm with the per-edge weights on a DIRECTED graph with a split
+    row, and the layer with fold_norm on against the same layer with it off (outputs and every gradient)."""
+    import numpy as np
+    from gammagl_b200 import layers as L
+    from gammagl_b200 import mpops
+    from oracle import oracle as O
+    N, E, K = 1500, 24000, 36
+    g = torch.Generator().manual_seed(5)
+    src = torch.randint(0, N, (E,), generator=g)
+    dst = torch.randint(0, N, (E,), generator=g)
+    dst[:2500] = 11
+    ei = L.add_self_loops(torch.stack([src, dst]), N)
+    x = torch.randn(N, K, generator=g)
+    gout = torch.randn(N, K, generator=g)
+    deg = np.bincount(ei[0].numpy(), minlength=N).astype(np.float32)
+    dis = deg ** np.float32(-0.5)
+    w = dis[ei[0].numpy()] * dis[ei[1].numpy()]
+    ref, _ = O.spmm_fwd('sum', ei.numpy(), w, x.numpy())
+    gref = O.spmm_bwd('sum', ei.numpy(), w, gout.numpy())
+    xx = x.to(DEV).requires_grad_(True)
+    out = mpops.gcn_propagate(ei.to(DEV), xx, 'both_src')
+    out.backward(gout.to(DEV))
+    assert rel(out, torch.from_numpy(ref)) < 1e-5
+    assert rel(xx.grad, torch.from_numpy(gref)) < 1e-5
+    torch.manual_seed(3)
+    a = L.SAGEConv(K, 20, activation=torch.relu, aggr='gcn').to(DEV)
+    b = L.SAGEConv(K, 20, activation=torch.relu, aggr='gcn', fold_norm=False).to(DEV)
+    b.load_state_dict(a.state_dict())
+    with torch.no_grad():
+        a.bias.copy_(torch.randn(1, 20, generator=g))
+        b.bias.copy_(a.bias)
+    e0 = torch.stack([src, dst]).to(DEV)
+    e0[0, 0] = N - 1                                  # sage_conv.py:83 sizes the self loops by max(src) + 1
+    xa, xb = x.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
+    go = torch.randn(N, 20, generator=g).to(DEV)
+    oa, ob = a(xa, e0), b(xb, e0)
+    oa.backward(go); ob.backward(go)
+    assert rel(oa, ob) < 1e-5 and rel(xa.grad, xb.grad) < 1e-5
+    for (na, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert rel(pa.grad, pb.grad) < 2e-5, na
+
+
 @pytest.mark.parametrize('H,C,hub', [(8, 8, 3000), (2, 64, 0), (4, 16, 2500), (1, 4, 0), (8, 16, 1500), (3, 8, 2000),
                                      # H * C > 128: head groups (the reference default-shaped 8 x 64 layer, K = 512)
                                      (8, 64, 2000), (3, 128, 0), (5, 32, 1500)])

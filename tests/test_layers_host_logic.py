@@ -93,7 +93,11 @@ def gcn_propagate(edge_index, x, norm='both', bias=None, relu=False):
     N = x.shape[0]
     src, dst = edge_index
     w = torch.ones(edge_index.shape[1], dtype=x.dtype)
-    p = -0.5 if norm == 'both' else -1.0
+    p = -0.5 if norm in ('both', 'both_src') else -1.0
+    if norm == 'both_src':
+        d = torch.bincount(src, minlength=N).to(x.dtype)
+        dis = torch.where(d > 0, d.pow(p), torch.zeros_like(d))
+        w = w * dis[src] * dis[dst]
     if norm in ('both', 'left'):
         d = torch.bincount(src, minlength=N).to(x.dtype)
         w = w * torch.where(d > 0, d.pow(p), torch.zeros_like(d))[src]
