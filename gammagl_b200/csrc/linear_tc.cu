@@ -294,6 +294,203 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
   }
 }
 
+// ---- warp-specialised persistent form -------------------------------------------------------------------------------------------
+// One CTA per SM (320 threads), tiles t = blockIdx.x, + gridDim.x, ...; everything that the one-tile form above does in sequence
+// runs concurrently here, decoupled by mbarriers:
+//   warps 0-3  A producers: thread p stages row p of the tile, slice by slice (fp32 -> hi / lo) into a 2-deep ring of A slices
+//              (a_full: 128 arrivals after fence.proxy.async; a_empty: tcgen05.commit of the pass that read the slice);
+//   warp 4     MMA role (one elected lane): waits a_full / w_full, issues 21 MMAs per (pass, chunk), commits w_done, a_empty and, after
+//              the last pass, acc_full; the accumulators of tile i and i + 1 alternate between TMEM columns [0,256) and [256,512);
+//   warp 5     W producer (one elected lane): bulk async copies of the pre-split blocks into a 3-deep ring (w_full / w_done);
+//   warps 6-9  epilogue: wait acc_full, TMEM -> bias / ReLU -> 32-byte stores, arrive acc_empty (128 arrivals) -- while the tensor
+//              core already multiplies the next tile.
+// Barrier phases are derived from running counters (slice q, block i, tile it); every thread of a role waits every phase of its
+// barriers in order; the FIRST wait on an `empty` barrier uses the inverted parity and passes at once.
+constexpr int kWsRing = 3;
+template <int KC>
+__global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restrict__ A, const float* __restrict__ wc,
+                                                           const float* __restrict__ bias, const int relu, float* __restrict__ out,
+                                                           const int64_t M, const int32_t K, const int32_t N, const int32_t k_passes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(16) float bias_s[256];
+  __shared__ __align__(8) unsigned long long bars[4 + 2 * kWsRing + 4];   // a_full[2] a_empty[2] w_full[S] w_done[S] acc_full[2] acc_empty[2]
+  __shared__ uint32_t tmem_base_slot;
+  constexpr uint32_t A_BYTES = KC * kBM * 16;   // one of A_hi / A_lo of a slice
+  constexpr uint32_t B_BYTES = KC * kNC * 16;   // one of W_hi / W_lo of a block
+  unsigned char* a_ring = smem;                               // slice buffer b at a_ring + b * 2 * A_BYTES: [A_hi | A_lo]
+  unsigned char* b_ring = smem + 4 * A_BYTES;                 // slot s at b_ring + s * 2 * B_BYTES: [W_hi | W_lo]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+  const uint32_t A_FULL = bar0, A_EMPTY = bar0 + 16, W_FULL = bar0 + 32, W_DONE = W_FULL + 8 * kWsRing, ACC_FULL = W_DONE + 8 * kWsRing,
+                 ACC_EMPTY = ACC_FULL + 16;
+  const int n_chunks = (N + kNC - 1) / kNC;
+  const int total = k_passes * n_chunks;
+  const int n_tiles = (int)((M + kBM - 1) / kBM);
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_all = my_tiles * total;
+
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_base_slot)),
+                 "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(A_FULL + 8 * i) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(A_EMPTY + 8 * i) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ACC_FULL + 8 * i) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(ACC_EMPTY + 8 * i) : "memory");
+    }
+    for (int i = 0; i < kWsRing; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(W_FULL + 8 * i) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(W_DONE + 8 * i) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (tid < 256) bias_s[tid] = (bias != nullptr && tid < N) ? __ldg(bias + tid) : 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp_u < 4) {
+    // ---------------- A producers ----------------
+    const int r = tid;   // row of the tile
+    for (int it = 0; it < my_tiles; ++it) {
+      const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + r;
+      const float* arow = A + row * K;
+      for (int kp = 0; kp < k_passes; ++kp) {
+        const int q = it * k_passes + kp;
+        const uint32_t buf = (uint32_t)q & 1u;
+        float4 va[KC];
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) {
+          const int k = (kp * KC + kc) * 4;
+          va[kc] = (row < M && k < K) ? __ldg(reinterpret_cast<const float4*>(arow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_wait_parity(A_EMPTY + 8 * buf, (((uint32_t)q >> 1) & 1u) ^ 1u);   // the pass that read this buffer two slices ago has retired
+        unsigned char* hi = a_ring + buf * 2 * A_BYTES + (uint32_t)r * 16;
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) {
+          float4 h, l;
+          split_tf32(va[kc].x, h.x, l.x); split_tf32(va[kc].y, h.y, l.y); split_tf32(va[kc].z, h.z, l.z); split_tf32(va[kc].w, h.w, l.w);
+          *reinterpret_cast<float4*>(hi + (uint32_t)kc * (kBM * 16)) = h;
+          *reinterpret_cast<float4*>(hi + A_BYTES + (uint32_t)kc * (kBM * 16)) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(A_FULL + 8 * buf) : "memory");
+      }
+    }
+  } else if (warp_u == 4) {
+    // ---------------- MMA role ----------------
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    const uint32_t a_ring_s = (uint32_t)__cvta_generic_to_shared(a_ring), b_ring_s = (uint32_t)__cvta_generic_to_shared(b_ring);
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t ab = (uint32_t)it & 1u;
+      mbar_wait_parity(ACC_EMPTY + 8 * ab, (((uint32_t)it >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int kp = 0; kp < k_passes; ++kp) {
+        const int q = it * k_passes + kp;
+        const uint32_t buf = (uint32_t)q & 1u;
+        mbar_wait_parity(A_FULL + 8 * buf, ((uint32_t)q >> 1) & 1u);
+        for (int c = 0; c < n_chunks; ++c) {
+          const int i = q * n_chunks + c;
+          const uint32_t slot = (uint32_t)(i % kWsRing);
+          mbar_wait_parity(W_FULL + 8 * slot, (uint32_t)(i / kWsRing) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            const uint32_t d = tmem_base + ab * 256u + (uint32_t)(c * kNC);
+            const uint32_t a_hi_s = a_ring_s + buf * 2 * A_BYTES, a_lo_s = a_hi_s + A_BYTES;
+            const uint32_t bh_s = b_ring_s + slot * 2 * B_BYTES, bl_s = bh_s + B_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < KC / 2; ++ks) {
+              const uint64_t ah = umma_desc(a_hi_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
+              const uint64_t al = umma_desc(a_lo_s + (uint32_t)ks * 2 * (kBM * 16), kBM * 16, 128);
+              const uint64_t bh = umma_desc(bh_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
+              const uint64_t bl = umma_desc(bl_s + (uint32_t)ks * 2 * (kNC * 16), kNC * 16, 128);
+              umma_tf32(d, al, bh, IDESC, (kp > 0 || ks > 0) ? 1u : 0u);
+              umma_tf32(d, ah, bl, IDESC, 1u);
+              umma_tf32(d, ah, bh, IDESC, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(W_DONE + 8 * slot) : "memory");
+            if (c + 1 == n_chunks) {
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(A_EMPTY + 8 * buf) : "memory");
+              if (kp + 1 == k_passes)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ACC_FULL + 8 * ab) : "memory");
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp_u == 5) {
+    // ---------------- W producer ----------------
+    if (elect_one()) {
+      for (int i = 0; i < total_all; ++i) {
+        const uint32_t slot = (uint32_t)(i % kWsRing);
+        mbar_wait_parity(W_DONE + 8 * slot, ((uint32_t)(i / kWsRing) & 1u) ^ 1u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(W_FULL + 8 * slot), "r"(2u * B_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(b_ring + slot * 2 * B_BYTES)), "l"(wc + (int64_t)(i % total) * (2 * B_BYTES / 4)),
+                       "r"(2u * B_BYTES), "r"(W_FULL + 8 * slot) : "memory");
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue (warps 6-9: TMEM lane quarter = warp % 4) ----------------
+    const int q4 = warp & 3;
+    const int n_cols = n_chunks * kNC;
+    const bool wide = ((N & 7) == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0);
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t ab = (uint32_t)it & 1u;
+      const int64_t r = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + q4 * 32 + lane;
+      mbar_wait_parity(ACC_FULL + 8 * ab, ((uint32_t)it >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t t_lane = tmem_base + ab * 256u + ((uint32_t)(q4 * 32) << 16);
+      for (int col = 0; col < n_cols; col += 32) {
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+            "%25,%26,%27,%28,%29,%30,%31}, [%32];\n\ttcgen05.wait::ld.sync.aligned;"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(t_lane + (uint32_t)col) : "memory");
+        if (r < M && col < N) {
+          float* orow = out + r * N + col;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col + j >= N) break;
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col + j), b1 = *reinterpret_cast<const float4*>(bias_s + col + j + 4);
+            float o[8] = {__uint_as_float(v[j]) + b0.x,     __uint_as_float(v[j + 1]) + b0.y, __uint_as_float(v[j + 2]) + b0.z,
+                          __uint_as_float(v[j + 3]) + b0.w, __uint_as_float(v[j + 4]) + b1.x, __uint_as_float(v[j + 5]) + b1.y,
+                          __uint_as_float(v[j + 6]) + b1.z, __uint_as_float(v[j + 7]) + b1.w};
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+            }
+            if (wide) {
+              asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(orow + j), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
+                           "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+            } else {
+              __stcs(reinterpret_cast<float4*>(orow + j), make_float4(o[0], o[1], o[2], o[3]));
+              if (col + j + 4 < N) __stcs(reinterpret_cast<float4*>(orow + j + 4), make_float4(o[4], o[5], o[6], o[7]));
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads done before the accumulator is handed back
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ACC_EMPTY + 8 * ab) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
 }  // namespace ggl
 
 using namespace ggl;
@@ -337,12 +534,21 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
   const char* dbg_env = getenv("GGLB200_LINEAR_DBG");   // timing experiments only (1: no W copies, 2: no stores, 4: no A loads)
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   const unsigned grid = (unsigned)((M + kBM - 1) / kBM);
+  const char* form = getenv("GGLB200_LINEAR");   // "ws" (default): warp-specialised persistent kernel; "tile": one CTA per tile
+  const bool ws = form && form[0] == 'w';
+  const unsigned grid_ws = (unsigned)((int64_t)grid < (int64_t)sm_count() ? grid : sm_count());
 #define GGL_LIN(KC_)                                                                                                        \
   do {                                                                                                                      \
     const int64_t items = (int64_t)k_passes * n_chunks * KC_ * kNC;                                                         \
     linear_prep_w_kernel<KC_><<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(W, wc, (int32_t)K, (int32_t)N, k_passes,  \
                                                                                    n_chunks);                               \
     GGL_LAUNCHED("linear_prep_w");                                                                                          \
+    if (ws) {                                                                                                               \
+      const size_t smem_ws = (size_t)4 * KC_ * kBM * 16 + (size_t)kWsRing * 2 * KC_ * kNC * 16;                             \
+      GGL_CUDA(cudaFuncSetAttribute(linear_ws_kernel<KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));     \
+      linear_ws_kernel<KC_><<<grid_ws, 320, smem_ws, stream>>>(A, wc, bias, relu, out, M, (int32_t)K, (int32_t)N, k_passes); \
+      break;                                                                                                                \
+    }                                                                                                                       \
     const size_t smem = (size_t)2 * KC_ * kBM * 16 + (size_t)4 * KC_ * kNC * 16;                                            \
     GGL_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     linear_tf32x3_kernel<KC_><<<grid, 256, smem, stream>>>(A, wc, bias, relu, out, M, (int32_t)K, (int32_t)N, tmem_cols,    \

@@ -24,7 +24,7 @@ import os
 import torch
 
 from . import mpops
-from .csr import segment_csr_of
+from .csr import derived_of, segment_csr_of
 
 
 _EPILOGUE = os.environ.get('GGLB200_EPILOGUE', '1') != '0'   # 0: bias / activation as separate torch ops (same results)
@@ -221,10 +221,13 @@ class SAGEConv(MessagePassing):
             out = self.propagate(src_feat, edge, edge_weight=None, num_nodes=num_nodes, aggr='mean')
         elif self.aggr == 'gcn':                                            # sage_conv.py:82-88
             src_feat = self.fc_neigh(src_feat)
-            n = int(1 + edge[0].max().item())
-            edge = add_self_loops(edge, n)
-            if (self.fused and self.fold_norm and n == num_nodes == int(src_feat.shape[0])
-                    and int(edge[1].max().item()) < n):
+            raw = edge
+
+            def with_loops():                                               # two host syncs + a 2 (E + n) copy: once per edge list
+                n_ = int(1 + raw[0].max().item())
+                return n_, int(raw[1].max().item()), add_self_loops(raw, n_)
+            n, max_dst, edge = derived_of(raw, 'sage_gcn_self_loops', with_loops) if raw.is_cuda else with_loops()
+            if self.fused and self.fold_norm and n == num_nodes == int(src_feat.shape[0]) and max_dst < n:
                 # the same sum with calc_gcn_norm's weights folded into two row scalings and the bias into the row write:
                 # no [E] weight vector, no w[perm] gather, no separate bias pass (mpops.gcn_propagate, norm of utils/norm.py)
                 out = mpops.gcn_propagate(edge, src_feat, 'both_src', bias=self.bias if self.add_bias else None)

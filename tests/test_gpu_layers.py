@@ -251,6 +251,11 @@ def test_sage_gcn_folded_vs_oracle_and_unfolded_layer():
     assert rel(oa, ob) < 1e-5 and rel(xa.grad, xb.grad) < 1e-5
     for (na, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         assert rel(pa.grad, pb.grad) < 2e-5, na
+    # the self-looped edge list is derived ONCE per edge_index, so the identity-keyed graph cache hits on the second forward
+    from gammagl_b200 import csr
+    csr.clear_caches()
+    a(xa, e0); a(xa, e0)
+    assert len(csr._derived.d) == 1 and len(csr._graphs.d) == 1
 
 
 @pytest.mark.parametrize('H,C,hub', [(8, 8, 3000), (2, 64, 0), (4, 16, 2500), (1, 4, 0), (8, 16, 1500), (3, 8, 2000),

@@ -110,3 +110,31 @@ def test_two_streams_share_a_cached_graph(mp):
         assert np.max(np.abs(oa.cpu().numpy() - ra)) <= 1e-5 * np.max(np.abs(ra))
         assert np.max(np.abs(ob.cpu().numpy() - rb)) <= 1e-5 * np.max(np.abs(rb))
         assert torch.equal(oa, outs[0][0]) and torch.equal(ob, outs[0][1])     # deterministic, no cross-talk
+
+
+def test_rebuilt_edge_lists_hit_the_cache_by_content(mp):
+    """Reference layers build a fresh edge tensor every forward (sage_conv.py:83-85 add_self_loops): an identity miss falls back
+    to an exact content match, so the CSR is built once; a tensor modified in place afterwards is never matched."""
+    from gammagl_b200 import csr
+    g = torch.Generator().manual_seed(4)
+    N, E, K = 300, 5000, 12
+    ei = torch.stack([torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g)]).to(DEV)
+    x = torch.randn(N, K, generator=g).to(DEV)
+    ids = ei[1].clone()
+    msg = torch.randn(E, K, generator=g).to(DEV)
+    csr.clear_caches()
+    h0, s0 = csr._graphs.content_hits, csr._segments.content_hits
+    a = mp.gspmm(ei, None, x, 'sum')
+    b = mp.gspmm(ei.clone(), None, x, 'sum')                       # new storage, same contents
+    assert torch.equal(a, b) and csr._graphs.content_hits == h0 + 1
+    sa = mp.unsorted_segment_sum(msg, ids, N)
+    sb = mp.unsorted_segment_sum(msg, ids.clone(), N)
+    assert torch.equal(sa, sb) and csr._segments.content_hits == s0 + 1
+    # in-place change of a cached tensor: its old entry must not serve a clone of the NEW contents
+    e2 = ei.clone()
+    first = mp.gspmm(e2, None, x, 'sum')
+    e2[1, :100] = (e2[1, :100] + 1) % N
+    want, _ = O.spmm_fwd('sum', e2.cpu().numpy(), np.ones(E, dtype=np.float32), x.cpu().numpy())
+    got = mp.gspmm(e2.clone(), None, x, 'sum')
+    assert np.abs(got.cpu().numpy() - want).max() <= 1e-5 * np.abs(want).max()
+    assert not torch.equal(got, first)
