@@ -306,14 +306,15 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
 //              core already multiplies the next tile.
 // Barrier phases are derived from running counters (slice q, block i, tile it); every thread of a role waits every phase of its
 // barriers in order; the FIRST wait on an `empty` barrier uses the inverted parity and passes at once.
-constexpr int kWsRing = 3;
+constexpr int kWsRingMax = 4;   // W ring depth: 2 .. 4 slots (GGLB200_LINEAR_RING, default 2: a smaller shared-memory carve-out leaves the A producers more L1)
 template <int KC>
 __global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restrict__ A, const float* __restrict__ wc,
                                                            const float* __restrict__ bias, const int relu, float* __restrict__ out,
-                                                           const int64_t M, const int32_t K, const int32_t N, const int32_t k_passes) {
+                                                           const int64_t M, const int32_t K, const int32_t N, const int32_t k_passes,
+                                                           const int32_t ring) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(16) float bias_s[256];
-  __shared__ __align__(8) unsigned long long bars[4 + 2 * kWsRing + 4];   // a_full[2] a_empty[2] w_full[S] w_done[S] acc_full[2] acc_empty[2]
+  __shared__ __align__(8) unsigned long long bars[4 + 2 * kWsRingMax + 4];   // a_full[2] a_empty[2] w_full[S] w_done[S] acc_full[2] acc_empty[2]
   __shared__ uint32_t tmem_base_slot;
   constexpr uint32_t A_BYTES = KC * kBM * 16;   // one of A_hi / A_lo of a slice
   constexpr uint32_t B_BYTES = KC * kNC * 16;   // one of W_hi / W_lo of a block
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
-  const uint32_t A_FULL = bar0, A_EMPTY = bar0 + 16, W_FULL = bar0 + 32, W_DONE = W_FULL + 8 * kWsRing, ACC_FULL = W_DONE + 8 * kWsRing,
+  const uint32_t A_FULL = bar0, A_EMPTY = bar0 + 16, W_FULL = bar0 + 32, W_DONE = W_FULL + 8 * kWsRingMax, ACC_FULL = W_DONE + 8 * kWsRingMax,
                  ACC_EMPTY = ACC_FULL + 16;
   const int n_chunks = (N + kNC - 1) / kNC;
   const int total = k_passes * n_chunks;
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restri
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ACC_FULL + 8 * i) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(ACC_EMPTY + 8 * i) : "memory");
     }
-    for (int i = 0; i < kWsRing; ++i) {
+    for (int i = 0; i < kWsRingMax; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(W_FULL + 8 * i) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(W_DONE + 8 * i) : "memory");
     }
@@ -357,30 +358,42 @@ __global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restri
 
   if (warp_u < 4) {
     // ---------------- A producers ----------------
+    // Two slices in registers: the loads of slice q + 1 are in flight while slice q waits for its buffer and is split / stored, so
+    // the DRAM latency never sits between two MMA passes.
     const int r = tid;   // row of the tile
-    for (int it = 0; it < my_tiles; ++it) {
+    const int n_slices = my_tiles * k_passes;
+    auto load_slice = [&](float4 (&v)[KC], int q) {
+      const int it = q / k_passes, kp = q - it * k_passes;
       const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + r;
       const float* arow = A + row * K;
-      for (int kp = 0; kp < k_passes; ++kp) {
-        const int q = it * k_passes + kp;
-        const uint32_t buf = (uint32_t)q & 1u;
-        float4 va[KC];
 #pragma unroll
-        for (int kc = 0; kc < KC; ++kc) {
-          const int k = (kp * KC + kc) * 4;
-          va[kc] = (row < M && k < K) ? __ldg(reinterpret_cast<const float4*>(arow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        mbar_wait_parity(A_EMPTY + 8 * buf, (((uint32_t)q >> 1) & 1u) ^ 1u);   // the pass that read this buffer two slices ago has retired
-        unsigned char* hi = a_ring + buf * 2 * A_BYTES + (uint32_t)r * 16;
+      for (int kc = 0; kc < KC; ++kc) {
+        const int k = (kp * KC + kc) * 4;
+        v[kc] = (row < M && k < K) ? __ldg(reinterpret_cast<const float4*>(arow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store_slice = [&](const float4 (&v)[KC], int q) {
+      const uint32_t buf = (uint32_t)q & 1u;
+      mbar_wait_parity(A_EMPTY + 8 * buf, (((uint32_t)q >> 1) & 1u) ^ 1u);   // the pass that read this buffer two slices ago has retired
+      unsigned char* hi = a_ring + buf * 2 * A_BYTES + (uint32_t)r * 16;
 #pragma unroll
-        for (int kc = 0; kc < KC; ++kc) {
-          float4 h, l;
-          split_tf32(va[kc].x, h.x, l.x); split_tf32(va[kc].y, h.y, l.y); split_tf32(va[kc].z, h.z, l.z); split_tf32(va[kc].w, h.w, l.w);
-          *reinterpret_cast<float4*>(hi + (uint32_t)kc * (kBM * 16)) = h;
-          *reinterpret_cast<float4*>(hi + A_BYTES + (uint32_t)kc * (kBM * 16)) = l;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(A_FULL + 8 * buf) : "memory");
+      for (int kc = 0; kc < KC; ++kc) {
+        float4 h, l;
+        split_tf32(v[kc].x, h.x, l.x); split_tf32(v[kc].y, h.y, l.y); split_tf32(v[kc].z, h.z, l.z); split_tf32(v[kc].w, h.w, l.w);
+        *reinterpret_cast<float4*>(hi + (uint32_t)kc * (kBM * 16)) = h;
+        *reinterpret_cast<float4*>(hi + A_BYTES + (uint32_t)kc * (kBM * 16)) = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(A_FULL + 8 * buf) : "memory");
+    };
+    float4 va[KC], vb[KC];
+    load_slice(va, 0);
+    for (int q = 0; q < n_slices; q += 2) {
+      if (q + 1 < n_slices) load_slice(vb, q + 1);
+      store_slice(va, q);
+      if (q + 1 < n_slices) {
+        if (q + 2 < n_slices) load_slice(va, q + 2);
+        store_slice(vb, q + 1);
       }
     }
   } else if (warp_u == 4) {
@@ -397,8 +410,8 @@ __global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restri
         mbar_wait_parity(A_FULL + 8 * buf, ((uint32_t)q >> 1) & 1u);
         for (int c = 0; c < n_chunks; ++c) {
           const int i = q * n_chunks + c;
-          const uint32_t slot = (uint32_t)(i % kWsRing);
-          mbar_wait_parity(W_FULL + 8 * slot, (uint32_t)(i / kWsRing) & 1u);
+          const uint32_t slot = (uint32_t)(i % ring);
+          mbar_wait_parity(W_FULL + 8 * slot, (uint32_t)(i / ring) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
             const uint32_t d = tmem_base + ab * 256u + (uint32_t)(c * kNC);
@@ -429,8 +442,8 @@ __global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restri
     // ---------------- W producer ----------------
     if (elect_one()) {
       for (int i = 0; i < total_all; ++i) {
-        const uint32_t slot = (uint32_t)(i % kWsRing);
-        mbar_wait_parity(W_DONE + 8 * slot, ((uint32_t)(i / kWsRing) & 1u) ^ 1u);
+        const uint32_t slot = (uint32_t)(i % ring);
+        mbar_wait_parity(W_DONE + 8 * slot, ((uint32_t)(i / ring) & 1u) ^ 1u);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(W_FULL + 8 * slot), "r"(2u * B_BYTES) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"((uint32_t)__cvta_generic_to_shared(b_ring + slot * 2 * B_BYTES)), "l"(wc + (int64_t)(i % total) * (2 * B_BYTES / 4)),
@@ -537,6 +550,8 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
   const char* form = getenv("GGLB200_LINEAR");   // "ws" (default): warp-specialised persistent kernel; "tile": one CTA per tile
   const bool ws = form && form[0] == 'w';
   const unsigned grid_ws = (unsigned)((int64_t)grid < (int64_t)sm_count() ? grid : sm_count());
+  const char* ring_env = getenv("GGLB200_LINEAR_RING");
+  const int ring = (ring_env && atoi(ring_env) >= 2 && atoi(ring_env) <= kWsRingMax) ? atoi(ring_env) : 2;
 #define GGL_LIN(KC_)                                                                                                        \
   do {                                                                                                                      \
     const int64_t items = (int64_t)k_passes * n_chunks * KC_ * kNC;                                                         \
@@ -544,9 +559,10 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
                                                                                    n_chunks);                               \
     GGL_LAUNCHED("linear_prep_w");                                                                                          \
     if (ws) {                                                                                                               \
-      const size_t smem_ws = (size_t)4 * KC_ * kBM * 16 + (size_t)kWsRing * 2 * KC_ * kNC * 16;                             \
+      const size_t smem_ws = (size_t)4 * KC_ * kBM * 16 + (size_t)ring * 2 * KC_ * kNC * 16;                                 \
       GGL_CUDA(cudaFuncSetAttribute(linear_ws_kernel<KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));     \
-      linear_ws_kernel<KC_><<<grid_ws, 320, smem_ws, stream>>>(A, wc, bias, relu, out, M, (int32_t)K, (int32_t)N, k_passes); \
+      linear_ws_kernel<KC_><<<grid_ws, 320, smem_ws, stream>>>(A, wc, bias, relu, out, M, (int32_t)K, (int32_t)N, k_passes,  \
+                                                               ring);                                                        \
       break;                                                                                                                \
     }                                                                                                                       \
     const size_t smem = (size_t)2 * KC_ * kBM * 16 + (size_t)4 * KC_ * kNC * 16;                                            \

@@ -1,0 +1,10 @@
+#!/bin/bash
+# round-2 call 30 (1 GPU): warp-specialised GEMM with register double-buffered A producers: tests, ring A/B, layer bench, ncu
+O=gpurun_out; mkdir -p $O
+export GGLB200_LINEAR=ws
+timeout 120 python -m pytest tests/test_gpu_linear_tc.py -q -m gpu 2>&1 | tail -2
+for r in 2 3; do echo ring $r; GGLB200_LINEAR_RING=$r timeout 100 python tools/probe_linear.py 2>&1 | tee $O/probe_linear_r2_ws2_ring$r.json; done
+timeout 300 python tools/bench_layer.py 256 > $O/bench_layer_r2_ws2.json 2>/dev/null; cut -c1-1000 $O/bench_layer_r2_ws2.json
+timeout 400 ncu --set full --import-source on --clock-control none -k regex:linear_ws -c 1 -o $O/prof_linear python tools/bench_layer.py 256 > $O/ncu_linear.log 2>&1
+ncu -i $O/prof_linear.ncu-rep --page source --csv > $O/ncu_r2_linear_ws_source.csv 2>/dev/null
+ncu -i $O/prof_linear.ncu-rep --page raw --csv > $O/ncu_r2_linear_ws_raw.csv 2>/dev/null; rm -f $O/prof_linear.ncu-rep
