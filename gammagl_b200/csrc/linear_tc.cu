@@ -14,7 +14,12 @@
 // truncation of the lo parts are O(2^-21) relative: parity with the fp32 reference at 1e-5 is tested, plain TF32 (2^-11) would
 // not pass it.
 //
-// Layout / instructions (cta_group::1, one CTA per 128 output rows, 256 threads, two CTAs resident per SM):
+// Two kernels share the operand layout and the W preparation: `linear_ws_kernel` (default) -- persistent, warp-specialised, one CTA per
+// SM, two TMEM accumulators so the epilogue of a tile overlaps the MMAs of the next -- and `linear_tf32x3_kernel` (GGLB200_LINEAR=tile)
+// -- one CTA per 128-row tile, two CTAs per SM, all warps run the phases in sequence.  Measured at C3 (100 -> 256, bias + ReLU):
+// 0.93 ms and 1.56 ms (cuBLAS GEMM alone 2.95 ms); DESIGN.md 4.2 has the history and the probes.
+//
+// Layout / instructions (cta_group::1, 128 output rows per tile):
 //   * operands in the canonical NO-SWIZZLE K-major layout of tcgen05 shared-memory descriptors: 8-row x 16-byte core matrices;
 //     element (r, k) of a [R, K] operand sits at  (k / 4) * R * 16  +  r * 16  +  (k % 4) * 4   (K-chunk stride LBO = 16 R,
 //     8-row-group stride SBO = 128).  Threads write A_hi/A_lo (lane <-> row: conflict-free 16-byte stores) and, per 64-column
@@ -308,23 +313,24 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
 // barriers in order; the FIRST wait on an `empty` barrier uses the inverted parity and passes at once.
 constexpr int kWsRingMax = 4;   // W ring depth: 2 .. 4 slots (GGLB200_LINEAR_RING, default 2: a smaller shared-memory carve-out leaves the A producers more L1)
 template <int KC>
-__global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restrict__ A, const float* __restrict__ wc,
+__global__ void __launch_bounds__(352, 1) linear_ws_kernel(const float* __restrict__ A, const float* __restrict__ wc,
                                                            const float* __restrict__ bias, const int relu, float* __restrict__ out,
                                                            const int64_t M, const int32_t K, const int32_t N, const int32_t k_passes,
-                                                           const int32_t ring) {
+                                                           const int32_t ring, const int32_t staged) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(16) float bias_s[256];
-  __shared__ __align__(8) unsigned long long bars[4 + 2 * kWsRingMax + 4];   // a_full[2] a_empty[2] w_full[S] w_done[S] acc_full[2] acc_empty[2]
+  __shared__ __align__(8) unsigned long long bars[4 + 2 * kWsRingMax + 4 + 2];   // a_full[2] a_empty[2] w_full[S] w_done[S] acc_full[2] acc_empty[2] raw_full raw_empty
   __shared__ uint32_t tmem_base_slot;
   constexpr uint32_t A_BYTES = KC * kBM * 16;   // one of A_hi / A_lo of a slice
   constexpr uint32_t B_BYTES = KC * kNC * 16;   // one of W_hi / W_lo of a block
   unsigned char* a_ring = smem;                               // slice buffer b at a_ring + b * 2 * A_BYTES: [A_hi | A_lo]
   unsigned char* b_ring = smem + 4 * A_BYTES;                 // slot s at b_ring + s * 2 * B_BYTES: [W_hi | W_lo]
+  unsigned char* raw = b_ring + (uint32_t)ring * 2 * B_BYTES; // staged form: the fp32 tile as it lies in global memory, [128, K]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
   const uint32_t A_FULL = bar0, A_EMPTY = bar0 + 16, W_FULL = bar0 + 32, W_DONE = W_FULL + 8 * kWsRingMax, ACC_FULL = W_DONE + 8 * kWsRingMax,
-                 ACC_EMPTY = ACC_FULL + 16;
+                 ACC_EMPTY = ACC_FULL + 16, RAW_FULL = ACC_EMPTY + 16, RAW_EMPTY = RAW_FULL + 8;
   const int n_chunks = (N + kNC - 1) / kNC;
   const int total = k_passes * n_chunks;
   const int n_tiles = (int)((M + kBM - 1) / kBM);
@@ -347,6 +353,8 @@ __global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restri
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(W_FULL + 8 * i) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(W_DONE + 8 * i) : "memory");
     }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(RAW_FULL) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(RAW_EMPTY) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -386,6 +394,27 @@ __global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restri
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(A_FULL + 8 * buf) : "memory");
     };
+    if (staged) {
+      // Staged form (k_passes <= 2): the whole fp32 tile -- 128 consecutive rows = ONE contiguous piece of global memory -- arrives by a
+      // single bulk async copy (warp 10); a thread takes its row into registers, hands the staging buffer back at once (the next
+      // tile's copy overlaps this tile's split / store / MMA) and then feeds the slice ring from registers.  No L1, no per-thread
+      // 16-byte requests: the loads were the limit of the form below (8 k cycles per 28 KB slice in flight).
+      float4 v0[KC], v1[KC];
+      for (int it = 0; it < my_tiles; ++it) {
+        const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + r;
+        mbar_wait_parity(RAW_FULL, (uint32_t)it & 1u);
+        const unsigned char* rrow = raw + (size_t)r * (size_t)K * 4;
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) {
+          const int k0 = kc * 4, k1 = (KC + kc) * 4;
+          v0[kc] = (row < M && k0 < K) ? *reinterpret_cast<const float4*>(rrow + k0 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v1[kc] = (row < M && k1 < K && k_passes > 1) ? *reinterpret_cast<const float4*>(rrow + k1 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(RAW_EMPTY) : "memory");   // row is in registers
+        store_slice(v0, it * k_passes);
+        if (k_passes > 1) store_slice(v1, it * k_passes + 1);
+      }
+    } else {
     float4 va[KC], vb[KC];
     load_slice(va, 0);
     for (int q = 0; q < n_slices; q += 2) {
@@ -395,6 +424,7 @@ __global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restri
         if (q + 2 < n_slices) load_slice(va, q + 2);
         store_slice(vb, q + 1);
       }
+    }
     }
   } else if (warp_u == 4) {
     // ---------------- MMA role ----------------
@@ -448,6 +478,20 @@ __global__ void __launch_bounds__(320, 1) linear_ws_kernel(const float* __restri
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"((uint32_t)__cvta_generic_to_shared(b_ring + slot * 2 * B_BYTES)), "l"(wc + (int64_t)(i % total) * (2 * B_BYTES / 4)),
                        "r"(2u * B_BYTES), "r"(W_FULL + 8 * slot) : "memory");
+      }
+    }
+    __syncwarp();
+  } else if (warp_u == 10) {
+    // ---------------- A tile copies (staged form) ----------------
+    if (staged && elect_one()) {
+      for (int it = 0; it < my_tiles; ++it) {
+        const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM;
+        const int64_t rows = (M - row0 < kBM) ? (M - row0) : kBM;
+        const uint32_t bytes = (uint32_t)(rows * K * 4);
+        mbar_wait_parity(RAW_EMPTY, ((uint32_t)it & 1u) ^ 1u);   // every producer thread holds its row of the previous tile
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(RAW_FULL), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(raw)), "l"(A + row0 * K), "r"(bytes), "r"(RAW_FULL) : "memory");
       }
     }
     __syncwarp();
@@ -548,8 +592,10 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   const unsigned grid = (unsigned)((M + kBM - 1) / kBM);
   const char* form = getenv("GGLB200_LINEAR");   // "ws" (default): warp-specialised persistent kernel; "tile": one CTA per tile
-  const bool ws = form && form[0] == 'w';
+  const bool ws = !(form && form[0] == 't');
   const unsigned grid_ws = (unsigned)((int64_t)grid < (int64_t)sm_count() ? grid : sm_count());
+  const char* stage_env = getenv("GGLB200_LINEAR_STAGE");   // "0": keep the per-thread loads even where the staged form applies
+  const bool no_stage = stage_env && stage_env[0] == '0';
   const char* ring_env = getenv("GGLB200_LINEAR_RING");
   const int ring = (ring_env && atoi(ring_env) >= 2 && atoi(ring_env) <= kWsRingMax) ? atoi(ring_env) : 2;
 #define GGL_LIN(KC_)                                                                                                        \
@@ -559,10 +605,12 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
                                                                                    n_chunks);                               \
     GGL_LAUNCHED("linear_prep_w");                                                                                          \
     if (ws) {                                                                                                               \
-      const size_t smem_ws = (size_t)4 * KC_ * kBM * 16 + (size_t)ring * 2 * KC_ * kNC * 16;                                 \
+      const size_t smem_ring = (size_t)4 * KC_ * kBM * 16 + (size_t)ring * 2 * KC_ * kNC * 16;                             \
+      const int staged = (!no_stage && k_passes <= 2 && smem_ring + (size_t)kBM * K * 4 + 2048 <= 232448) ? 1 : 0;          \
+      const size_t smem_ws = smem_ring + (staged ? (size_t)kBM * K * 4 : 0);                                                 \
       GGL_CUDA(cudaFuncSetAttribute(linear_ws_kernel<KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));     \
-      linear_ws_kernel<KC_><<<grid_ws, 320, smem_ws, stream>>>(A, wc, bias, relu, out, M, (int32_t)K, (int32_t)N, k_passes,  \
-                                                               ring);                                                        \
+      linear_ws_kernel<KC_><<<grid_ws, 352, smem_ws, stream>>>(A, wc, bias, relu, out, M, (int32_t)K, (int32_t)N, k_passes,  \
+                                                               ring, staged);                                                \
       break;                                                                                                                \
     }                                                                                                                       \
     const size_t smem = (size_t)2 * KC_ * kBM * 16 + (size_t)4 * KC_ * kNC * 16;                                            \
