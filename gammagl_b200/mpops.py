@@ -613,26 +613,37 @@ def check_message_bytes(num_edges, row_numel, elem_size, what):
                             'max on 2-D features, or raise the limit' % (what, num_edges, row_numel, need / 1e9, MAX_MESSAGE_BYTES / 1e9))
 
 
+def _linear_tf32x3(a, w, bflat, relu):
+    """Launch gglb200_linear_tf32x3 on contiguous fp32 a [M, K], w [K, N] (no autograd)."""
+    lib = _lib.load()
+    M, K = a.shape
+    N = w.shape[1]
+    dev = a.device
+    with torch.cuda.device(dev):
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+        nb = lib.gglb200_linear_workspace_bytes(K, N)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gglb200_linear_tf32x3(_ptr(a), _ptr(w), _ptr(bflat), int(bool(relu)), _ptr(out), M, K, N, _ptr(ws), nb,
+                                             _stream(dev)), 'linear_tf32x3')
+    return out
+
+
+# input gradient of the Linear, g @ W^T: 'tc' = the same tcgen05 kernel on the transposed weight, 'lib' = torch.matmul
+_LINEAR_BWD = os.environ.get('GGLB200_LINEAR_BWD', 'tc')     # measured at C3 (256 -> 100): 1.37 ms vs 2.91 ms
+
+
 class _LinearTC(torch.autograd.Function):
     """out = act(A @ W + bias) on the tcgen05 tensor cores with fp32 accuracy (csrc/linear_tc.cu, 3xTF32, TMEM accumulator):
-    the Linear + bias + ReLU that follows the aggregation when a layer aggregates first (gcn_conv.py:79,104-106).  The two
-    backward GEMMs are plain library GEMMs (torch.matmul)."""
+    the Linear + bias + ReLU that follows the aggregation when a layer aggregates first (gcn_conv.py:79,104-106).  The weight
+    gradient (a reduction over the rows) is a library GEMM; the input gradient is the same kind of GEMM as the forward
+    (GGLB200_LINEAR_BWD)."""
 
     @staticmethod
     def forward(ctx, a, w, bias, relu):
-        lib = _lib.load()
         a = a.contiguous()
         w = w.contiguous()
-        M, K = a.shape
-        N = w.shape[1]
-        dev = a.device
         bflat = None if bias is None else bias.detach().reshape(-1).to(torch.float32).contiguous()
-        with torch.cuda.device(dev):
-            out = torch.empty((M, N), dtype=torch.float32, device=dev)
-            nb = lib.gglb200_linear_workspace_bytes(K, N)
-            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
-            _lib.check(lib.gglb200_linear_tf32x3(_ptr(a), _ptr(w), _ptr(bflat), int(bool(relu)), _ptr(out), M, K, N, _ptr(ws), nb,
-                                                 _stream(dev)), 'linear_tf32x3')
+        out = _linear_tf32x3(a, w, bflat, relu)
         ctx.relu = bool(relu)
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.save_for_backward(a, w, out if relu else None)
@@ -644,7 +655,13 @@ class _LinearTC(torch.autograd.Function):
         g = g.contiguous()
         if ctx.relu:
             g = g * (out > 0).to(g.dtype)
-        ga = g @ w.t() if ctx.needs_input_grad[0] else None
+        ga = None
+        if ctx.needs_input_grad[0]:
+            wt = w.t()
+            if _LINEAR_BWD == 'tc' and g.dtype == torch.float32 and linear_tc_supported(g, wt):
+                ga = _linear_tf32x3(g, wt.contiguous(), None, False)
+            else:
+                ga = g @ wt
         gw = a.t() @ g if ctx.needs_input_grad[1] else None
         gb = g.sum(dim=0).reshape(ctx.bias_shape) if ctx.bias_shape is not None and ctx.needs_input_grad[2] else None
         return ga, gw, gb, None
