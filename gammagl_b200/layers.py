@@ -30,11 +30,18 @@ from .csr import derived_of, segment_csr_of
 _EPILOGUE = os.environ.get('GGLB200_EPILOGUE', '1') != '0'   # 0: bias / activation as separate torch ops (same results)
 
 
+# 'tc': every mirrored Linear whose shape the tcgen05 kernel supports (fp32, in / out features multiples of 4 up to 256) runs
+# mpops.linear_tc (3xTF32 on the tensor cores, 1.3e-6 vs fp64; C3 100 -> 256: 0.93 ms vs 2.95 ms for the library GEMM) in forward and
+# input-gradient; 'lib' (default) keeps torch.matmul.  Per layer: Linear(..., tensor_core=True).
+LAYER_LINEAR = os.environ.get('GGLB200_LAYER_LINEAR', 'lib')
+
+
 class Linear(torch.nn.Module):
     """tlx.layers.Linear: y = x @ W (+ b), W stored [in_features, out_features]."""
 
-    def __init__(self, in_features, out_features, bias=False):
+    def __init__(self, in_features, out_features, bias=False, tensor_core=None):
         super().__init__()
+        self.tensor_core = tensor_core
         w = torch.empty(in_features, out_features)
         bound = math.sqrt(6.0 / (in_features + out_features))  # xavier_uniform
         torch.nn.init.uniform_(w, -bound, bound)
@@ -42,6 +49,9 @@ class Linear(torch.nn.Module):
         self.biases = torch.nn.Parameter(torch.zeros(out_features)) if bias else None
 
     def forward(self, x):
+        tc = self.tensor_core if self.tensor_core is not None else LAYER_LINEAR == 'tc'
+        if tc and x.is_cuda and x.dim() == 2 and mpops.linear_tc_supported(x, self.weights):
+            return mpops.linear_tc(x, self.weights, self.biases)
         y = x @ self.weights
         return y if self.biases is None else y + self.biases
 

@@ -89,3 +89,26 @@ def test_gcn_conv_aggregate_first_runs_the_tensor_core_gemm():
     od.square().sum().backward()
     assert rel(out, od) < 1e-5
     assert rel(xx.grad, xd.grad) < 1e-5
+
+
+def test_layer_linear_on_tensor_cores_and_its_input_gradient():
+    """layers.Linear(tensor_core=True): forward and input gradient on the tcgen05 kernel (GGLB200_LINEAR_BWD=tc), weight / bias
+    gradients from the library GEMM -- all within 1e-5 of fp64; unsupported shapes (47 classes) fall back to torch.matmul."""
+    from gammagl_b200.layers import Linear
+    g = torch.Generator().manual_seed(2)
+    M = 5000
+    for fin, fout in ((256, 100), (128, 128), (256, 47)):
+        lin = Linear(fin, fout, bias=True, tensor_core=True).to(DEV)
+        with torch.no_grad():
+            lin.biases.copy_(torch.randn(fout, generator=g))
+        x = torch.randn(M, fin, generator=g)
+        go = torch.randn(M, fout, generator=g)
+        xx = x.to(DEV).requires_grad_(True)
+        out = lin(xx)
+        out.backward(go.to(DEV))
+        xd = x.double().requires_grad_(True)
+        W, b = lin.weights.detach().double().cpu().requires_grad_(True), lin.biases.detach().double().cpu().requires_grad_(True)
+        od = xd @ W + b
+        od.backward(go.double())
+        assert rel(out, od) < 1e-5 and rel(xx.grad, xd.grad) < 1e-5
+        assert rel(lin.weights.grad, W.grad) < 1e-5 and rel(lin.biases.grad, b.grad) < 1e-5
