@@ -30,10 +30,11 @@ from .csr import derived_of, segment_csr_of
 _EPILOGUE = os.environ.get('GGLB200_EPILOGUE', '1') != '0'   # 0: bias / activation as separate torch ops (same results)
 
 
-# 'tc': every mirrored Linear whose shape the tcgen05 kernel supports (fp32, in / out features multiples of 4 up to 256) runs
-# mpops.linear_tc (3xTF32 on the tensor cores, 1.3e-6 vs fp64; C3 100 -> 256: 0.93 ms vs 2.95 ms for the library GEMM) in forward and
-# input-gradient; 'lib' (default) keeps torch.matmul.  Per layer: Linear(..., tensor_core=True).
-LAYER_LINEAR = os.environ.get('GGLB200_LAYER_LINEAR', 'lib')
+# 'tc' (default): every mirrored Linear whose shape the tcgen05 kernel supports (CUDA fp32, in / out features multiples of 4 up to
+# 256) runs mpops.linear_tc (3xTF32 on the tensor cores, 1.3e-6 vs fp64 -- inside the 1e-5 fp32 tolerance; C3 100 -> 256: 0.93 ms vs
+# 2.95 ms for the library GEMM) in forward and input gradient; other shapes and 'lib' use torch.matmul.  Per layer:
+# Linear(..., tensor_core=True / False).
+LAYER_LINEAR = os.environ.get('GGLB200_LAYER_LINEAR', 'tc')
 
 
 class Linear(torch.nn.Module):
@@ -50,7 +51,7 @@ class Linear(torch.nn.Module):
 
     def forward(self, x):
         tc = self.tensor_core if self.tensor_core is not None else LAYER_LINEAR == 'tc'
-        if tc and x.is_cuda and x.dim() == 2 and mpops.linear_tc_supported(x, self.weights):
+        if tc and x.is_cuda and x.dim() == 2 and x.shape[0] > 0 and mpops.linear_tc_supported(x, self.weights):
             return mpops.linear_tc(x, self.weights, self.biases)
         y = x @ self.weights
         return y if self.biases is None else y + self.biases
