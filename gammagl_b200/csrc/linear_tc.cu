@@ -532,9 +532,13 @@ __global__ void __launch_bounds__(352, 1) linear_ws_kernel(const float* __restri
             if (wide) {
               asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(orow + j), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
                            "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
-            } else {
+            } else if ((N & 3) == 0) {
               __stcs(reinterpret_cast<float4*>(orow + j), make_float4(o[0], o[1], o[2], o[3]));
               if (col + j + 4 < N) __stcs(reinterpret_cast<float4*>(orow + j + 4), make_float4(o[4], o[5], o[6], o[7]));
+            } else {   // N not a multiple of 4 (47 classes ...): rows are only 4-byte aligned
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (col + j + i < N) __stcs(orow + j + i, o[i]);
             }
           }
         }
@@ -577,7 +581,7 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
   if (M == 0) return GGL_OK;
   GGL_REQUIRE(A && W && out, GGL_EINVAL, "linear: NULL pointer");
   GGL_REQUIRE(K % 4 == 0 && K <= 256, GGL_EUNSUPPORTED, "linear: K = %lld (supported: multiples of 4 up to 256)", (long long)K);
-  GGL_REQUIRE(N % 4 == 0 && N <= 256, GGL_EUNSUPPORTED, "linear: N = %lld (supported: multiples of 4 up to 256)", (long long)N);
+  GGL_REQUIRE(N <= 256, GGL_EUNSUPPORTED, "linear: N = %lld (supported: up to 256)", (long long)N);
   GGL_REQUIRE((((uintptr_t)A | (uintptr_t)out | (uintptr_t)bias) & 15) == 0, GGL_EUNSUPPORTED, "linear: 16-byte aligned A / out / bias");
   GGL_REQUIRE((M + kBM - 1) / kBM < INT32_MAX, GGL_ERANGE, "linear: M too large");
   GGL_REQUIRE(workspace != nullptr && workspace_bytes >= gglb200_linear_workspace_bytes(K, N), GGL_EWORKSPACE,
@@ -592,7 +596,7 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   const unsigned grid = (unsigned)((M + kBM - 1) / kBM);
   const char* form = getenv("GGLB200_LINEAR");   // "ws" (default): warp-specialised persistent kernel; "tile": one CTA per tile
-  const bool ws = !(form && form[0] == 't');
+  const bool ws = !(form && form[0] == 't') || (N % 4 != 0);   // the one-tile form stores 16-byte vectors only
   const unsigned grid_ws = (unsigned)((int64_t)grid < (int64_t)sm_count() ? grid : sm_count());
   const char* stage_env = getenv("GGLB200_LINEAR_STAGE");   // "0": keep the per-thread loads even where the staged form applies
   const bool no_stage = stage_env && stage_env[0] == '0';

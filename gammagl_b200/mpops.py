@@ -669,11 +669,11 @@ class _LinearTC(torch.autograd.Function):
 
 def linear_tc_supported(a, w):
     return (a.is_cuda and a.dtype == torch.float32 and w.dtype == torch.float32 and a.dim() == 2 and w.dim() == 2
-            and a.shape[1] == w.shape[0] and a.shape[1] % 4 == 0 and a.shape[1] <= 256 and w.shape[1] % 4 == 0 and w.shape[1] <= 256)
+            and a.shape[1] == w.shape[0] and a.shape[1] % 4 == 0 and a.shape[1] <= 256 and 0 < w.shape[1] <= 256)
 
 
 def linear_tc(a, w, bias=None, relu=False):
-    """act(a @ w + bias) for a [M, K <= 256] fp32, w [K, N <= 256] fp32 (K, N multiples of 4) on the tcgen05 tensor cores at fp32
+    """act(a @ w + bias) for a [M, K <= 256] fp32 (K a multiple of 4), w [K, N <= 256] fp32 on the tcgen05 tensor cores at fp32
     accuracy; raises for other shapes (see linear_tc_supported)."""
     require_cuda(a, 'a')
     require_cuda(w, 'w')

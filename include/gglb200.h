@@ -241,7 +241,7 @@ GGL_API int gglb200_sample_pick(const int64_t* rowptr, const int64_t* col, const
  * The dense feature x weight GEMM next to the aggregation, on the tcgen05 tensor cores with a TMEM accumulator:
  *   out[M,N] = act(A[M,K] @ W[K,N] + bias[N]),  fp32 in / out, act = ReLU when relu != 0, bias may be NULL.
  * The Linear of GCNConv / SAGEConv / GINConv (layers/conv/gcn_conv.py:79,104-106, sage_conv.py:80, gin_conv.py:57) applied to
- * aggregated rows (K = F_in <= 256, a multiple of 4; N <= 256, a multiple of 4).  fp32-accurate on TF32 tensor cores by
+ * aggregated rows (K = F_in <= 256, a multiple of 4; N <= 256, any width).  fp32-accurate on TF32 tensor cores by
  * operand splitting (3xTF32: a_hi.w_hi + a_hi.w_lo + a_lo.w_hi), ~1e-6 relative.  Other shapes: GGL_EUNSUPPORTED (the
  * host side then uses the library GEMM).
  * ------------------------------------------------------------------------------------------- */

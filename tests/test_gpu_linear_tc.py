@@ -16,7 +16,8 @@ def rel(a, b):
 
 @pytest.mark.parametrize('M,K,N', [(1000, 100, 256), (333, 128, 64), (128, 4, 4), (5000, 36, 100), (129, 64, 192), (77, 8, 16),
                                    (4096, 104, 128), (1, 100, 256),
-                                   (700, 256, 64), (513, 200, 128), (300, 132, 256)])     # K > 128: three / four K passes
+                                   (700, 256, 64), (513, 200, 128), (300, 132, 256),      # K > 128: three / four K passes
+                                   (1000, 256, 47), (77, 8, 3), (260, 100, 130)])         # N not a multiple of 4 (class counts)
 @pytest.mark.parametrize('bias,relu', [(False, False), (True, True)])
 def test_linear_tc_matches_fp64(M, K, N, bias, relu):
     from gammagl_b200 import mpops
@@ -93,7 +94,8 @@ def test_gcn_conv_aggregate_first_runs_the_tensor_core_gemm():
 
 def test_layer_linear_on_tensor_cores_and_its_input_gradient():
     """layers.Linear(tensor_core=True): forward and input gradient on the tcgen05 kernel (GGLB200_LINEAR_BWD=tc), weight / bias
-    gradients from the library GEMM -- all within 1e-5 of fp64; unsupported shapes (47 classes) fall back to torch.matmul."""
+    gradients from the library GEMM -- all within 1e-5 of fp64; 47 output classes run the scalar-store epilogue, their input
+    gradient (K = 47, not a multiple of 4) falls back to torch.matmul."""
     from gammagl_b200.layers import Linear
     g = torch.Generator().manual_seed(2)
     M = 5000
