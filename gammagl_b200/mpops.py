@@ -43,6 +43,9 @@ def _dtype_code(t):
         raise _lib.GglError('unsupported dtype %s' % t.dtype)
 
 
+_PAD_ODD_K = os.environ.get('GGLB200_PAD_ODD_K', '1') != '0'
+
+
 def spmm_csr(csr, col, x2d, reduce, w=None, wperm=None, heads=1, want_arg=False, arg_empty=0, n_rows=None, out_scale=None,
              bias=None, relu=False):
     """Launch the aggregation kernel family on a Csr.  x2d: [n_src, K] contiguous.  Returns (out, arg)."""
@@ -50,6 +53,17 @@ def spmm_csr(csr, col, x2d, reduce, w=None, wperm=None, heads=1, want_arg=False,
     n_rows = csr.n_rows if n_rows is None else n_rows
     K = x2d.shape[1]
     dev = x2d.device
+    if _PAD_ODD_K and heads == 1 and K > 4 and K % 4 != 0 and x2d.dtype == torch.float32 and 4 * x2d.shape[0] <= csr.E:
+        # fp32 rows that are not a multiple of 16 bytes (47 classes: 188 B) run one element per lane: 14.4 ms per pass at C3 against
+        # 4 ms for K = 48.  Gathered feature matrices are small next to the edge stream, so the rows are padded to the next
+        # multiple of 4 columns (one copy of x), aggregated with 16-byte lanes and sliced back: columns are independent, results
+        # are bit-identical.  (Segment operators reduce [E, K] messages: padding those would cost more than it saves.)
+        pad = (-K) % 4
+        xp = torch.nn.functional.pad(x2d, (0, pad))
+        bp = None if bias is None else torch.nn.functional.pad(bias.reshape(-1), (0, pad))
+        outp, argp = spmm_csr(csr, col, xp, reduce, w=w, wperm=wperm, heads=1, want_arg=want_arg, arg_empty=arg_empty, n_rows=n_rows,
+                              out_scale=out_scale, bias=bp, relu=relu)
+        return outp[:, :K].contiguous(), (None if argp is None else argp[:, :K].contiguous())
     with torch.cuda.device(dev):
         _lib.tune_device(dev.index)
         csr.use_on_current_stream()        # a CSR built on another stream: order this stream after its build
@@ -575,7 +589,7 @@ class _GcnPropagate(torch.autograd.Function):
         grad = grad_out.contiguous().view(g.N, -1)
         if ctx.relu:
             (out,) = ctx.saved_tensors
-            grad = grad * (out > 0).to(grad.dtype)
+            grad = torch.ops.aten.threshold_backward(grad, out.view_as(grad), 0.0)   # one pass: grad where out > 0, else 0
         gbias = None
         if ctx.bias_shape is not None:
             gbias = grad.sum(dim=0, dtype=torch.float32).to(ctx.bias_dtype).reshape(ctx.bias_shape)
@@ -654,7 +668,7 @@ class _LinearTC(torch.autograd.Function):
         a, w, out = ctx.saved_tensors
         g = g.contiguous()
         if ctx.relu:
-            g = g * (out > 0).to(g.dtype)
+            g = torch.ops.aten.threshold_backward(g, out, 0.0)   # one pass: g where out > 0, else 0
         ga = None
         if ctx.needs_input_grad[0]:
             wt = w.t()

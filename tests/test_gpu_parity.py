@@ -174,6 +174,29 @@ def test_gspmm_vs_oracle(mp, N, E, K, hub):
             assert rel_err(ggot, gref) < 1e-5, op
 
 
+def test_odd_feature_widths_padded_and_unpadded_agree_bitwise(mp, monkeypatch):
+    """fp32 rows that are not a multiple of 16 bytes (47 classes) are padded to 48 columns on the host side of the aggregation
+    (16-byte lanes instead of one element per lane); columns are independent, so both forms must agree bit for bit -- values,
+    arg-max indices and gradients."""
+    N, E, K = 2500, 40000, 47
+    index = make_graph(N, E, seed=3, hub=2000).to(DEV)
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(N, K, generator=g).to(DEV)
+    w = (torch.rand(E, generator=g) + 0.05).to(DEV)
+    gout = torch.randn(N, K, generator=g).to(DEV)
+    res = {}
+    for pad in (True, False):
+        monkeypatch.setattr(mp, '_PAD_ODD_K', pad)
+        for op in ('sum', 'mean', 'max'):
+            xx = x.clone().requires_grad_(True)
+            out = mp.gspmm(index, w, xx, op)
+            out.backward(gout)
+            res[(pad, op)] = (out.detach(), xx.grad)
+    for op in ('sum', 'mean', 'max'):
+        assert torch.equal(res[(True, op)][0], res[(False, op)][0]), op
+        assert torch.equal(res[(True, op)][1], res[(False, op)][1]), op
+
+
 @pytest.mark.parametrize('E,N,K,hub', [(1 << 16, 1 << 12, 100, 0), (50000, 3000, 33, 4000), (20000, 500, 4, 3000),
                                         (30000, 2500, 1, 0), (9000, 300, 130, 0)])
 def test_segment_ops_vs_oracle(mp, E, N, K, hub):
