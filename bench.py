@@ -673,6 +673,7 @@ def run_partitioned(torch, dist, dev, world, rank, args, ei_global_fn):
             # propagate over the partition -> ReLU, three times, forward + backward through autograd
             gcn3 = None
             try:
+                from gammagl_b200 import mpops as mpops_
                 Ws = [torch.nn.Parameter(torch.randn(K5, K5, generator=g, device=dev) * (K5 ** -0.5)) for _ in range(3)]
 
                 def gcn3_step():
@@ -681,7 +682,7 @@ def run_partitioned(torch, dist, dev, world, rank, args, ei_global_fn):
                         w_.grad = None
                     h = x
                     for li, w_ in enumerate(Ws):
-                        h = P.peer_gcn_propagate(graph, h @ w_, 'both')
+                        h = P.peer_gcn_propagate(graph, mpops_.linear_tc(h, w_), 'both')   # tcgen05 Linear (forward + input gradient)
                         if li < 2:
                             h = torch.relu(h)
                     h.backward(gout)
@@ -698,7 +699,7 @@ def run_partitioned(torch, dist, dev, world, rank, args, ei_global_fn):
                 torch.cuda.synchronize()
                 t3 = torch.tensor([a3.elapsed_time(b3) / s5], device=dev)
                 dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-                gcn3 = {'model': 'GCN, 3 layers, hidden 128 (Linear -> partitioned normalised propagate -> ReLU), forward + backward',
+                gcn3 = {'model': 'GCN, 3 layers, hidden 128 (tcgen05 Linear -> partitioned normalised propagate -> ReLU), forward + backward',
                         'ms_per_step': float(t3.item()), 'edge_passes_per_step': 6,
                         'value': world * 6 * Eg / (float(t3.item()) * 1e-3), 'unit': 'edges/s'}
                 del Ws

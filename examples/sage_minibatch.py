@@ -17,14 +17,23 @@ from gammagl_b200.sampler import NeighborSampler  # noqa: E402
 
 
 class SAGE(torch.nn.Module):                      # gammagl/models/graphsage.py: two SAGEConv layers over the sampled blocks
-    def __init__(self, f_in, hidden, classes):
+    def __init__(self, f_in, hidden, classes, fuse_gather=False):
         super().__init__()
-        self.convs = torch.nn.ModuleList([SAGEConv(f_in, hidden, aggr='mean'), SAGEConv(hidden, classes, aggr='mean')])
+        self.fuse_gather = fuse_gather
+        self.convs = torch.nn.ModuleList([SAGEConv(f_in, hidden, aggr='mean', aggregate_first=fuse_gather),
+                                          SAGEConv(hidden, classes, aggr='mean')])
 
-    def forward(self, x, adjs):
+    def forward(self, x, adjs, n_id=None):
+        """fuse_gather: `x` is the FULL feature matrix; the first block is aggregated straight from it through global source ids
+        (n_id[src_local]) and the neighbour Linear runs on the n_dst aggregated rows -- no x[n_id] gather of the n_src sampled rows,
+        no Linear over them.  Otherwise `x` = x_full[n_id] as in the reference example."""
         for i, adj in enumerate(adjs):
             n_src, n_dst = adj.size
-            x = self.convs[i]((x, x[:n_dst]), adj.edge_index)
+            if i == 0 and self.fuse_gather:
+                ei = torch.stack([n_id[adj.edge_index[0]], adj.edge_index[1]])
+                x = self.convs[0]((x, x[n_id[:n_dst]]), ei)
+            else:
+                x = self.convs[i]((x, x[:n_dst]), adj.edge_index)
             if i + 1 < len(adjs):
                 x = torch.relu(x)
         return x
@@ -37,6 +46,7 @@ def main():
     ap.add_argument('--feat', type=int, default=100)
     ap.add_argument('--batch', type=int, default=1024)
     ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--fuse-gather', action='store_true', help='aggregate the first block straight from the full feature matrix')
     a = ap.parse_args()
     dev = torch.device('cuda', 0)
     g = torch.Generator(device=dev).manual_seed(0)
@@ -44,7 +54,7 @@ def main():
     y = torch.randint(0, 47, (a.nodes,), generator=g, device=dev)
     x = torch.randn(a.nodes, a.feat, generator=g, device=dev) + torch.nn.functional.one_hot(y, 47).float() @ torch.randn(47, a.feat, generator=g, device=dev)
     sampler = NeighborSampler(ei, [25, 10], num_nodes=a.nodes, seed=0)
-    net = SAGE(a.feat, 256, 47).to(dev)
+    net = SAGE(a.feat, 256, 47, fuse_gather=a.fuse_gather).to(dev)
     opt = torch.optim.Adam(net.parameters(), lr=3e-3)
     perm = torch.randperm(a.nodes, generator=g, device=dev)
     torch.cuda.synchronize()
@@ -53,7 +63,7 @@ def main():
         batch = perm[(step * a.batch) % (a.nodes - a.batch):][:a.batch]
         bs, n_id, adjs = sampler.sample(batch)
         opt.zero_grad(set_to_none=True)
-        out = net(x[n_id], adjs)
+        out = net(x, adjs, n_id) if a.fuse_gather else net(x[n_id], adjs)
         loss = torch.nn.functional.cross_entropy(out, y[batch])
         loss.backward()
         opt.step()

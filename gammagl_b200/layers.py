@@ -210,9 +210,14 @@ class GCNConv(MessagePassing):
 
 
 class SAGEConv(MessagePassing):
-    def __init__(self, in_channels, out_channels, activation=None, aggr='mean', add_bias=True, fused=True, fold_norm=True):
+    def __init__(self, in_channels, out_channels, activation=None, aggr='mean', add_bias=True, fused=True, fold_norm=True,
+                 aggregate_first=False):
         super().__init__(fused)
         self.fold_norm = fold_norm
+        # aggr='mean' only: mean(W x_j) = W mean(x_j), so the neighbour Linear can run on the n_dst aggregated rows instead of the
+        # n_src source rows -- in a sampled block n_src is 10-25x n_dst, and `src_feat` may then be the FULL feature matrix with
+        # global source ids in the edge list: the x[n_id] gather disappears into the aggregation kernel (examples/sage_minibatch.py).
+        self.aggregate_first = aggregate_first
         if aggr not in ('mean', 'gcn', 'pool'):
             raise NotImplementedError("aggr '%s' (lstm) is outside the aggregation path" % aggr)
         self.aggr, self.act, self.in_feat = aggr, activation, in_channels
@@ -227,7 +232,9 @@ class SAGEConv(MessagePassing):
     def forward(self, feat, edge):
         src_feat, dst_feat = feat if isinstance(feat, tuple) else (feat, feat)
         num_nodes = int(dst_feat.shape[0])
-        if self.aggr == 'mean':                                             # sage_conv.py:79-81
+        if self.aggr == 'mean' and self.aggregate_first:
+            out = self.fc_neigh(self.propagate(src_feat, edge, edge_weight=None, num_nodes=num_nodes, aggr='mean'))
+        elif self.aggr == 'mean':                                           # sage_conv.py:79-81
             src_feat = self.fc_neigh(src_feat)
             out = self.propagate(src_feat, edge, edge_weight=None, num_nodes=num_nodes, aggr='mean')
         elif self.aggr == 'gcn':                                            # sage_conv.py:82-88
