@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256, 2) linear_tf32x3_kernel(const float* __re
 //              core already multiplies the next tile.
 // Barrier phases are derived from running counters (slice q, block i, tile it); every thread of a role waits every phase of its
 // barriers in order; the FIRST wait on an `empty` barrier uses the inverted parity and passes at once.
-constexpr int kWsRingMax = 4;   // W ring depth: 2 .. 4 slots (GGLB200_LINEAR_RING, default 2: a smaller shared-memory carve-out leaves the A producers more L1)
+constexpr int kWsRingMax = 6;   // W ring depth: 2 .. 6 slots (GGLB200_LINEAR_RING; default 2 for 56-column passes, 5 for the 32-column plan)
 template <int KC>
 __global__ void __launch_bounds__(352, 1) linear_ws_kernel(const float* __restrict__ A, const float* __restrict__ wc,
                                                            const float* __restrict__ bias, const int relu, float* __restrict__ out,
@@ -395,24 +395,28 @@ __global__ void __launch_bounds__(352, 1) linear_ws_kernel(const float* __restri
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(A_FULL + 8 * buf) : "memory");
     };
     if (staged) {
-      // Staged form (k_passes <= 2): the whole fp32 tile -- 128 consecutive rows = ONE contiguous piece of global memory -- arrives by a
+      // Staged form (k_passes <= 2, or <= 4 with 32-column passes): the whole fp32 tile -- 128 consecutive rows = ONE contiguous piece of global memory -- arrives by a
       // single bulk async copy (warp 10); a thread takes its row into registers, hands the staging buffer back at once (the next
       // tile's copy overlaps this tile's split / store / MMA) and then feeds the slice ring from registers.  No L1, no per-thread
       // 16-byte requests: the loads were the limit of the form below (8 k cycles per 28 KB slice in flight).
-      float4 v0[KC], v1[KC];
+      constexpr int PMAX = KC <= 8 ? 4 : 2;   // passes whose slices a thread keeps in registers (32-column plan: up to 4 x 8 chunks)
+      float4 v[PMAX][KC];
       for (int it = 0; it < my_tiles; ++it) {
         const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kBM + r;
         mbar_wait_parity(RAW_FULL, (uint32_t)it & 1u);
         const unsigned char* rrow = raw + (size_t)r * (size_t)K * 4;
 #pragma unroll
-        for (int kc = 0; kc < KC; ++kc) {
-          const int k0 = kc * 4, k1 = (KC + kc) * 4;
-          v0[kc] = (row < M && k0 < K) ? *reinterpret_cast<const float4*>(rrow + k0 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v1[kc] = (row < M && k1 < K && k_passes > 1) ? *reinterpret_cast<const float4*>(rrow + k1 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int pp = 0; pp < PMAX; ++pp) {
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc) {
+            const int k = (pp * KC + kc) * 4;
+            v[pp][kc] = (row < M && k < K && pp < k_passes) ? *reinterpret_cast<const float4*>(rrow + k * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(RAW_EMPTY) : "memory");   // row is in registers
-        store_slice(v0, it * k_passes);
-        if (k_passes > 1) store_slice(v1, it * k_passes + 1);
+#pragma unroll
+        for (int pp = 0; pp < PMAX; ++pp)
+          if (pp < k_passes) store_slice(v[pp], it * k_passes + pp);
       }
     } else {
     float4 va[KC], vb[KC];
@@ -556,6 +560,16 @@ __global__ void __launch_bounds__(352, 1) linear_ws_kernel(const float* __restri
 
 using namespace ggl;
 
+// 32-column plan of the warp-specialised kernel (K <= 128): passes of 8 chunks keep the A ring at 64 KB, which buys a 5-slot W ring
+// (16 KB blocks) next to the staged tile -- the copy latency of a W block (~2.3 k cycles) is then covered by four blocks in flight.
+static bool linear_plan_deep(int64_t K, int* k_passes, int* kc) {
+  const int chunks = (int)((K + 3) / 4);
+  if (chunks > 32) return false;
+  *k_passes = (chunks + 7) / 8;
+  int c = (chunks + *k_passes - 1) / *k_passes;
+  *kc = (c + 1) & ~1;
+  return true;
+}
 static void linear_plan(int64_t K, int* k_passes, int* kc) {
   // K passes: slices of at most 14 sixteen-byte chunks (56 columns), even, as equal as possible -- 112 KB of shared memory per CTA
   const int chunks = (int)((K + 3) / 4);
@@ -571,7 +585,12 @@ extern "C" size_t gglb200_linear_workspace_bytes(int64_t K, int64_t N) {
   linear_plan(K, &k_passes, &kc);
   const int KC = linear_kc_class(kc);
   const int64_t n_chunks = (N + kNC - 1) / kNC;
-  return (size_t)k_passes * n_chunks * 2 * KC * kNC * 16 + 256;
+  size_t bytes = (size_t)k_passes * n_chunks * 2 * KC * kNC * 16;
+  if (linear_plan_deep(K, &k_passes, &kc)) {   // whichever plan the launch picks must fit
+    const size_t deep = (size_t)k_passes * n_chunks * 2 * linear_kc_class(kc) * kNC * 16;
+    if (deep > bytes) bytes = deep;
+  }
+  return bytes + 256;
 }
 
 extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float* bias, int relu, float* out, int64_t M, int64_t K,
@@ -601,7 +620,19 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
   const char* stage_env = getenv("GGLB200_LINEAR_STAGE");   // "0": keep the per-thread loads even where the staged form applies
   const bool no_stage = stage_env && stage_env[0] == '0';
   const char* ring_env = getenv("GGLB200_LINEAR_RING");
-  const int ring = (ring_env && atoi(ring_env) >= 2 && atoi(ring_env) <= kWsRingMax) ? atoi(ring_env) : 2;
+  int ring = (ring_env && atoi(ring_env) >= 2 && atoi(ring_env) <= kWsRingMax) ? atoi(ring_env) : 2;
+  // GGLB200_LINEAR_PLAN=deep: 32-column passes + 5-slot W ring for the staged warp-specialised form (K <= 128)
+  const char* plan_env = getenv("GGLB200_LINEAR_PLAN");
+  bool deep = false;
+  if (ws && !no_stage && plan_env && plan_env[0] == 'd') {
+    int kp2, kc2;
+    if (linear_plan_deep(K, &kp2, &kc2) && kc2 <= 8) {
+      k_passes = kp2;
+      kc = kc2;
+      deep = true;
+      if (!ring_env) ring = 5;
+    }
+  }
 #define GGL_LIN(KC_)                                                                                                        \
   do {                                                                                                                      \
     const int64_t items = (int64_t)k_passes * n_chunks * KC_ * kNC;                                                         \
@@ -610,7 +641,8 @@ extern "C" int gglb200_linear_tf32x3(const float* A, const float* W, const float
     GGL_LAUNCHED("linear_prep_w");                                                                                          \
     if (ws) {                                                                                                               \
       const size_t smem_ring = (size_t)4 * KC_ * kBM * 16 + (size_t)ring * 2 * KC_ * kNC * 16;                             \
-      const int staged = (!no_stage && k_passes <= 2 && smem_ring + (size_t)kBM * K * 4 + 2048 <= 232448) ? 1 : 0;          \
+      const int staged = (!no_stage && k_passes <= ((deep && KC_ <= 8) ? 4 : 2) &&                                          \
+                          smem_ring + (size_t)kBM * K * 4 + 2048 <= 232448) ? 1 : 0;                                       \
       const size_t smem_ws = smem_ring + (staged ? (size_t)kBM * K * 4 : 0);                                                 \
       GGL_CUDA(cudaFuncSetAttribute(linear_ws_kernel<KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));     \
       linear_ws_kernel<KC_><<<grid_ws, 352, smem_ws, stream>>>(A, wc, bias, relu, out, M, (int32_t)K, (int32_t)N, k_passes,  \

@@ -92,8 +92,9 @@ def test_new_entry_points_validate_without_gpu():
 def test_round2_entry_points_validate_without_gpu():
     """tcgen05 Linear / sort-free reduce / sampler: size queries are host arithmetic, argument errors return before any launch."""
     lib = _lib.load()
-    # K = 100 -> 25 sixteen-byte chunks -> 2 passes of 14; N = 256 -> 4 chunks of 64 columns; [W_hi | W_lo] tile pairs + alignment slack
-    assert lib.gglb200_linear_workspace_bytes(100, 256) == 2 * 4 * 2 * 14 * 64 * 16 + 256
+    # K = 100 -> 25 sixteen-byte chunks -> 2 passes of 14 (or 4 passes of 8 in the 32-column plan: the larger of the two is reserved);
+    # N = 256 -> 4 chunks of 64 columns; [W_hi | W_lo] tile pairs + alignment slack
+    assert lib.gglb200_linear_workspace_bytes(100, 256) == max(2 * 4 * 2 * 14 * 64 * 16, 4 * 4 * 2 * 8 * 64 * 16) + 256
     assert lib.gglb200_linear_workspace_bytes(8, 16) == 1 * 1 * 2 * 4 * 64 * 16 + 256
     assert lib.gglb200_linear_workspace_bytes(0, 16) == 0
     assert lib.gglb200_linear_tf32x3(None, None, None, 0, None, 0, 8, 8, None, 0, None) == 0        # M == 0: nothing to do
