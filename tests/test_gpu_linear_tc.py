@@ -114,3 +114,26 @@ def test_layer_linear_on_tensor_cores_and_its_input_gradient():
         od.backward(go.double())
         assert rel(out, od) < 1e-5 and rel(xx.grad, xd.grad) < 1e-5
         assert rel(lin.weights.grad, W.grad) < 1e-5 and rel(lin.biases.grad, b.grad) < 1e-5
+
+
+@pytest.mark.parametrize('env', [{'GGLB200_LINEAR': 'tile'}, {'GGLB200_LINEAR_STAGE': '0'}, {'GGLB200_LINEAR_PLAN': 'deep'},
+                                 {'GGLB200_LINEAR_RING': '4', 'GGLB200_LINEAR_STAGE': '0'}],
+                         ids=['one_tile_per_cta', 'per_thread_a_loads', 'plan_32_column_passes', 'ring4'])
+@pytest.mark.parametrize('M,K,N', [(1000, 100, 256), (513, 200, 128), (129, 64, 192), (77, 8, 16)])
+def test_linear_tc_alternative_forms(M, K, N, env, monkeypatch):
+    """The switches of the tcgen05 Linear (read per call by the library): one CTA per tile, per-thread A loads instead of the staged
+    tile, the 32-column plan, a deeper W ring -- every form must give the same answer as the default to the last bit of the 3xTF32
+    scheme (same products, same accumulation order per output element) and stay within 1e-5 of fp64."""
+    from gammagl_b200 import mpops
+    g = torch.Generator().manual_seed(M * 7 + K + N)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(K, N, generator=g) * 0.3).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    ref = torch.relu(a.double() @ w.double() + b.double())
+    base = mpops.linear_tc(a, w, b, True)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = mpops.linear_tc(a, w, b, True)
+    assert rel(alt, ref) < 1e-5 and rel(base, ref) < 1e-5
+    if 'GGLB200_LINEAR_PLAN' not in env:          # the 32-column plan splits K differently: other partial-sum order
+        assert torch.equal(alt, base)
