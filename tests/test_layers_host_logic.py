@@ -218,3 +218,39 @@ def test_routing_of_propagate(host):
     finally:
         for k, f in real.items():
             setattr(mpops, k, f)
+
+
+def test_sage_mean_aggregate_first_matches_reference_order(host):
+    """SAGEConv(aggr='mean', aggregate_first=True): the neighbour Linear after the mean (n_dst rows) instead of before it (n_src rows),
+    homogeneous call and bipartite block with the FULL feature matrix + global source ids -- same output and parameter gradients."""
+    g = torch.Generator().manual_seed(3)
+    N, n_src, n_dst, E, F, H = 60, 25, 7, 90, 6, 5
+    x = torch.randn(N, F, generator=g)
+    n_id = torch.randperm(N, generator=g)[:n_src]
+    src, dst = torch.randint(0, n_src, (E,), generator=g), torch.randint(0, n_dst, (E,), generator=g)
+    torch.manual_seed(0)
+    a = L.SAGEConv(F, H, aggr='mean')
+    b = L.SAGEConv(F, H, aggr='mean', aggregate_first=True)
+    b.load_state_dict(a.state_dict())
+    xs = x[n_id]
+    ref = a((xs, xs[:n_dst]), torch.stack([src, dst]))
+    got = b((x, x[n_id[:n_dst]]), torch.stack([n_id[src], dst]))
+    assert ref.shape == got.shape == (n_dst, H) and rel(got, ref.detach().numpy()) < 1e-5
+    go = torch.randn(n_dst, H, generator=g)
+    ref.backward(go); got.backward(go)
+    for (na, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert rel(pb.grad, pa.grad.numpy()) < 1e-5, na
+    ei = torch.stack([torch.randint(0, N, (200,), generator=g), torch.randint(0, N, (200,), generator=g)])
+    assert rel(b(x, ei), a(x, ei).detach().numpy()) < 1e-5
+
+
+def test_sage_gcn_self_loop_list_is_derived_once(host):
+    """The self-looped edge list of SAGEConv(aggr='gcn') is memoised per edge_index (csr.derived_of) only for CUDA tensors; on the CPU
+    every call derives it afresh -- and both the folded and the literal form give the reference's numbers (fixture test above)."""
+    from gammagl_b200 import csr
+    csr.clear_caches()
+    layer = L.SAGEConv(4, 3, aggr='gcn')
+    ei = torch.tensor([[0, 1, 2, 3], [1, 2, 3, 0]])
+    x = torch.randn(4, 4)
+    a, b = layer(x, ei), layer(x, ei)
+    assert torch.equal(a, b) and len(csr._derived.d) == 0
