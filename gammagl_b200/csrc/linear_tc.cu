@@ -88,8 +88,21 @@ __device__ __forceinline__ bool elect_one() {   // one lane of a fully active wa
 }
 
 __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
-  asm volatile("{\n\t.reg .pred p;\n\tLW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LD;\n\tbra LW;\n\tLD:\n\t}"
-               ::"r"(bar), "r"(parity) : "memory");
+  // Bounded: a hand-off that never arrives (a protocol error) must end the launch with an error, not hang the GPU.  Every 4096
+  // polls the global nanosecond timer is read; 10 s without progress -> trap.
+  uint64_t t0 = 0;
+  for (uint32_t spins = 1;; ++spins) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if ((spins & 4095u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 10000000000ull) __trap();
+    }
+  }
 }
 
 // KC = 16-byte K chunks per K PASS (even, <= 14: one MMA K step = 2 chunks).  K is covered by k_passes passes, each re-staging its slice
